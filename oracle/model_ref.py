@@ -1,0 +1,290 @@
+"""torch restatement of the reference's Shift-GCN modules (TEST INFRASTRUCTURE ONLY).
+
+Each class restates one reference class of model/shift_gcn.py with plain torch ops, keeps the
+reference's attribute names (so state_dicts are interchangeable) and takes the
+temporal shift from oracle/shift_torch.py.  It runs on CPU (fp32 or fp64) as the parity checker and
+as bench.py's ``cpu_baseline`` / ``--impl reference`` arm; /root/reference cannot travel to the GPU
+box, this file can.
+
+Pinned against the real reference (imported through oracle/ref_import.py) by
+tests/test_oracle_vs_reference.py and by the committed fixtures in tests/golden/.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .shift_torch import OracleShift
+
+
+# --------------------------------------------------------------------------- TF32 emulation (checker only)
+# The product contracts on tcgen05 tensor cores with TF32 operands (10-bit mantissa, round-to-nearest ties away,
+# fp32 accumulate).  With TF32_EMULATION on, the oracle rounds the SAME operands the kernels round (forward,
+# backward-data and weight-gradient contractions), so kernel bugs are separated from TF32 rounding: the CUDA
+# path must match the emulating oracle to ~1e-5 and the exact oracle to the 1e-2 the north star allows for TF32.
+TF32_EMULATION = False
+
+
+def tf32_round(t):
+    """cvt.rna.tf32.f32: keep 10 mantissa bits, round to nearest, ties away from zero"""
+    f = t.detach().to(torch.float32).contiguous()
+    bits = f.view(torch.int32)
+    rounded = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    return rounded.to(t.dtype)
+
+
+class _Tf32Matmul(torch.autograd.Function):
+    """y = a @ w with TF32-rounded operands in all three contractions (fwd, dgrad, wgrad)."""
+
+    @staticmethod
+    def forward(ctx, a, w):
+        ctx.save_for_backward(a, w)
+        return torch.matmul(tf32_round(a), tf32_round(w))
+
+    @staticmethod
+    def backward(ctx, g):
+        a, w = ctx.saved_tensors
+        gr = tf32_round(g)
+        ga = torch.matmul(gr, tf32_round(w).transpose(-1, -2))
+        gw = torch.matmul(tf32_round(a).reshape(-1, a.shape[-1]).t(), gr.reshape(-1, g.shape[-1]))
+        return ga, gw
+
+
+def contract(a, w):
+    """a [..., K] @ w [K, N]"""
+    return _Tf32Matmul.apply(a, w) if TF32_EMULATION else torch.matmul(a, w)
+
+
+# --------------------------------------------------------------------------- index tables
+def shift_tables_closed_form(num_point, in_channels, out_channels):
+    """Closed form of the two gather tables, int64.
+
+    shift_in [v*C + c] = ((v + c) mod V) * C + c      shift_out[v*D + d] = ((v - d) mod V) * D + d
+    """
+    v = np.arange(num_point, dtype=np.int64)[:, None]
+    c = np.arange(in_channels, dtype=np.int64)[None, :]
+    d = np.arange(out_channels, dtype=np.int64)[None, :]
+    tab_in = (((v + c) % num_point) * in_channels + c).reshape(-1)
+    tab_out = (((v - d) % num_point) * out_channels + d).reshape(-1)
+    return tab_in, tab_out
+
+
+def shift_tables_loop(num_point, in_channels, out_channels):
+    """The reference's literal construction, model/shift_gcn.py:108-118 (double loop, modulo V*C)."""
+    tab_in = np.empty(num_point * in_channels, dtype=np.int64)
+    for i in range(num_point):
+        for j in range(in_channels):
+            tab_in[i * in_channels + j] = (i * in_channels + j + j * in_channels) % (in_channels * num_point)
+    tab_out = np.empty(num_point * out_channels, dtype=np.int64)
+    for i in range(num_point):
+        for j in range(out_channels):
+            tab_out[i * out_channels + j] = (i * out_channels + j - j * out_channels) % (out_channels * num_point)
+    return tab_in, tab_out
+
+
+def _kaiming_conv(conv):
+    nn.init.kaiming_normal_(conv.weight, mode="fan_out")     # model/shift_gcn.py:21-23
+    nn.init.constant_(conv.bias, 0)
+
+
+# --------------------------------------------------------------------------- modules
+class RefTcn(nn.Module):
+    """model/shift_gcn.py:31-45 -- strided (k,1) conv + BN; the relu member is never applied."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=9, stride=1):
+        super().__init__()
+        pad = int((kernel_size - 1) / 2)
+        self.conv = nn.Conv2d(in_channels, out_channels, (kernel_size, 1), padding=(pad, 0), stride=(stride, 1))
+        self.bn = nn.BatchNorm2d(out_channels)
+        self.relu = nn.ReLU()
+        _kaiming_conv(self.conv)
+        nn.init.constant_(self.bn.weight, 1)
+        nn.init.constant_(self.bn.bias, 0)
+
+    def forward(self, x):
+        return self.bn(self.conv(x))
+
+
+class RefShiftTcn(nn.Module):
+    """model/shift_gcn.py:48-74 -- bn -> Shift(1) -> 1x1 conv -> relu -> Shift(stride) -> bn2."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=9, stride=1):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.bn = nn.BatchNorm2d(in_channels)
+        self.bn2 = nn.BatchNorm2d(in_channels)                       # sized by in_channels (:56)
+        nn.init.constant_(self.bn2.weight, 1)
+        nn.init.constant_(self.bn2.bias, 0)
+        self.relu = nn.ReLU(inplace=True)
+        self.shift_in = OracleShift(channel=in_channels, stride=1, init_scale=1)
+        self.shift_out = OracleShift(channel=out_channels, stride=stride, init_scale=1)
+        self.temporal_linear = nn.Conv2d(in_channels, out_channels, 1)
+        nn.init.kaiming_normal_(self.temporal_linear.weight, mode="fan_out")   # bias keeps torch default (:62-63)
+
+    def forward(self, x):
+        u = self.bn(x)
+        p = self.shift_in(u)
+        if TF32_EMULATION:
+            w = self.temporal_linear.weight.reshape(self.out_channels, self.in_channels)
+            lin = contract(p.permute(0, 2, 3, 1), w.t()).permute(0, 3, 1, 2) + self.temporal_linear.bias.view(1, -1, 1, 1)
+        else:
+            lin = self.temporal_linear(p)
+        q = F.relu(lin)
+        s = self.shift_out(q)
+        return self.bn2(s)
+
+
+class RefShiftGcn(nn.Module):
+    """model/shift_gcn.py:77-142 -- gather, mask, C x D contraction, gather, BN1d, residual, relu."""
+
+    def __init__(self, in_channels, out_channels, A=None, coff_embedding=4, num_subset=3, num_point=25):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        if in_channels != out_channels:
+            self.down = nn.Sequential(nn.Conv2d(in_channels, out_channels, 1), nn.BatchNorm2d(out_channels))
+        else:
+            self.down = None
+        self.Linear_weight = nn.Parameter(torch.zeros(in_channels, out_channels))
+        nn.init.normal_(self.Linear_weight, 0, math.sqrt(1.0 / out_channels))
+        self.Linear_bias = nn.Parameter(torch.zeros(1, 1, out_channels))
+        self.Feature_Mask = nn.Parameter(torch.zeros(1, num_point, in_channels))
+        self.bn = nn.BatchNorm1d(num_point * out_channels)
+        self.relu = nn.ReLU()
+        if self.down is not None:                                  # the init loop at :102-106
+            _kaiming_conv(self.down[0])
+            nn.init.constant_(self.down[1].weight, 1)
+            nn.init.constant_(self.down[1].bias, 0)
+        tab_in, tab_out = shift_tables_loop(num_point, in_channels, out_channels)
+        self.shift_in = nn.Parameter(torch.from_numpy(tab_in), requires_grad=False)
+        self.shift_out = nn.Parameter(torch.from_numpy(tab_out), requires_grad=False)
+
+    def forward(self, x0):
+        n, c, t, v = x0.shape
+        rows = x0.permute(0, 2, 3, 1).reshape(n * t, v * c)                     # :123-126
+        xs = rows.index_select(1, self.shift_in).view(n * t, v, c)             # :127-128
+        xm = xs * (torch.tanh(self.Feature_Mask) + 1)                          # :129
+        y = contract(xm, self.Linear_weight) + self.Linear_bias                # :131-132
+        z = y.reshape(n * t, -1).index_select(1, self.shift_out)               # :135-136
+        z = self.bn(z)                                                         # :137
+        z = z.view(n, t, v, self.out_channels).permute(0, 3, 1, 2)             # :138
+        res = x0 if self.down is None else self.down(x0)                       # :140
+        return F.relu(z + res)                                                 # :141
+
+
+class RefUnit(nn.Module):
+    """model/shift_gcn.py:145-162 -- relu(tcn1(gcn1(x)) + residual(x))."""
+
+    def __init__(self, in_channels, out_channels, A=None, stride=1, residual=True, num_point=25):
+        super().__init__()
+        self.gcn1 = RefShiftGcn(in_channels, out_channels, A, num_point=num_point)
+        self.tcn1 = RefShiftTcn(out_channels, out_channels, stride=stride)
+        self.relu = nn.ReLU()
+        self.residual_mode = ("none" if not residual else
+                              "identity" if (in_channels == out_channels and stride == 1) else "conv")
+        if self.residual_mode == "conv":
+            self.residual = RefTcn(in_channels, out_channels, kernel_size=1, stride=stride)
+
+    def forward(self, x):
+        y = self.tcn1(self.gcn1(x))
+        if self.residual_mode == "identity":
+            y = y + x
+        elif self.residual_mode == "conv":
+            y = y + self.residual(x)
+        return F.relu(y)
+
+
+LAYER_PLAN = (  # (in, out, stride, residual)   model/shift_gcn.py:178-187
+    (3, 64, 1, False), (64, 64, 1, True), (64, 64, 1, True), (64, 64, 1, True),
+    (64, 128, 2, True), (128, 128, 1, True), (128, 128, 1, True),
+    (128, 256, 2, True), (256, 256, 1, True), (256, 256, 1, True),
+)
+
+
+class RefModel(nn.Module):
+    """model/shift_gcn.py:165-216 -- data_bn, ten units, mean over (T,V) and M, fc.
+
+    The adjacency is not used by any forward in the reference, so no graph is needed.
+    """
+
+    def __init__(self, num_class=60, num_point=25, num_person=2, in_channels=3):
+        super().__init__()
+        self.data_bn = nn.BatchNorm1d(num_person * in_channels * num_point)
+        for i, (cin, cout, stride, res) in enumerate(LAYER_PLAN, start=1):
+            setattr(self, f"l{i}", RefUnit(cin, cout, None, stride=stride, residual=res, num_point=num_point))
+        self.fc = nn.Linear(256, num_class)
+        nn.init.normal_(self.fc.weight, 0, math.sqrt(2.0 / num_class))
+        nn.init.constant_(self.data_bn.weight, 1)
+        nn.init.constant_(self.data_bn.bias, 0)
+
+    def forward(self, x):
+        N, C, T, V, M = x.shape
+        x = x.permute(0, 4, 3, 1, 2).contiguous().view(N, M * V * C, T)           # :196
+        x = self.data_bn(x)                                                       # :197
+        x = x.view(N, M, V, C, T).permute(0, 1, 3, 4, 2).contiguous().view(N * M, C, T, V)   # :198
+        for i in range(1, 11):
+            x = getattr(self, f"l{i}")(x)
+        x = x.view(N, M, x.shape[1], -1).mean(3).mean(1)                          # :212-214
+        return self.fc(x)
+
+
+# --------------------------------------------------------------------------- deterministic fills
+def fill_value(name, shape, dtype=np.float32):
+    """Deterministic, platform-independent pseudo-random fill keyed by the state_dict key.
+
+    Used by the golden-fixture generator and by the tests to give the reference, the oracle and the
+    CUDA modules identical non-degenerate weights without storing megabytes of parameters
+    (init values -- mask 0, bias 0, gamma 1 -- hide bugs).
+    """
+    n = int(np.prod(shape)) if len(shape) else 1
+    seed = 0
+    for ch in name:
+        seed = (seed * 131 + ord(ch)) % 1000003
+    i = np.arange(n, dtype=np.float64)
+    # low-discrepancy-ish values in (-1, 1): fractional parts of an irrational multiple
+    base = np.modf((i + 1.0) * 0.6180339887498949 + seed * 0.7548776662466927)[0] * 2.0 - 1.0
+    leaf = name.split(".")[-1]
+    parent = name.split(".")[-2] if "." in name else ""
+    if leaf == "running_var":
+        vals = 1.0 + 0.5 * base                      # U(0.5, 1.5)
+    elif leaf == "running_mean":
+        vals = 0.1 * base
+    elif leaf == "num_batches_tracked":
+        return np.zeros(shape, dtype=np.int64)
+    elif leaf == "weight" and ("bn" in parent or parent in ("1",)):
+        vals = 1.0 + 0.5 * base                      # BN gamma in (0.5, 1.5)
+    elif leaf == "bias":
+        vals = 0.1 * base
+    elif leaf == "Linear_bias":
+        vals = 0.1 * base
+    elif leaf == "Feature_Mask":
+        vals = 0.8 * base
+    elif leaf == "ypos":
+        vals = 2.5 * base                            # fractional shifts in (-2.5, 2.5)
+        if n >= 8:
+            vals[1] = 1.0                            # exact integers exercise the floor() edge
+            vals[3] = -2.0
+            vals[5] = 0.0
+            vals[6] = 9.25                           # beyond any small halo
+            vals[7] = -11.5
+    elif leaf == "xpos":
+        vals = 1e-8 * base
+    elif leaf == "Linear_weight":
+        vals = base * math.sqrt(3.0 / shape[1])
+    elif leaf == "weight" and len(shape) == 4:       # 1x1 convs
+        vals = base * math.sqrt(3.0 / shape[1])
+    elif leaf == "weight" and len(shape) == 2:       # fc
+        vals = base * math.sqrt(3.0 / shape[1])
+    else:
+        vals = base
+    return vals.reshape(shape).astype(dtype)
+
+
+def fill_module_(module, prefix=""):
+    """In-place deterministic fill of every float parameter/buffer (int64 tables are left alone)."""
+    with torch.no_grad():
+        for key, t in module.state_dict().items():
+            if t.dtype in (torch.float32, torch.float64):
+                t.copy_(torch.from_numpy(fill_value(prefix + key, tuple(t.shape), np.float64)).to(t.dtype))
+    return module

@@ -1,0 +1,102 @@
+"""ctypes binding of libshiftgcn_b200.so (the C ABI declared in include/shiftgcn_b200.h).
+
+There is deliberately NO fallback: if the library is missing or the device is not sm_100, every op raises.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+c_float_p = ctypes.c_void_p   # device pointers travel as integers
+c_double_p = ctypes.c_void_p
+_i, _ll, _d, _vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_void_p
+
+
+class SgcnRowGemm(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("in0", "in1", "out", "wimg", "pro_a", "pro_b", "pro_c", "bias", "epi_a", "epi_b",
+                                   "res", "res2", "res2m", "xin", "stats", "red0")] + \
+               [("groups", _ll), ("V", _i), ("G", _i), ("T", _i), ("K", _i), ("N", _i), ("relu", _i)]
+
+
+class SgcnWgrad(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("a_src", "a_tab0", "b_src", "b_src2", "b_tab0", "b_tab1", "b_tab2", "dw")] + \
+               [("groups", _ll), ("V", _i), ("G", _i), ("T", _i), ("CA", _i), ("CB", _i)]
+
+
+class SgcnTShift(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("q", "res", "out", "ypos_eff", "scale", "shift", "stats")] + \
+               [("n_samples", _ll), ("T_in", _i), ("T_out", _i), ("V", _i), ("C", _i), ("stride", _i), ("relu", _i)]
+
+
+class SgcnTShiftBwd(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("q", "gy", "y", "ypos_eff", "mean", "invstd", "k1", "m1", "m2", "sums", "dpre",
+                                   "dbias")] + \
+               [("n_samples", _ll), ("T_in", _i), ("T_out", _i), ("V", _i), ("C", _i), ("stride", _i), ("relu", _i)]
+
+
+class SgcnTShiftInBwd(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("dp", "h", "z", "ypos_eff", "mean", "invstd", "scale", "shift", "k1", "m1", "m2",
+                                   "zmean", "zinvstd", "sums", "vd_sums", "gh")] + \
+               [("n_samples", _ll), ("T", _i), ("V", _i), ("C", _i), ("relu_h", _i)]
+
+
+# name -> argtypes (restype is always int unless noted); must list every symbol of include/shiftgcn_b200.h
+SIGNATURES = {
+    "sgcn_abi_version": [],
+    "sgcn_device_check": [],
+    "sgcn_selftest_umma": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "sgcn_shift_fwd_nchw_f32": [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
+    "sgcn_shift_fwd_nchw_f64": [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
+    "sgcn_shift_bwd_nchw_f32": [_vp] * 9 + [_ll, _i, _i, _i, _i, _vp],
+    "sgcn_shift_bwd_nchw_f64": [_vp] * 9 + [_ll, _i, _i, _i, _i, _vp],
+    "sgcn_rowgemm": [ctypes.POINTER(SgcnRowGemm), _i, _i, _vp],
+    "sgcn_wgrad": [ctypes.POINTER(SgcnWgrad), _i, _vp],
+    "sgcn_bn_res_relu_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp],
+    "sgcn_tshift_fwd": [ctypes.POINTER(SgcnTShift), _i, _vp],
+    "sgcn_tshift_bwd": [ctypes.POINTER(SgcnTShiftBwd), _i, _vp],
+    "sgcn_tshift_in_bwd": [ctypes.POINTER(SgcnTShiftInBwd), _i, _vp],
+    "sgcn_relu_bn1d_bwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
+    "sgcn_channel_stats": [_vp, _vp, _ll, _i, _vp],
+    "sgcn_relu_mask_grad": [_vp, _vp, _vp, _ll, _vp],
+    "sgcn_bn_fwd_finalize": [_vp] * 10 + [_i, _d, _d, _d, _i, _vp],
+    "sgcn_tshift_bwd_finalize": [_vp] * 11 + [_i, _d, _d, _i, _vp],
+    "sgcn_tshift_in_bwd_finalize": [_vp] * 11 + [_i, _d, _d, _i, _vp],
+    "sgcn_bn1d_bwd_finalize": [_vp] * 10 + [_i, _i, _d, _i, _vp],
+    "sgcn_mask_prepare": [_vp, _vp, _i, _vp],
+    "sgcn_mask_grad_finalize": [_vp, _vp, _vp, _i, _vp],
+    "sgcn_prep_weight_image": [_vp, _ll, _ll, _i, _i, _vp, _vp],
+    "sgcn_reduce_export": [_vp, _vp, _i, _d, _vp],
+}
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load the shared library (never builds implicitly; run ``__graft_entry__.build()`` first)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"shiftgcn_b200: {path} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(needs nvcc 12.9). There is no CPU or PyTorch fallback for the Shift-GCN hot path.")
+    lib = ctypes.CDLL(path)
+    lib.sgcn_last_error.restype = ctypes.c_char_p
+    lib.sgcn_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header / library drift
+        fn.restype = ctypes.c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().sgcn_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"shiftgcn_b200 {what} failed (code {rc}): {msg}")

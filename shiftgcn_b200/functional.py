@@ -1,0 +1,292 @@
+"""Launch sequences and autograd glue of the fused Shift-GCN units.
+
+Everything here works on channels-last "row" tensors ``(n, T, V, C)`` (contiguous), i.e. the reference's own
+``x.permute(0,2,3,1).contiguous()`` layout (model/shift_gcn.py:123) kept for the whole network.  The nn.Modules in
+``modules.py`` convert at the boundary (zero-copy when the caller already uses ``torch.channels_last``).
+
+Kernel schedule of one identity unit in training (a = one activation tensor pass over HBM):
+
+  forward   spatial GEMM (x -> z, BN1d batch sums)            2a      sgcn_rowgemm  SPATIAL / ROT_RAW
+            BN1d + residual + ReLU (-> h, BN2d sums of h)     3a      sgcn_bn_res_relu_fwd
+            BN + shift + 1x1 conv + ReLU (h -> q)             2a      sgcn_rowgemm  LERP / LINEAR
+            output shift, BN2d sums of s                      1a      sgcn_tshift_fwd  mode 0
+            shift + BN + residual + ReLU (-> y)               3a      sgcn_tshift_fwd  mode 1
+  backward  sums for bn2 / ypos_out                           3a      sgcn_tshift_bwd  mode 0
+            dpre = [q>0] * Shift^T(BN-bwd)                    4a      sgcn_tshift_bwd  mode 1
+            dp = dpre * W_t                                   2a      sgcn_rowgemm  PLAIN / LINEAR
+            dW_t                                              2a      sgcn_wgrad  TEMPORAL
+            sums for bn / ypos_in                             2a      sgcn_tshift_in_bwd  mode 0
+            gh = [h>0] * BN-bwd(Shift^T dp), BN1d sums        4a      sgcn_tshift_in_bwd  mode 1
+            g_x = spatial backward-data (+ both residuals)    6a      sgcn_rowgemm  DY / SPATIAL_BWD
+            dW                                                3a      sgcn_wgrad  SPATIAL
+"""
+import torch
+
+from . import ops
+
+BN_EPS = 1e-5
+
+
+def _bn_args(bn):
+    """(gamma, beta, running_mean, running_var, nbt, momentum) of a torch BatchNorm module"""
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    return bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, mom
+
+
+class Workspace:
+    """Zero-initialised fp64 reduction buffers that the finalize kernels hand back zeroed."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, name, numel, device):
+        key = (name, numel, str(device))
+        buf = self._bufs.get(key)
+        if buf is None:
+            buf = torch.zeros(numel, device=device, dtype=torch.float64)
+            self._bufs[key] = buf
+        return buf
+
+    def reset(self):
+        for b in self._bufs.values():
+            b.zero_()
+
+
+# ================================================================================================ spatial unit
+def spatial_forward(x, res, W, bias, mask, bn, training, ws, fuse_eval, h_stats=None):
+    """x: (n,T,V,C) rows; res: None (identity, needs C == D) or (n,T,V,D) rows already normalised.
+
+    Returns (h, saved) where saved holds what the backward needs (None in the fused eval path).
+    """
+    n, T, V, C = x.shape
+    D = W.shape[1]
+    R = n * T
+    dev = x.device
+    mm = ops.mask_prepare(mask.reshape(V, C))
+    wimg = ops.weight_image(W, 1, D, D, C)                         # B[n=d][k=c] = W[c][d]
+    gamma, beta, rmean, rvar, nbt, mom = _bn_args(bn)
+    resid = x if res is None else res
+    if fuse_eval:
+        mean, invstd, scale, shift = ops.bn_fwd_finalize(None, gamma, beta, rmean, rvar, None, V * D, R, mom, bn.eps, False)
+        h = torch.empty((n, T, V, D), device=dev, dtype=torch.float32)
+        ops.rowgemm(ops.PRO_SPATIAL, ops.EPI_ROT_FUSED, in0=x, out=h, wimg=wimg, groups=R, V=V, K=C, N=D, pro_a=mm,
+                    bias=bias.reshape(D), epi_a=scale, epi_b=shift, res=resid, relu=1)
+        return h, None
+    z = torch.empty((n, T, V, D), device=dev, dtype=torch.float32)
+    stats = ws.get("bn1d", 2 * V * D, dev)
+    ops.rowgemm(ops.PRO_SPATIAL, ops.EPI_ROT_RAW, in0=x, out=z, wimg=wimg, groups=R, V=V, K=C, N=D, pro_a=mm,
+                bias=bias.reshape(D), stats=stats)
+    mean, invstd, scale, shift = ops.bn_fwd_finalize(stats if training else None, gamma, beta, rmean, rvar, nbt, V * D,
+                                                      R, mom, bn.eps, training)
+    if not training:
+        stats.zero_()
+    h = torch.empty((n, T, V, D), device=dev, dtype=torch.float32)
+    ops.bn_res_relu_fwd(z, resid, h, scale, shift, h_stats, R * V, V, D, relu=1)
+    saved = dict(x=x, z=z, h=h, mm=mm, mean=mean, invstd=invstd, training=training)
+    return h, saved
+
+
+def spatial_backward(saved, gh, W, mask, gamma, vd_sums_ready, ws, unit_res=None):
+    """gh: grad wrt the gcn output with the ReLU mask already applied when ``vd_sums_ready`` (fused unit),
+    otherwise the raw incoming gradient.  unit_res = (g_y, y) adds the block's identity-residual gradient.
+
+    Returns dict(gx, gres, dW, dbias, dmask, dgamma, dbeta).
+    """
+    x, z, h, mm = saved["x"], saved["z"], saved["h"], saved["mm"]
+    n, T, V, C = x.shape
+    D = W.shape[1]
+    R = n * T
+    dev = x.device
+    vd = ws.get("bn1d_bwd", 2 * V * D, dev)
+    if not vd_sums_ready:
+        ghm = torch.empty_like(gh)
+        ops.relu_bn1d_bwd_stats(gh, h, z, saved["mean"], saved["invstd"], ghm, vd, R, V, D)
+        gh = ghm
+    fin = ops.bn1d_bwd_finalize(vd, gamma, saved["mean"], saved["invstd"], V, D, R, saved["training"])
+    wimg_t = ops.weight_image(W, D, 1, C, D)                       # B[n=c][k=d] = W[c][d]
+    gx = torch.empty_like(x)
+    dmask_raw = ws.get("dmask", V * C, dev)
+    identity = C == D and saved.get("identity_res", True)
+    ops.rowgemm(ops.PRO_DY, ops.EPI_SPATIAL_BWD, in0=gh, in1=z, out=gx, wimg=wimg_t, groups=R, V=V, K=D, N=C,
+                pro_a=fin["alpha"], pro_b=fin["beta"], pro_c=fin["gamma"], epi_a=mm,
+                res=gh if identity else None,
+                res2=unit_res[0] if unit_res is not None else None,
+                res2m=unit_res[1] if unit_res is not None else None, xin=x, red0=dmask_raw)
+    dW = torch.zeros((C, D), device=dev, dtype=torch.float32)
+    ops.wgrad(ops.WG_SPATIAL, a_src=x, a_tab0=mm, b_src=gh, b_src2=z, b_tab0=fin["alpha"], b_tab1=fin["beta"],
+              b_tab2=fin["gamma"], dw=dW, groups=R, V=V, CA=C, CB=D)
+    dmask = ops.mask_grad_finalize(dmask_raw, mask.reshape(V, C))
+    return dict(gx=gx, gres=None if identity else gh, dW=dW, dbias=fin["dbias"].reshape(1, 1, D),
+                dmask=dmask.reshape(1, V, C), dgamma=fin["dgamma"], dbeta=fin["dbeta"])
+
+
+# ================================================================================================ temporal unit
+def temporal_forward(h, res, relu, bn, ypos_in, Wt, bt, ypos_out, bn2, stride, training, ws, h_stats_ready):
+    """h: (n,T,V,C) rows -> y: (n,T/stride,V,C) rows = [relu](bn2(Shift_s(relu(conv(Shift_1(bn(h)))))) + res)"""
+    n, T, V, C = h.shape
+    To = T // stride
+    dev = h.device
+    ga, ba, rma, rva, nbta, moma = _bn_args(bn)
+    stats_a = ws.get("bn_a", 2 * C, dev)
+    if training and not h_stats_ready:
+        ops.channel_stats(h, stats_a, n * T * V, C)
+    mean_a, invstd_a, scale_a, shift_a = ops.bn_fwd_finalize(stats_a if training else None, ga, ba, rma, rva, nbta, C,
+                                                              n * T * V, moma, bn.eps, training)
+    wimg = ops.weight_image(Wt, C, 1, C, C)                        # B[n=co][k=ci] = Wt[co][ci]
+    ypos_in_eff = ypos_in.detach().contiguous()
+    q = torch.empty((n, T, V, C), device=dev, dtype=torch.float32)
+    ops.rowgemm(ops.PRO_LERP, ops.EPI_LINEAR, in0=h, out=q, wimg=wimg, groups=n * T, V=V, K=C, N=C, T=T,
+                pro_a=scale_a, pro_b=shift_a, pro_c=ypos_in_eff, bias=bt, relu=1)
+    ypos_out_eff = (ypos_out.detach() + 0.5) if stride != 1 else ypos_out.detach().contiguous()   # cuda/shift.py:14-19
+    gb, bb, rmb, rvb, nbtb, momb = _bn_args(bn2)
+    stats_b = ws.get("bn_b", 2 * C, dev)
+    if training:
+        ops.tshift_fwd(0, q=q, ypos_eff=ypos_out_eff, n_samples=n, T_in=T, T_out=To, V=V, C=C, stride=stride,
+                       stats=stats_b)
+    mean_b, invstd_b, scale_b, shift_b = ops.bn_fwd_finalize(stats_b if training else None, gb, bb, rmb, rvb, nbtb, C,
+                                                              n * To * V, momb, bn2.eps, training)
+    y = torch.empty((n, To, V, C), device=dev, dtype=torch.float32)
+    ops.tshift_fwd(1, q=q, ypos_eff=ypos_out_eff, n_samples=n, T_in=T, T_out=To, V=V, C=C, stride=stride, res=res,
+                   out=y, scale=scale_b, shift=shift_b, relu=relu)
+    saved = dict(h=h, q=q, y=y, relu=relu, stride=stride, training=training, ypos_in_eff=ypos_in_eff,
+                 ypos_out_eff=ypos_out_eff, mean_a=mean_a, invstd_a=invstd_a, scale_a=scale_a, shift_a=shift_a,
+                 mean_b=mean_b, invstd_b=invstd_b)
+    return y, saved
+
+
+def temporal_backward(saved, gy, gamma_a, Wt, gamma_b, ws, spatial_saved=None, spatial_ws=None, relu_h=False,
+                      want_raw=False):
+    """Returns dict(gh, dWt, dbt, dgamma_a, dbeta_a, dgamma_b, dbeta_b, gx_in, gy_in, gx_out, gy_out[, raw_in, raw_out]).
+
+    With ``spatial_saved`` (fused unit) the last kernel also applies the gcn ReLU mask and accumulates the
+    BN1d backward sums, so the spatial backward can start immediately.
+    """
+    h, q, y = saved["h"], saved["q"], saved["y"]
+    n, T, V, C = h.shape
+    stride = saved["stride"]
+    To = T // stride
+    dev = h.device
+    training = saved["training"]
+    relu = saved["relu"]
+    sums5 = ws.get("tshift_bwd", 5 * C, dev)
+    common = dict(q=q, gy=gy, y=y if relu else None, relu=relu, ypos_eff=saved["ypos_out_eff"], mean=saved["mean_b"],
+                  invstd=saved["invstd_b"], n_samples=n, T_in=T, T_out=To, V=V, C=C, stride=stride)
+    ops.tshift_bwd(0, sums=sums5, **common)
+    fb = ops.tshift_bwd_finalize(sums5, gamma_b, saved["invstd_b"], C, n * To * V, n, training, input_shift=False,
+                                 want_raw=want_raw)
+    dpre = torch.empty((n, T, V, C), device=dev, dtype=torch.float32)
+    dbias_acc = ws.get("dbt", C, dev)
+    ops.tshift_bwd(1, k1=fb["k1"], m1=fb["m1"], m2=fb["m2"], dpre=dpre, dbias=dbias_acc, **common)
+    dbt = ops.reduce_export(dbias_acc)
+    wimg_t = ops.weight_image(Wt, 1, C, C, C)                      # B[n=ci][k=co] = Wt[co][ci]
+    dp = torch.empty((n, T, V, C), device=dev, dtype=torch.float32)
+    ops.rowgemm(ops.PRO_PLAIN, ops.EPI_LINEAR, in0=dpre, out=dp, wimg=wimg_t, groups=n * T, V=V, K=C, N=C, relu=0)
+    dWt = torch.zeros((C, C), device=dev, dtype=torch.float32)
+    ops.wgrad(ops.WG_TEMPORAL, a_src=dpre, b_src=h, b_tab0=saved["scale_a"], b_tab1=saved["shift_a"],
+              b_tab2=saved["ypos_in_eff"], dw=dWt, groups=n * T, V=V, CA=C, CB=C, T=T)
+    sums3 = ws.get("tshift_in_bwd", 3 * C, dev)
+    common_in = dict(dp=dp, h=h, ypos_eff=saved["ypos_in_eff"], mean=saved["mean_a"], invstd=saved["invstd_a"],
+                     n_samples=n, T=T, V=V, C=C)
+    ops.tshift_in_bwd(0, scale=saved["scale_a"], shift=saved["shift_a"], sums=sums3, **common_in)
+    fa = ops.tshift_bwd_finalize(sums3, gamma_a, saved["invstd_a"], C, n * T * V, n, training, input_shift=True,
+                                 want_raw=want_raw)
+    gh = torch.empty((n, T, V, C), device=dev, dtype=torch.float32)
+    if spatial_saved is not None:
+        vd = spatial_ws.get("bn1d_bwd", 2 * V * C, dev)
+        ops.tshift_in_bwd(1, k1=fa["k1"], m1=fa["m1"], m2=fa["m2"], gh=gh, relu_h=1, z=spatial_saved["z"],
+                          zmean=spatial_saved["mean"], zinvstd=spatial_saved["invstd"], vd_sums=vd, **common_in)
+    else:
+        ops.tshift_in_bwd(1, k1=fa["k1"], m1=fa["m1"], m2=fa["m2"], gh=gh, relu_h=1 if relu_h else 0, **common_in)
+    out = dict(gh=gh, dWt=dWt.reshape(C, C, 1, 1), dbt=dbt, dgamma_a=fa["dgamma"], dbeta_a=fa["dbeta"],
+               dgamma_b=fb["dgamma"], dbeta_b=fb["dbeta"], gx_in=fa["gx"], gy_in=fa["gy"], gx_out=fb["gx"],
+               gy_out=fb["gy"])
+    if want_raw:
+        out["raw_in"], out["raw_out"] = fa["raw"], fb["raw"]
+    return out
+
+
+# ================================================================================================ autograd
+class SpatialFn(torch.autograd.Function):
+    """Shift_gcn.forward (model/shift_gcn.py:121-142) on rows; ``res`` = down(x0) rows or None for identity."""
+
+    @staticmethod
+    def forward(ctx, x, res, W, bias, mask, gamma, beta, module):
+        training = module.training
+        need_grad = torch.is_grad_enabled() and any(
+            t is not None and t.requires_grad for t in (x, res, W, bias, mask, gamma, beta))
+        h, saved = spatial_forward(x, res, W, bias, mask, module.bn, training, module._ws,
+                                   fuse_eval=(not training and not need_grad))
+        ctx.module = module
+        ctx.saved = saved
+        if saved is not None:
+            saved["identity_res"] = res is None
+            ctx.save_for_backward(W, mask, gamma)
+        return h
+
+    @staticmethod
+    def backward(ctx, g):
+        W, mask, gamma = ctx.saved_tensors
+        r = spatial_backward(ctx.saved, g.contiguous(), W, mask, gamma, False, ctx.module._ws)
+        return r["gx"], r["gres"], r["dW"], r["dbias"], r["dmask"], r["dgamma"], r["dbeta"], None
+
+
+class TemporalFn(torch.autograd.Function):
+    """Shift_tcn.forward (model/shift_gcn.py:65-74) on rows, optionally fused with the block residual + ReLU
+    of TCN_GCN_unit.forward (:160-162)."""
+
+    @staticmethod
+    def forward(ctx, h, res, ga, ba, xpos_in, ypos_in, Wt, bt, xpos_out, ypos_out, gb, bb, module, relu):
+        y, saved = temporal_forward(h, res, relu, module.bn, ypos_in, Wt.reshape(Wt.shape[0], Wt.shape[1]), bt,
+                                    ypos_out, module.bn2, module.shift_out.stride, module.training, module._ws, False)
+        ctx.module = module
+        ctx.saved = saved
+        ctx.has_res = res is not None
+        ctx.save_for_backward(ga, Wt, gb)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        ga, Wt, gb = ctx.saved_tensors
+        gy = gy.contiguous()
+        r = temporal_backward(ctx.saved, gy, ga, Wt.reshape(Wt.shape[0], Wt.shape[1]), gb, ctx.module._ws)
+        gres = None
+        if ctx.has_res:
+            gres = ops.relu_mask_grad(gy, ctx.saved["y"]) if ctx.saved["relu"] else gy
+        return (r["gh"], gres, r["dgamma_a"], r["dbeta_a"], r["gx_in"], r["gy_in"], r["dWt"], r["dbt"], r["gx_out"],
+                r["gy_out"], r["dgamma_b"], r["dbeta_b"], None, None)
+
+
+class UnitFn(torch.autograd.Function):
+    """A whole identity-residual TCN_GCN_unit (in == out channels, stride 1; model/shift_gcn.py:155-156,160-162):
+    relu(tcn1(gcn1(x)) + x) with every cross-stage fusion enabled."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, mask, g1, b1, ga, ba, xpos_in, ypos_in, Wt, bt, xpos_out, ypos_out, gb, bb, unit):
+        gcn, tcn = unit.gcn1, unit.tcn1
+        training = unit.training
+        n, T, V, C = x.shape
+        need_grad = torch.is_grad_enabled() and any(
+            t.requires_grad for t in (x, W, bias, mask, g1, b1, ga, ba, ypos_in, Wt, bt, ypos_out, gb, bb))
+        h_stats = tcn._ws.get("bn_a", 2 * C, x.device) if training else None
+        h, s_saved = spatial_forward(x, None, W, bias, mask, gcn.bn, training, gcn._ws,
+                                     fuse_eval=(not training and not need_grad), h_stats=h_stats)
+        y, t_saved = temporal_forward(h, x, 1, tcn.bn, ypos_in, Wt.reshape(C, C), bt, ypos_out, tcn.bn2, 1, training,
+                                      tcn._ws, h_stats_ready=training)
+        ctx.unit = unit
+        ctx.s_saved, ctx.t_saved = s_saved, t_saved
+        if s_saved is not None:
+            s_saved["identity_res"] = True
+        ctx.save_for_backward(W, mask, g1, ga, Wt, gb)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        W, mask, g1, ga, Wt, gb = ctx.saved_tensors
+        unit = ctx.unit
+        gy = gy.contiguous()
+        C = W.shape[0]
+        t = temporal_backward(ctx.t_saved, gy, ga, Wt.reshape(C, C), gb, unit.tcn1._ws, spatial_saved=ctx.s_saved,
+                              spatial_ws=unit.gcn1._ws)
+        s = spatial_backward(ctx.s_saved, t["gh"], W, mask, g1, True, unit.gcn1._ws, unit_res=(gy, ctx.t_saved["y"]))
+        return (s["gx"], s["dW"], s["dbias"], s["dmask"], s["dgamma"], s["dbeta"], t["dgamma_a"], t["dbeta_a"],
+                t["gx_in"], t["gy_in"], t["dWt"], t["dbt"], t["gx_out"], t["gy_out"], t["dgamma_b"], t["dbeta_b"], None)

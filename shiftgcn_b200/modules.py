@@ -1,0 +1,266 @@
+"""Drop-in nn.Modules for the reference's model/shift_gcn.py: ``tcn``, ``Shift_tcn``, ``Shift_gcn``,
+``TCN_GCN_unit`` and ``Model`` -- same constructor signatures, attribute names and state_dict keys / dtypes
+(SURVEY.md App. D), same train / eval semantics, computed by the fused sm_100a kernels of this package.
+
+Logical tensors stay (N, C, T, V) as in the reference; physically the network runs channels-last
+(``torch.channels_last`` strides), which is the reference's own internal ``(n, t, v, c)`` layout
+(model/shift_gcn.py:123), so chained units exchange activations without any copy.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as FN
+from .shift import Shift
+
+FUSED_CHANNELS = (64, 128, 256)
+XPOS_LIMIT = 1e-6     # the fused temporal kernels treat xpos (init U(-1e-8, 1e-8), zero gradient) as 0
+
+
+def import_class(name):
+    components = name.split('.')
+    mod = __import__(components[0])
+    for comp in components[1:]:
+        mod = getattr(mod, comp)
+    return mod
+
+
+def conv_init(conv):
+    nn.init.kaiming_normal_(conv.weight, mode='fan_out')
+    nn.init.constant_(conv.bias, 0)
+
+
+def bn_init(bn, scale):
+    nn.init.constant_(bn.weight, scale)
+    nn.init.constant_(bn.bias, 0)
+
+
+def _param_device():
+    # the reference creates these parameters with device='cuda' (model/shift_gcn.py:90,93,96)
+    return torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+
+
+def _require_cuda(x, who):
+    if not x.is_cuda:
+        raise RuntimeError(f"{who}: shiftgcn_b200 has no CPU path; move the module and its input to a B200 (sm_100a)")
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"{who}: expected float32 activations, got {x.dtype}")
+
+
+def to_rows(x):
+    """logical (n, C, T, V) -> contiguous (n, T, V, C); zero-copy for channels_last inputs"""
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def from_rows(r):
+    """(n, T, V, C) rows -> logical (n, C, T, V) view (channels_last strides)"""
+    return r.permute(0, 3, 1, 2)
+
+
+def shift_tables(num_point, in_channels, out_channels):
+    """int64 gather tables of the spatial shift (model/shift_gcn.py:108-118), vectorised:
+    shift_in[v*C + c] = (v*C + c + c*C) mod (V*C),  shift_out[v*D + d] = (v*D + d - d*D) mod (V*D)."""
+    v = np.arange(num_point, dtype=np.int64)[:, None]
+    c = np.arange(in_channels, dtype=np.int64)[None, :]
+    d = np.arange(out_channels, dtype=np.int64)[None, :]
+    tab_in = np.mod(v * in_channels + c + c * in_channels, in_channels * num_point).reshape(-1)
+    tab_out = np.mod(v * out_channels + d - d * out_channels, out_channels * num_point).reshape(-1)
+    return tab_in, tab_out
+
+
+class tcn(nn.Module):
+    """Strided (k x 1) convolution + BatchNorm: the block residual of the strided units (reference :31-45)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=9, stride=1):
+        super().__init__()
+        pad = int((kernel_size - 1) / 2)
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=(kernel_size, 1), padding=(pad, 0),
+                              stride=(stride, 1))
+        self.bn = nn.BatchNorm2d(out_channels)
+        self.relu = nn.ReLU()          # present in the reference, never applied
+        conv_init(self.conv)
+        bn_init(self.bn, 1)
+
+    def forward(self, x):
+        return self.bn(self.conv(x))
+
+
+class Shift_tcn(nn.Module):
+    """bn -> Shift(stride 1) -> 1x1 conv -> ReLU -> Shift(stride) -> bn2  (reference :48-74)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=9, stride=1):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.bn = nn.BatchNorm2d(in_channels)
+        self.bn2 = nn.BatchNorm2d(in_channels)
+        bn_init(self.bn2, 1)
+        self.relu = nn.ReLU(inplace=True)
+        self.shift_in = Shift(channel=in_channels, stride=1, init_scale=1)
+        self.shift_out = Shift(channel=out_channels, stride=stride, init_scale=1)
+        self.temporal_linear = nn.Conv2d(in_channels, out_channels, 1)
+        nn.init.kaiming_normal_(self.temporal_linear.weight, mode='fan_out')
+        self._ws = FN.Workspace()
+        self._xpos_ok = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._xpos_ok = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def fused_supported(self, x):
+        c, v = x.shape[1], x.shape[3]
+        if not (self.in_channels == self.out_channels == c and c in FUSED_CHANNELS and 8 <= v <= 40):
+            return False
+        if x.shape[2] // self.shift_out.stride < 1:
+            return False
+        if self._xpos_ok is None:      # one host sync, repeated only after load_state_dict
+            with torch.no_grad():
+                m = torch.maximum(self.shift_in.xpos.abs().max(), self.shift_out.xpos.abs().max())
+                self._xpos_ok = bool(m.item() <= XPOS_LIMIT)
+        return self._xpos_ok
+
+    def _args(self):
+        return (self.bn.weight, self.bn.bias, self.shift_in.xpos, self.shift_in.ypos, self.temporal_linear.weight,
+                self.temporal_linear.bias, self.shift_out.xpos, self.shift_out.ypos, self.bn2.weight, self.bn2.bias)
+
+    def forward_rows(self, h_rows, res_rows, relu):
+        return FN.TemporalFn.apply(h_rows, res_rows, *self._args(), self, int(relu))
+
+    def forward(self, x):
+        _require_cuda(x, "Shift_tcn")
+        if self.fused_supported(x):
+            return from_rows(self.forward_rows(to_rows(x), None, 0))
+        # general path (any channel count, bilinear xpos): stand-alone shift kernels between library ops
+        x = self.bn(x)
+        x = self.shift_in(x)
+        x = self.temporal_linear(x)
+        x = self.relu(x)
+        x = self.shift_out(x)
+        return self.bn2(x)
+
+
+class Shift_gcn(nn.Module):
+    """Spatial shift graph convolution (reference :77-142): joint-shift gather, tanh mask, C x D contraction,
+    joint-shift gather, BatchNorm1d over (v, d), residual (identity or 1x1 conv + BN), ReLU."""
+
+    def __init__(self, in_channels, out_channels, A, coff_embedding=4, num_subset=3, num_point=25):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.num_point = num_point
+        if in_channels != out_channels:
+            self.down = nn.Sequential(nn.Conv2d(in_channels, out_channels, 1), nn.BatchNorm2d(out_channels))
+        else:
+            self.down = lambda x: x
+        dev = _param_device()
+        self.Linear_weight = nn.Parameter(torch.empty(in_channels, out_channels, device=dev))
+        nn.init.normal_(self.Linear_weight, 0, math.sqrt(1.0 / out_channels))
+        self.Linear_bias = nn.Parameter(torch.zeros(1, 1, out_channels, device=dev))
+        self.Feature_Mask = nn.Parameter(torch.zeros(1, num_point, in_channels, device=dev))
+        self.bn = nn.BatchNorm1d(num_point * out_channels)
+        self.relu = nn.ReLU()
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                conv_init(m)
+            elif isinstance(m, nn.BatchNorm2d):
+                bn_init(m, 1)
+        tab_in, tab_out = shift_tables(num_point, in_channels, out_channels)
+        self.shift_in = nn.Parameter(torch.from_numpy(tab_in), requires_grad=False)
+        self.shift_out = nn.Parameter(torch.from_numpy(tab_out), requires_grad=False)
+        self._ws = FN.Workspace()
+
+    def fused_supported(self, x0):
+        return (self.in_channels in FUSED_CHANNELS and self.out_channels in FUSED_CHANNELS
+                and x0.shape[1] == self.in_channels and x0.shape[3] == self.num_point and 8 <= self.num_point <= 40)
+
+    def _args(self):
+        return (self.Linear_weight, self.Linear_bias, self.Feature_Mask, self.bn.weight, self.bn.bias)
+
+    def forward_rows(self, x_rows, x0):
+        res = None if self.in_channels == self.out_channels else to_rows(self.down(x0))
+        return FN.SpatialFn.apply(x_rows, res, *self._args(), self)
+
+    def _forward_general(self, x0):
+        """Unfused path for shapes the tensor-core kernels do not cover (e.g. the 3-channel first layer):
+        the same arithmetic with library ops.  TODO(next): SIMT kernels for C_in < 64."""
+        n, c, t, v = x0.shape
+        rows = x0.permute(0, 2, 3, 1).reshape(n * t, v * c)
+        xs = rows[:, self.shift_in].view(n * t, v, c)
+        xm = xs * (torch.tanh(self.Feature_Mask) + 1)
+        y = torch.matmul(xm, self.Linear_weight) + self.Linear_bias
+        z = y.reshape(n * t, -1)[:, self.shift_out]
+        z = self.bn(z).view(n, t, v, self.out_channels)
+        res = self.down(x0).permute(0, 2, 3, 1)
+        return from_rows(F.relu(z + res).contiguous())
+
+    def forward(self, x0):
+        _require_cuda(x0, "Shift_gcn")
+        if not self.fused_supported(x0):
+            return self._forward_general(x0)
+        return from_rows(self.forward_rows(to_rows(x0), x0))
+
+
+class TCN_GCN_unit(nn.Module):
+    """relu(tcn1(gcn1(x)) + residual(x))  (reference :145-162)."""
+
+    def __init__(self, in_channels, out_channels, A, stride=1, residual=True, num_point=25):
+        super().__init__()
+        self.gcn1 = Shift_gcn(in_channels, out_channels, A, num_point=num_point)
+        self.tcn1 = Shift_tcn(out_channels, out_channels, stride=stride)
+        self.relu = nn.ReLU()
+        if not residual:
+            self.residual = lambda x: 0
+            self._res_mode = "none"
+        elif (in_channels == out_channels) and (stride == 1):
+            self.residual = lambda x: x
+            self._res_mode = "identity"
+        else:
+            self.residual = tcn(in_channels, out_channels, kernel_size=1, stride=stride)
+            self._res_mode = "conv"
+
+    def forward(self, x):
+        _require_cuda(x, "TCN_GCN_unit")
+        gcn, tcn1 = self.gcn1, self.tcn1
+        if self._res_mode == "identity" and gcn.fused_supported(x) and tcn1.fused_supported(x):
+            y = FN.UnitFn.apply(to_rows(x), *gcn._args(), *tcn1._args(), self)
+            return from_rows(y)
+        h = gcn(x)
+        if tcn1.fused_supported(h):
+            res = to_rows(self.residual(x)) if self._res_mode != "none" else None
+            return from_rows(tcn1.forward_rows(to_rows(h), res, 1))
+        return self.relu(tcn1(h) + self.residual(x))
+
+
+class Model(nn.Module):
+    """data_bn -> 10 TCN_GCN_units (3-64-64-64-64-128-128-128-256-256-256, stride 2 at l5 and l8) -> global mean
+    over (T, V) and persons -> fc  (reference :165-216)."""
+
+    def __init__(self, num_class=60, num_point=25, num_person=2, graph=None, graph_args=dict(), in_channels=3):
+        super().__init__()
+        if graph is None:
+            raise ValueError()
+        Graph = import_class(graph)
+        self.graph = Graph(**graph_args)
+        A = self.graph.A
+        self.data_bn = nn.BatchNorm1d(num_person * in_channels * num_point)
+        plan = [(3, 64, 1, False), (64, 64, 1, True), (64, 64, 1, True), (64, 64, 1, True), (64, 128, 2, True),
+                (128, 128, 1, True), (128, 128, 1, True), (128, 256, 2, True), (256, 256, 1, True), (256, 256, 1, True)]
+        for i, (cin, cout, stride, res) in enumerate(plan, start=1):
+            setattr(self, f"l{i}", TCN_GCN_unit(cin, cout, A, stride=stride, residual=res, num_point=num_point))
+        self.fc = nn.Linear(256, num_class)
+        nn.init.normal_(self.fc.weight, 0, math.sqrt(2. / num_class))
+        bn_init(self.data_bn, 1)
+
+    def forward(self, x):
+        N, C, T, V, M = x.size()
+        x = x.permute(0, 4, 3, 1, 2).contiguous().view(N, M * V * C, T)
+        x = self.data_bn(x)
+        x = x.view(N, M, V, C, T).permute(0, 1, 3, 4, 2).contiguous().view(N * M, C, T, V)
+        for i in range(1, 11):
+            x = getattr(self, f"l{i}")(x)
+        c_new = x.size(1)
+        x = x.mean(dim=(2, 3)).view(N, M, c_new).mean(1)      # == view(N, M, C, T*V).mean(3).mean(1), stride-agnostic
+        return self.fc(x)

@@ -1,0 +1,248 @@
+"""Thin tensor -> pointer wrappers over the C ABI (include/shiftgcn_b200.h).
+
+PyTorch is plumbing only: it owns device memory and the current stream.  Every function validates device /
+dtype / contiguity (the checks the reference does with AT_ASSERTM, shift_cuda.cpp:15-17, plus the ones it
+omits), launches on ``torch.cuda.current_stream()`` and never synchronises.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import SgcnRowGemm, SgcnTShift, SgcnTShiftBwd, SgcnTShiftInBwd, SgcnWgrad
+
+PRO_SPATIAL, PRO_LERP, PRO_PLAIN, PRO_DY = 0, 1, 2, 3
+EPI_ROT_RAW, EPI_ROT_FUSED, EPI_LINEAR, EPI_SPATIAL_BWD = 0, 1, 2, 3
+WG_SPATIAL, WG_TEMPORAL = 0, 1
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=torch.float32, name="tensor"):
+    """device pointer of a contiguous CUDA tensor (None -> NULL)"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _d(t, name="buffer"):
+    return _p(t, torch.float64, name)
+
+
+def device_check():
+    _lib.check(_lib.load().sgcn_device_check(), "device check")
+
+
+def groups_per_tile(V):
+    if V < 8 or V > 40:
+        raise RuntimeError(f"shiftgcn_b200 fused kernels support 8 <= num_point <= 40, got {V}")
+    return 128 // V
+
+
+# ------------------------------------------------------------------------------------------------ self test
+def selftest_umma(a, b, mode, K, N, M2=128):
+    lib = _lib.load()
+    rows = 128
+    d = torch.empty(rows, N, device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.sgcn_selftest_umma(_p(a), _p(b), _p(d), mode, K, N, M2, _stream()), "selftest_umma")
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ stand-alone shift (NCHW)
+def shift_forward(inp, xpos, ypos, stride):
+    """``shift_cuda.forward`` (model/Temporal_shift/cuda/shift_cuda.cpp:19-23): ypos already carries the +0.5."""
+    lib = _lib.load()
+    if inp.dim() != 4:
+        raise RuntimeError("input must be (N, C, H, W)")
+    if inp.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("shift supports float32 / float64")
+    dt = inp.dtype
+    fn = lib.sgcn_shift_fwd_nchw_f32 if dt == torch.float32 else lib.sgcn_shift_fwd_nchw_f64
+    n, c, h, w = inp.shape
+    stride = int(stride)
+    if stride < 1:
+        raise RuntimeError("stride must be >= 1")
+    xpos = xpos.to(dt).contiguous()
+    ypos = ypos.to(dt).contiguous()
+    if xpos.numel() != c or ypos.numel() != c:
+        raise RuntimeError("xpos / ypos must have one entry per channel")
+    out = torch.empty((n, c, h // stride, w), device=inp.device, dtype=dt)
+    with torch.cuda.device(inp.device):
+        _lib.check(fn(_p(inp, dt, "input"), _p(out, dt), _p(xpos, dt, "xpos"), _p(ypos, dt, "ypos"), n, c, h, w, stride,
+                      _stream()), "shift forward")
+    return out
+
+
+def shift_backward(grad_output, inp, output, xpos, ypos, stride, return_raw=False):
+    """``shift_cuda.backward`` (shift_cuda.cpp:25-42): returns [grad_input, grad_xpos, grad_ypos]."""
+    lib = _lib.load()
+    dt = inp.dtype
+    if dt not in (torch.float32, torch.float64):
+        raise RuntimeError("shift supports float32 / float64")
+    fn = lib.sgcn_shift_bwd_nchw_f32 if dt == torch.float32 else lib.sgcn_shift_bwd_nchw_f64
+    n, c, h, w = inp.shape
+    stride = int(stride)
+    xpos = xpos.to(dt).contiguous()
+    ypos = ypos.to(dt).contiguous()
+    if output is not None and not output.is_contiguous():
+        raise RuntimeError("output must be contiguous")           # the reference checks it (shift_cuda.cpp:34)
+    if tuple(grad_output.shape) != (n, c, h // stride, w):
+        raise RuntimeError("grad_output has the wrong shape")
+    grad_input = torch.empty_like(inp, memory_format=torch.contiguous_format)
+    gx = torch.empty(c, device=inp.device, dtype=dt)
+    gy = torch.empty(c, device=inp.device, dtype=dt)
+    raw = torch.empty(2, c, device=inp.device, dtype=dt) if return_raw else None
+    scratch = torch.zeros(2, c, device=inp.device, dtype=torch.float64)
+    with torch.cuda.device(inp.device):
+        _lib.check(fn(_p(grad_output, dt, "grad_output"), _p(inp, dt, "input"), _p(xpos, dt), _p(ypos, dt),
+                      _p(grad_input, dt), _p(gx, dt), _p(gy, dt), _p(raw, dt), _d(scratch), n, c, h, w, stride,
+                      _stream()), "shift backward")
+    if return_raw:
+        return [grad_input, gx, gy], raw
+    return [grad_input, gx, gy]
+
+
+# ------------------------------------------------------------------------------------------------ small helpers
+def weight_image(src, ld_n, ld_k, N, K):
+    """canonical TF32 image of B[n][k] = src.flatten()[n*ld_n + k*ld_k]"""
+    lib = _lib.load()
+    img = torch.empty(N * K, device=src.device, dtype=torch.float32)
+    _lib.check(lib.sgcn_prep_weight_image(_p(src, name="weight"), ld_n, ld_k, N, K, _p(img), _stream()), "weight image")
+    return img
+
+
+def mask_prepare(mask):
+    lib = _lib.load()
+    mm = torch.empty_like(mask)
+    _lib.check(lib.sgcn_mask_prepare(_p(mask, name="Feature_Mask"), _p(mm), mask.numel(), _stream()), "mask prepare")
+    return mm
+
+
+def mask_grad_finalize(raw, mask):
+    lib = _lib.load()
+    dm = torch.empty_like(mask)
+    _lib.check(lib.sgcn_mask_grad_finalize(_d(raw), _p(mask), _p(dm), mask.numel(), _stream()), "mask grad")
+    return dm
+
+
+def reduce_export(src, scale=1.0):
+    lib = _lib.load()
+    dst = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+    _lib.check(lib.sgcn_reduce_export(_d(src), _p(dst), src.numel(), float(scale), _stream()), "reduce export")
+    return dst
+
+
+def bn_fwd_finalize(stats, gamma, beta, running_mean, running_var, nbt, features, count, momentum, eps, training):
+    """-> (mean, invstd, scale, shift) fp32 [features]; updates running stats / num_batches_tracked when training"""
+    lib = _lib.load()
+    dev = gamma.device if gamma is not None else running_mean.device
+    out = torch.empty(4, features, device=dev, dtype=torch.float32)
+    _lib.check(lib.sgcn_bn_fwd_finalize(
+        _d(stats), _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(nbt, torch.int64),
+        _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), features, float(count), float(momentum), float(eps),
+        1 if training else 0, _stream()), "bn forward finalize")
+    return out[0], out[1], out[2], out[3]
+
+
+def tshift_bwd_finalize(sums, gamma, invstd, C, count, n_batch, training, input_shift=False, want_raw=False):
+    """-> dict(dgamma, dbeta, k1, m1, m2, gx, gy[, raw])"""
+    lib = _lib.load()
+    out = torch.empty(8, C, device=gamma.device, dtype=torch.float32)
+    fn = lib.sgcn_tshift_in_bwd_finalize if input_shift else lib.sgcn_tshift_bwd_finalize
+    _lib.check(fn(_d(sums), _p(gamma), _p(invstd), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), _p(out[4]),
+                  _p(out[5]), _p(out[6]), _p(out[7]) if want_raw else None, C, float(count), float(n_batch),
+                  1 if training else 0, _stream()), "tshift backward finalize")
+    return dict(dgamma=out[0], dbeta=out[1], k1=out[2], m1=out[3], m2=out[4], gx=out[5], gy=out[6], raw=out[7])
+
+
+def bn1d_bwd_finalize(vd_sums, gamma, mean, invstd, V, D, count, training):
+    """-> dict(dgamma, dbeta, alpha, beta, gamma, dbias)"""
+    lib = _lib.load()
+    out = torch.empty(5, V * D, device=gamma.device, dtype=torch.float32)
+    dbias = torch.empty(D, device=gamma.device, dtype=torch.float32)
+    _lib.check(lib.sgcn_bn1d_bwd_finalize(_d(vd_sums), _p(gamma), _p(mean), _p(invstd), _p(out[0]), _p(out[1]),
+                                          _p(out[2]), _p(out[3]), _p(out[4]), _p(dbias), V, D, float(count),
+                                          1 if training else 0, _stream()), "bn1d backward finalize")
+    return dict(dgamma=out[0], dbeta=out[1], alpha=out[2], beta=out[3], gamma=out[4], dbias=dbias)
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core kernels
+def rowgemm(pro, epi, *, in0, out, wimg, groups, V, K, N, T=1, in1=None, pro_a=None, pro_b=None, pro_c=None, bias=None,
+            epi_a=None, epi_b=None, res=None, res2=None, res2m=None, xin=None, stats=None, red0=None, relu=0):
+    lib = _lib.load()
+    p = SgcnRowGemm(in0=_p(in0, name="in0"), in1=_p(in1), out=_p(out, name="out"), wimg=_p(wimg), pro_a=_p(pro_a),
+                    pro_b=_p(pro_b), pro_c=_p(pro_c), bias=_p(bias), epi_a=_p(epi_a), epi_b=_p(epi_b), res=_p(res),
+                    res2=_p(res2), res2m=_p(res2m), xin=_p(xin), stats=_d(stats), red0=_d(red0), groups=int(groups),
+                    V=V, G=groups_per_tile(V), T=int(T), K=K, N=N, relu=int(relu))
+    _lib.check(lib.sgcn_rowgemm(ctypes.byref(p), pro, epi, _stream()), "rowgemm")
+
+
+def wgrad(mode, *, a_src, b_src, dw, groups, V, CA, CB, T=1, a_tab0=None, b_src2=None, b_tab0=None, b_tab1=None,
+          b_tab2=None):
+    lib = _lib.load()
+    p = SgcnWgrad(a_src=_p(a_src), a_tab0=_p(a_tab0), b_src=_p(b_src), b_src2=_p(b_src2), b_tab0=_p(b_tab0),
+                  b_tab1=_p(b_tab1), b_tab2=_p(b_tab2), dw=_p(dw), groups=int(groups), V=V, G=groups_per_tile(V),
+                  T=int(T), CA=CA, CB=CB)
+    _lib.check(lib.sgcn_wgrad(ctypes.byref(p), mode, _stream()), "wgrad")
+
+
+# ------------------------------------------------------------------------------------------------ SIMT kernels
+def bn_res_relu_fwd(z, res, h, scale, shift, stats_out, rows, V, D, relu=1):
+    lib = _lib.load()
+    _lib.check(lib.sgcn_bn_res_relu_fwd(_p(z), _p(res), _p(h), _p(scale), _p(shift), _d(stats_out), int(rows), V, D,
+                                        int(relu), _stream()), "bn_res_relu_fwd")
+
+
+def tshift_fwd(mode, *, q, ypos_eff, n_samples, T_in, T_out, V, C, stride, res=None, out=None, scale=None, shift=None,
+               stats=None, relu=0):
+    lib = _lib.load()
+    p = SgcnTShift(q=_p(q), res=_p(res), out=_p(out), ypos_eff=_p(ypos_eff), scale=_p(scale), shift=_p(shift),
+                   stats=_d(stats), n_samples=int(n_samples), T_in=T_in, T_out=T_out, V=V, C=C, stride=stride,
+                   relu=int(relu))
+    _lib.check(lib.sgcn_tshift_fwd(ctypes.byref(p), mode, _stream()), "tshift_fwd")
+
+
+def tshift_bwd(mode, *, q, gy, ypos_eff, mean, invstd, n_samples, T_in, T_out, V, C, stride, y=None, relu=0, k1=None,
+               m1=None, m2=None, sums=None, dpre=None, dbias=None):
+    lib = _lib.load()
+    p = SgcnTShiftBwd(q=_p(q), gy=_p(gy), y=_p(y), ypos_eff=_p(ypos_eff), mean=_p(mean), invstd=_p(invstd), k1=_p(k1),
+                      m1=_p(m1), m2=_p(m2), sums=_d(sums), dpre=_p(dpre), dbias=_d(dbias), n_samples=int(n_samples),
+                      T_in=T_in, T_out=T_out, V=V, C=C, stride=stride, relu=int(relu))
+    _lib.check(lib.sgcn_tshift_bwd(ctypes.byref(p), mode, _stream()), "tshift_bwd")
+
+
+def tshift_in_bwd(mode, *, dp, h, ypos_eff, mean, invstd, n_samples, T, V, C, scale=None, shift=None, k1=None, m1=None,
+                  m2=None, z=None, zmean=None, zinvstd=None, sums=None, vd_sums=None, gh=None, relu_h=0):
+    lib = _lib.load()
+    p = SgcnTShiftInBwd(dp=_p(dp), h=_p(h), z=_p(z), ypos_eff=_p(ypos_eff), mean=_p(mean), invstd=_p(invstd),
+                        scale=_p(scale), shift=_p(shift), k1=_p(k1), m1=_p(m1), m2=_p(m2), zmean=_p(zmean),
+                        zinvstd=_p(zinvstd), sums=_d(sums), vd_sums=_d(vd_sums), gh=_p(gh), n_samples=int(n_samples),
+                        T=T, V=V, C=C, relu_h=int(relu_h))
+    _lib.check(lib.sgcn_tshift_in_bwd(ctypes.byref(p), mode, _stream()), "tshift_in_bwd")
+
+
+def channel_stats(x, stats, rows, C):
+    lib = _lib.load()
+    _lib.check(lib.sgcn_channel_stats(_p(x), _d(stats), int(rows), C, _stream()), "channel_stats")
+
+
+def relu_bn1d_bwd_stats(g, h, z, zmean, zinvstd, gh, vd_sums, groups, V, C):
+    lib = _lib.load()
+    _lib.check(lib.sgcn_relu_bn1d_bwd_stats(_p(g), _p(h), _p(z), _p(zmean), _p(zinvstd), _p(gh), _d(vd_sums),
+                                            int(groups), V, C, _stream()), "relu_bn1d_bwd_stats")
+
+
+def relu_mask_grad(g, y):
+    lib = _lib.load()
+    out = torch.empty_like(g)
+    _lib.check(lib.sgcn_relu_mask_grad(_p(g), _p(y), _p(out), g.numel(), _stream()), "relu_mask_grad")
+    return out

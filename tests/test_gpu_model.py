@@ -1,0 +1,78 @@
+"""Whole-model parity (config 2: NTU-60 inference, config 3: MediaPipe training) at sizes the oracle finishes in seconds."""
+import copy
+
+import pytest
+import torch
+
+from oracle import model_ref
+from util import fill_pair, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(num_class, V, M, device):
+    from shiftgcn_b200.modules import Model
+    graph = "graph.ntu_rgb_d.Graph" if V == 25 else "graph.mediapipe_pose.Graph"
+    mod = Model(num_class=num_class, num_point=V, num_person=M, graph=graph, graph_args=dict(labeling_mode="spatial"))
+    ref = model_ref.RefModel(num_class=num_class, num_point=V, num_person=M)
+    fill_pair(mod, ref)
+    return mod.to(device), ref.double()
+
+
+def _calibrate(ref, mod, x):
+    """give every BN realistic running statistics (one train-mode pass with momentum 1 on the oracle)"""
+    ref.train()
+    for m in ref.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.momentum = 1.0
+    with torch.no_grad():
+        ref(x.double())
+    for m in ref.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.momentum = 0.1
+    sd = {k: v.float() if v.dtype.is_floating_point else v for k, v in ref.state_dict().items()}
+    mod.load_state_dict(sd)
+
+
+@pytest.mark.parametrize("num_class,V,M", [(60, 25, 2), (2, 33, 1)])
+def test_model_eval_logits_and_top1(cuda_device, num_class, V, M):
+    mod, ref = _build(num_class, V, M, cuda_device)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 3, 32, V, M, generator=g)
+    _calibrate(ref, mod, x)
+    mod.eval(), ref.eval()
+    with torch.no_grad():
+        out = mod(x.to(cuda_device))
+        want = ref(x.double())
+    assert rel_err(out, want) < 1e-2
+    assert torch.equal(out.argmax(1).cpu(), want.argmax(1))
+
+
+@pytest.mark.parametrize("num_class,V,M", [(60, 25, 2), (2, 33, 1)])
+def test_model_train_step(cuda_device, num_class, V, M):
+    mod, ref = _build(num_class, V, M, cuda_device)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(4, 3, 32, V, M, generator=g)
+    label = torch.randint(0, num_class, (4,), generator=g)
+    mod.train(), ref.train()
+    model_ref.TF32_EMULATION = True
+    try:
+        loss_r = torch.nn.functional.cross_entropy(ref(x.double()), label)
+        loss_r.backward()
+    finally:
+        model_ref.TF32_EMULATION = False
+    loss = torch.nn.functional.cross_entropy(mod(x.to(cuda_device)), label.to(cuda_device))
+    loss.backward()
+    assert abs(loss.item() - loss_r.item()) < 2e-3 * max(1.0, abs(loss_r.item()))
+    grads_r = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+    worst = {}
+    for name, p in mod.named_parameters():
+        if not p.requires_grad or name.endswith("pos"):
+            continue
+        assert p.grad is not None, name
+        want = grads_r[name]
+        scale = max(want.abs().max().item(), 1e-30)
+        err = (p.grad.double().cpu() - want).abs().max().item()
+        worst[name] = err / scale if scale > 1e-8 else 0.0
+    bad = {k: v for k, v in worst.items() if v > 2e-2}
+    assert not bad, f"gradient mismatch: {sorted(bad.items(), key=lambda kv: -kv[1])[:8]}"

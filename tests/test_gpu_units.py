@@ -1,0 +1,141 @@
+"""Module-level parity of the fused CUDA path against the oracle (oracle/model_ref.py, CPU fp64).
+
+Two comparisons per case:
+  * vs the oracle with TF32 operand emulation  -> separates kernel bugs from TF32 rounding (tolerance 2e-4),
+  * vs the exact oracle                        -> the north star's TF32 bar: relative error <= 1e-2.
+Quantities that involve no tensor-core contraction (BN statistics, shift tables) are checked at 1e-5.
+"""
+import copy
+
+import pytest
+import torch
+
+from oracle import model_ref
+from util import check_ypos_grad, fill_pair, raw_pos_log, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_EMU = 2e-4
+TOL_TF32 = 1e-2
+
+
+def _run_ref(ref, x, go, train, emulate):
+    model_ref.TF32_EMULATION = emulate
+    try:
+        ref = copy.deepcopy(ref).double()
+        ref.train(train)
+        xr = x.double().clone().requires_grad_(True)
+        with raw_pos_log(ref) as log:
+            out = ref(xr)
+            out.backward(go.double())
+        grads = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+        bufs = {k: b.clone() for k, b in ref.named_buffers()}
+        return out.detach(), xr.grad, grads, bufs, log.raw
+    finally:
+        model_ref.TF32_EMULATION = False
+
+
+def _compare(mod, ref, x, go, train, device, check_input_grad=True):
+    mod = mod.to(device)
+    mod.train(train)
+    xc = x.to(device).requires_grad_(True)
+    out = mod(xc)
+    out.backward(go.to(device))
+    torch.cuda.synchronize()
+    for emulate, tol in ((True, TOL_EMU), (False, TOL_TF32)):
+        out_r, gx_r, grads_r, bufs_r, raw = _run_ref(ref, x, go, train, emulate)
+        assert out.shape == out_r.shape
+        assert rel_err(out, out_r) < tol, f"output (emulate={emulate})"
+        if check_input_grad:
+            assert rel_err(xc.grad, gx_r) < tol, f"input grad (emulate={emulate})"
+        for name, p in mod.named_parameters():
+            if not p.requires_grad:
+                continue
+            assert p.grad is not None, f"{name}: no gradient"
+            want = grads_r[name]
+            if name.endswith("ypos"):
+                if emulate:
+                    check_ypos_grad(name, p.grad, want, raw.get(name))
+                continue
+            if name.endswith("xpos"):
+                assert torch.count_nonzero(p.grad).item() == 0
+                continue
+            scale = max(want.abs().max().item(), 1e-30)
+            err = (p.grad.double().cpu() - want).abs().max().item()
+            # gradients that are analytically ~0 (bias before a train-mode BN) are compared absolutely
+            floor = 1e-6 * max(go.abs().sum().item(), 1.0)
+            assert err < tol * scale + floor, f"grad {name}: err {err:.3e} scale {scale:.3e} (emulate={emulate})"
+        if train:
+            for name, b in mod.named_buffers():
+                if b.dtype.is_floating_point:
+                    assert rel_err(b, bufs_r[name]) < (1e-5 if "running" in name and emulate else tol), f"buffer {name}"
+                else:
+                    assert torch.equal(b.cpu(), bufs_r[name]), f"buffer {name}"
+
+
+def _inputs(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g), None
+
+
+@pytest.mark.parametrize("train", [True, False])
+@pytest.mark.parametrize("C,D,V,n,T", [(64, 64, 25, 2, 12), (64, 128, 25, 2, 7), (128, 128, 33, 1, 9), (128, 256, 25, 1, 6),
+                                       (256, 256, 25, 1, 6), (3, 64, 25, 2, 8)])
+def test_shift_gcn(cuda_device, C, D, V, n, T, train):
+    from shiftgcn_b200.modules import Shift_gcn
+    torch.manual_seed(1)
+    mod = Shift_gcn(C, D, None, num_point=V)
+    ref = model_ref.RefShiftGcn(C, D, None, num_point=V)
+    fill_pair(mod, ref)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, C, T, V, generator=g)
+    go = torch.randn(n, D, T, V, generator=g)
+    _compare(mod, ref, x, go, train, cuda_device)
+
+
+@pytest.mark.parametrize("train", [True, False])
+@pytest.mark.parametrize("C,V,n,T,stride", [(64, 25, 2, 12, 1), (64, 25, 2, 13, 2), (128, 33, 1, 10, 2), (256, 25, 1, 8, 1)])
+def test_shift_tcn(cuda_device, C, V, n, T, stride, train):
+    from shiftgcn_b200.modules import Shift_tcn
+    torch.manual_seed(1)
+    mod = Shift_tcn(C, C, stride=stride)
+    ref = model_ref.RefShiftTcn(C, C, stride=stride)
+    fill_pair(mod, ref)
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(n, C, T, V, generator=g)
+    go = torch.randn(n, C, T // stride, V, generator=g)
+    _compare(mod, ref, x, go, train, cuda_device)
+
+
+@pytest.mark.parametrize("train", [True, False])
+@pytest.mark.parametrize("C,D,V,n,T,stride,residual", [
+    (64, 64, 25, 2, 12, 1, True),        # identity unit -> UnitFn (fully fused)
+    (128, 128, 33, 1, 9, 1, True),
+    (256, 256, 25, 1, 6, 1, True),
+    (64, 128, 25, 2, 12, 2, True),       # strided unit, conv residual
+    (3, 64, 25, 2, 10, 1, False),        # first layer
+])
+def test_tcn_gcn_unit(cuda_device, C, D, V, n, T, stride, residual, train):
+    from shiftgcn_b200.modules import TCN_GCN_unit
+    torch.manual_seed(1)
+    mod = TCN_GCN_unit(C, D, None, stride=stride, residual=residual, num_point=V)
+    ref = model_ref.RefUnit(C, D, None, stride=stride, residual=residual, num_point=V)
+    fill_pair(mod, ref)
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(n, C, T, V, generator=g)
+    go = torch.randn(n, D, T // stride, V, generator=g)
+    _compare(mod, ref, x, go, train, cuda_device)
+
+
+def test_channels_last_input_is_zero_copy(cuda_device):
+    from shiftgcn_b200.modules import to_rows
+    x = torch.randn(2, 64, 6, 25, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    assert to_rows(x).data_ptr() == x.data_ptr()
+
+
+def test_no_cpu_path():
+    """the product fails loudly on CPU tensors instead of falling back"""
+    from shiftgcn_b200.modules import Shift_gcn
+    mod = Shift_gcn(64, 64, None).cpu()
+    with pytest.raises(RuntimeError):
+        mod(torch.randn(1, 64, 4, 25))
