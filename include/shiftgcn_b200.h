@@ -1,0 +1,211 @@
+/* shiftgcn_b200.h -- C ABI of the B200-native Shift-GCN hot path (libshiftgcn_b200.so).
+ *
+ * This is the drop-in boundary for the reference's only native interface, the pybind11 module `shift_cuda`
+ * (model/Temporal_shift/cuda/shift_cuda.cpp:44-47: forward / backward), widened to the fused spatial
+ * (model/shift_gcn.py:77-142) and temporal (model/shift_gcn.py:48-74) units that the reference runs as chains of
+ * torch library kernels.  Conventions:
+ *   - extern "C", plain pointers and sizes, no C++ / torch types; every pointer is a DEVICE pointer unless noted;
+ *   - every entry point returns 0 on success or a negative code; sgcn_last_error() gives the message (per host thread);
+ *   - kernels are enqueued on the `stream` argument (a cudaStream_t), never synchronise, allocate nothing, and are
+ *     CUDA-graph capturable.  The caller owns all buffers (the reference allocates outputs with at::zeros inside the
+ *     extension, shift_cuda_kernel.cu:408,440,480-481; here nothing needs pre-zeroing except the fp64 reduction
+ *     scratch, which every finalize call hands back zeroed);
+ *   - activations of the fused entry points are channels-last rows [(n, t, v), C] in fp32, the reference's own
+ *     internal layout (model/shift_gcn.py:123); the *_nchw entry points keep the reference extension's contiguous
+ *     (N, C, H, W) layout and its float / double dispatch (shift_cuda_kernel.cu:413).
+ * Built for sm_100a only.  The reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ */
+#ifndef SHIFTGCN_B200_H_
+#define SHIFTGCN_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- library ---------------------------------- */
+int sgcn_abi_version(void);
+const char* sgcn_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x, error otherwise (there is no fallback path) */
+int sgcn_device_check(void);
+/* tcgen05 descriptor self test (tests only): mode 0: D[128,N] = A[128,K] * B[N,K]^T; mode 1: D[128,N] = A[128,M]^T * B[128,N] */
+int sgcn_selftest_umma(const float* a, const float* b, float* d, int mode, int K, int N, int M, void* stream);
+
+/* ---------------------------------------------------------------- stand-alone temporal shift (NCHW) ------- */
+/* Replaces shift_cuda.forward (shift_cuda.cpp:19-23 -> shift_cuda_kernel.cu:405-431, kernel K1 :12-76).
+ * out[n,c,h,w] = bilinear sample of in[n,c] at (h*stride + ypos[c], w + xpos[c]), zero padded; out height = h/stride.
+ * ypos already includes the +0.5 the Python op adds for stride != 1 (cuda/shift.py:14-19). */
+int sgcn_shift_fwd_nchw_f32(const float* in, float* out, const float* xpos, const float* ypos, long long n, int c,
+                            int h, int w, int stride, void* stream);
+int sgcn_shift_fwd_nchw_f64(const double* in, double* out, const double* xpos, const double* ypos, long long n, int c,
+                            int h, int w, int stride, void* stream);
+/* Replaces shift_cuda.backward (shift_cuda.cpp:25-42 -> shift_cuda_kernel.cu:433-523): K2/K3 (grad_in), K4 + the
+ * mean/sum reductions + K5 (grad_xpos = 0, grad_ypos = sign * 0.01 or 1e-4).  raw_pos (optional, [2][c]) receives the
+ * reduced sums before K5; scratch is a zeroed double[2*c] that is handed back zeroed. */
+int sgcn_shift_bwd_nchw_f32(const float* grad_out, const float* in, const float* xpos, const float* ypos,
+                            float* grad_in, float* grad_xpos, float* grad_ypos, float* raw_pos, double* scratch,
+                            long long n, int c, int h, int w, int stride, void* stream);
+int sgcn_shift_bwd_nchw_f64(const double* grad_out, const double* in, const double* xpos, const double* ypos,
+                            double* grad_in, double* grad_xpos, double* grad_ypos, double* raw_pos, double* scratch,
+                            long long n, int c, int h, int w, int stride, void* stream);
+
+/* ---------------------------------------------------------------- fused tensor-core contractions ---------- */
+typedef struct SgcnRowGemm {
+  const float* in0;    /* SPATIAL: x   | LERP: h      | PLAIN: rows       | DY: grad wrt gcn output (after ReLU mask) */
+  const float* in1;    /* DY: z (pre-BN spatial output)                                                   */
+  float* out;          /* [rows, N]                                                                       */
+  const float* wimg;   /* canonical weight image from sgcn_prep_weight_image                              */
+  const float* pro_a;  /* SPATIAL: tanh(mask)+1 [V,K] | LERP: BN scale [K] | DY: alpha [V,K]               */
+  const float* pro_b;  /* LERP: BN shift [K]          | DY: beta  [V,K]                                    */
+  const float* pro_c;  /* LERP: effective ypos [K]    | DY: gamma [V,K]                                    */
+  const float* bias;   /* [N] or NULL                                                                     */
+  const float* epi_a;  /* ROT_FUSED: BN scale [V,N]   | SPATIAL_BWD: tanh(mask)+1 [V,N]                    */
+  const float* epi_b;  /* ROT_FUSED: BN shift [V,N]                                                        */
+  const float* res;    /* ROT_FUSED: residual rows [rows,N] | SPATIAL_BWD: gradient added as-is (or NULL)  */
+  const float* res2;   /* SPATIAL_BWD: block-residual gradient g_y (or NULL)                               */
+  const float* res2m;  /* SPATIAL_BWD: block output y; g_y counts where y > 0                              */
+  const float* xin;    /* SPATIAL_BWD: unit input x (for the mask gradient)                                */
+  double* stats;       /* ROT_RAW: per-(v,n) {sum, sum of squares}, accumulated                            */
+  double* red0;        /* SPATIAL_BWD: raw mask gradient [V,N], accumulated                                */
+  long long groups;    /* number of (n,t) groups = rows / V                                                */
+  int V;               /* joints per group                                                                 */
+  int G;               /* groups per tile, G*V <= 128                                                      */
+  int T;               /* frames per sample (LERP bounds)                                                  */
+  int K;               /* contraction width = input channels (64/128/256)                                  */
+  int N;               /* output channels (64/128/256)                                                     */
+  int relu;            /* ROT_FUSED / LINEAR: apply ReLU                                                   */
+} SgcnRowGemm;
+
+enum { SGCN_PRO_SPATIAL = 0, SGCN_PRO_LERP = 1, SGCN_PRO_PLAIN = 2, SGCN_PRO_DY = 3 };
+enum { SGCN_EPI_ROT_RAW = 0, SGCN_EPI_ROT_FUSED = 1, SGCN_EPI_LINEAR = 2, SGCN_EPI_SPATIAL_BWD = 3 };
+
+int sgcn_rowgemm(const SgcnRowGemm* params, int prologue, int epilogue, void* stream);
+
+typedef struct SgcnWgrad {
+  const float* a_src;   /* SPATIAL: unit input x [rows, CA]            | TEMPORAL: dpre [rows, CA] (grad wrt conv output) */
+  const float* a_tab0;  /* SPATIAL: tanh(mask)+1 [V, CA]                                                              */
+  const float* b_src;   /* SPATIAL: grad wrt gcn output gh [rows, CB]  | TEMPORAL: tcn input h [rows, CB]              */
+  const float* b_src2;  /* SPATIAL: pre-BN output z [rows, CB]                                                         */
+  const float* b_tab0;  /* SPATIAL: alpha [V, CB]                      | TEMPORAL: BN scale [CB]                       */
+  const float* b_tab1;  /* SPATIAL: beta  [V, CB]                      | TEMPORAL: BN shift [CB]                       */
+  const float* b_tab2;  /* SPATIAL: gamma [V, CB]                      | TEMPORAL: effective ypos [CB]                 */
+  float* dw;            /* [CA, CB] fp32, accumulated with atomics (caller zeroes it)                                  */
+  long long groups;
+  int V, G, T;
+  int CA, CB;
+} SgcnWgrad;
+
+enum { SGCN_WG_SPATIAL = 0, SGCN_WG_TEMPORAL = 1 };
+
+int sgcn_wgrad(const SgcnWgrad* params, int mode, void* stream);
+
+/* ---------------------------------------------------------------- bandwidth-bound SIMT kernels ------------ */
+/* forward temporal shift with stride: s = Shift(q); mode 0 -> stats[c] += {sum, sumsq}; mode 1 -> out = [relu](s*scale+shift+res) */
+typedef struct SgcnTShift {
+  const float* q;         /* [n, T_in, V, C]                       */
+  const float* res;       /* [n, T_out, V, C] or NULL (mode 1)     */
+  float* out;             /* [n, T_out, V, C] (mode 1)             */
+  const float* ypos_eff;  /* [C] ypos (+0.5 when stride != 1)      */
+  const float* scale;     /* [C] folded BN scale (mode 1)          */
+  const float* shift;     /* [C] folded BN shift (mode 1)          */
+  double* stats;          /* [C][2] (mode 0)                       */
+  long long n_samples;
+  int T_in, T_out, V, C, stride, relu;
+} SgcnTShift;
+
+/* backward of  out = [relu](BN(Shift(q)) + res):
+ * mode 0: sums[c][5] += { g, g*shat, g*dq, dq, shat*dq };  mode 1: dpre = [q>0] * Shift^T(k1*(g - m1 - shat*m2)), dbias[c] += dpre */
+typedef struct SgcnTShiftBwd {
+  const float* q;
+  const float* gy;        /* grad wrt out [n, T_out, V, C]                      */
+  const float* y;         /* out (ReLU mask source), needed when relu != 0      */
+  const float* ypos_eff;
+  const float* mean;      /* [C] BN mean used in the forward                    */
+  const float* invstd;    /* [C]                                                */
+  const float* k1;        /* [C] gamma*invstd        (mode 1)                   */
+  const float* m1;        /* [C] sum(g)/count  or 0  (mode 1)                   */
+  const float* m2;        /* [C] sum(g*shat)/count or 0 (mode 1)                */
+  double* sums;           /* [C][5] (mode 0)                                    */
+  float* dpre;            /* [n, T_in, V, C] (mode 1)                           */
+  double* dbias;          /* [C] (mode 1)                                       */
+  long long n_samples;
+  int T_in, T_out, V, C, stride, relu;
+} SgcnTShiftBwd;
+
+/* backward of  p = Shift_1(BN(h)):  du = Shift^T(dp)
+ * mode 0: sums[c][3] += { du, du*hhat, dp*dU };
+ * mode 1: gh = [h>0] * k1*(du - m1 - hhat*m2);  vd_sums[v,c][2] += { gh, gh*zhat } when z != NULL */
+typedef struct SgcnTShiftInBwd {
+  const float* dp;        /* grad wrt p [n, T, V, C]                            */
+  const float* h;         /* tcn input (gcn output)                             */
+  const float* z;         /* pre-BN spatial output or NULL                      */
+  const float* ypos_eff;
+  const float* mean;      /* [C] BN(h) statistics                               */
+  const float* invstd;
+  const float* scale;     /* [C] folded BN(h) scale / shift (mode 0)            */
+  const float* shift;
+  const float* k1;
+  const float* m1;
+  const float* m2;
+  const float* zmean;     /* [V, C] BN1d statistics of z (mode 1, z != NULL)    */
+  const float* zinvstd;
+  double* sums;           /* [C][3] (mode 0)                                    */
+  double* vd_sums;        /* [V, C][2] (mode 1)                                 */
+  float* gh;              /* [n, T, V, C] (mode 1)                              */
+  long long n_samples;
+  int T, V, C, relu_h;
+} SgcnTShiftInBwd;
+
+int sgcn_bn_res_relu_fwd(const float* z, const float* res, float* h, const float* scale, const float* shift,
+                         double* stats_out, long long rows, int V, int D, int relu, void* stream);
+int sgcn_tshift_fwd(const SgcnTShift* p, int mode, void* stream);
+int sgcn_tshift_bwd(const SgcnTShiftBwd* p, int mode, void* stream);
+int sgcn_tshift_in_bwd(const SgcnTShiftInBwd* p, int mode, void* stream);
+
+/* stats[c][2] += {sum, sumsq} over rows */
+int sgcn_channel_stats(const float* x, double* stats, long long rows, int C, void* stream);
+/* gh = g*[h>0]; vd_sums[v,c][2] += {gh, gh*zhat} */
+int sgcn_relu_bn1d_bwd_stats(const float* g, const float* h, const float* z, const float* zmean, const float* zinvstd,
+                             float* gh, double* vd_sums, long long groups, int V, int C, void* stream);
+/* out = g*[y>0] */
+int sgcn_relu_mask_grad(const float* g, const float* y, float* out, long long numel, void* stream);
+
+/* ---- small per-feature kernels (prep.cu) ---- */
+
+/* batch-norm forward finalize: {sum, sumsq} -> mean/invstd/scale/shift, running-stat update (momentum, unbiased var),
+ * num_batches_tracked += 1, stats cleared.  training == 0: scale/shift from the running statistics, nothing updated. */
+int sgcn_bn_fwd_finalize(double* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                         long long* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
+                         int features, double count, double momentum, double eps, int training, void* stream);
+
+/* backward finalize of the output shift + BN: from sums[c][5] -> dgamma, dbeta, k1, m1, m2 and the K5-constrained
+ * position gradient (raw = k1*(S2 - m1*S3 - m2*S4) / n_batch).  raw_out (optional) receives the raw means. */
+int sgcn_tshift_bwd_finalize(double* sums, const float* gamma, const float* invstd, float* dgamma, float* dbeta,
+                             float* k1, float* m1, float* m2, float* grad_xpos, float* grad_ypos, float* raw_out,
+                             int C, double count, double n_batch, int training, void* stream);
+
+/* backward finalize of BN + input shift: sums[c][3] -> dgamma, dbeta, k1, m1, m2, K5-constrained position gradient */
+int sgcn_tshift_in_bwd_finalize(double* sums, const float* gamma, const float* invstd, float* dgamma, float* dbeta,
+                                float* k1, float* m1, float* m2, float* grad_xpos, float* grad_ypos, float* raw_out,
+                                int C, double count, double n_batch, int training, void* stream);
+
+/* backward finalize of the BN1d over (v,d): vd_sums[f][2] -> dgamma, dbeta, alpha/beta/gamma tables of
+ * dz = alpha*gh + beta*z + gamma, and the Linear_bias gradient dbias[d] = sum_v k*(S_g - count*m1). */
+int sgcn_bn1d_bwd_finalize(double* vd_sums, const float* gamma, const float* mean, const float* invstd, float* dgamma,
+                           float* dbeta, float* alpha, float* beta, float* gam, float* dbias, int V, int D,
+                           double count, int training, void* stream);
+
+/* maskmul = tanh(mask) + 1 */
+int sgcn_mask_prepare(const float* mask, float* maskmul, int n, void* stream);
+/* dmask = raw * (1 - tanh(mask)^2); raw cleared */
+int sgcn_mask_grad_finalize(double* raw, const float* mask, float* dmask, int n, void* stream);
+
+/* canonical (SWIZZLE_128B, TF32-rounded) image of B[n][k] = src[n*ld_n + k*ld_k], chunked by 64 k */
+int sgcn_prep_weight_image(const float* src, long long ld_n, long long ld_k, int N, int K, float* image, void* stream);
+
+/* double -> float copy of a reduction buffer (+ clear) */
+int sgcn_reduce_export(double* src, float* dst, int n, double scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHIFTGCN_B200_H_ */

@@ -1,0 +1,137 @@
+"""Generate tests/golden/* from the REAL reference (TEST INFRASTRUCTURE ONLY; build container only).
+
+    python -m oracle.make_golden
+
+imports /root/reference through oracle/ref_import.py (CPU, fp64), gives every module the deterministic
+non-degenerate weights of oracle.model_ref.fill_value, and stores inputs + outputs + gradients.  The reference
+ships no fixtures of its own, so these files are what pins parity on the GPU box, where
+/root/reference does not exist.  The temporal shift inside Shift_tcn / TCN_GCN_unit / Model comes from the oracle
+restatement (the reference's CUDA extension cannot run here); that restatement is pinned separately against the
+reference's compiled kernels on the GPU (tests/test_gpu_reference_ext.py) and against the C oracle
+(``shift_op.npz`` below is produced by oracle/shift_oracle.c).
+"""
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import model_ref, ref_import, shift_c, shift_torch
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _run(module, x, go, train):
+    module.train(train)
+    xr = x.clone().requires_grad_(True)
+    shift_torch.RAW_POS_LOG = {}
+    out = module(xr)
+    out.backward(go)
+    log, shift_torch.RAW_POS_LOG = shift_torch.RAW_POS_LOG, None
+    rec = {"x": _np(x).astype(np.float32), "go": _np(go).astype(np.float32), "out": _np(out), "gx": _np(xr.grad)}
+    for k, p in module.named_parameters():
+        if p.grad is not None:
+            rec["grad/" + k] = _np(p.grad)
+        if k.endswith("xpos") and id(p) in log:
+            rec["raw/" + k[:-4] + "ypos"] = _np(log[id(p)][1])
+    if train:
+        for k, b in module.named_buffers():
+            rec["buf/" + k] = _np(b)
+    return rec
+
+
+def _f32_inputs(shape_x, shape_go, seed):
+    g = torch.Generator().manual_seed(seed)
+    # inputs are stored (and used) as exactly-representable fp32 values
+    return (torch.randn(*shape_x, generator=g).float().double(), torch.randn(*shape_go, generator=g).float().double())
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_import.load()
+    torch.manual_seed(1)
+
+    # ---- 1. integer gather tables, straight from reference Shift_gcn instances (bit-exact contract)
+    tables = {}
+    for (V, C, D) in [(25, 3, 64), (25, 64, 64), (25, 64, 128), (33, 64, 64), (33, 128, 256)]:
+        m = ref_import.build(ns.Shift_gcn, C, D, None, num_point=V)
+        tables[f"in_{V}_{C}_{D}"] = m.shift_in.data.numpy().astype(np.int64)
+        tables[f"out_{V}_{C}_{D}"] = m.shift_out.data.numpy().astype(np.int64)
+    np.savez_compressed(os.path.join(OUT, "tables.npz"), **tables)
+
+    # ---- 2. state_dict contract of the full models
+    contract = {}
+    for tag, kw in (("ntu60", dict(num_class=60, num_point=25, num_person=2, graph=ns.GRAPH_NTU)),
+                    ("mediapipe", dict(num_class=2, num_point=33, num_person=1, graph=ns.GRAPH_MEDIAPIPE))):
+        m = ref_import.build(ns.Model, graph_args=dict(labeling_mode="spatial"), **kw)
+        contract[tag] = [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()]
+    with open(os.path.join(OUT, "state_dict_contract.json"), "w") as f:
+        json.dump(contract, f)
+
+    # ---- 3. Shift_gcn: pure reference code
+    cases = {"gcn_64_64_v25": (64, 64, 25, 2, 6), "gcn_64_128_v25": (64, 128, 25, 1, 5), "gcn_128_128_v33": (128, 128, 33, 1, 4)}
+    for tag, (C, D, V, n, T) in cases.items():
+        for train in (True, False):
+            m = model_ref.fill_module_(ref_import.build(ns.Shift_gcn, C, D, None, num_point=V)).double()
+            x, go = _f32_inputs((n, C, T, V), (n, D, T, V), 100 + C + D + V)
+            rec = _run(m, x, go, train)
+            rec["meta"] = np.array([C, D, V, n, T, int(train)])
+            np.savez_compressed(os.path.join(OUT, f"{tag}_{'train' if train else 'eval'}.npz"), **rec)
+
+    # ---- 4. TCN_GCN_unit (reference module code + oracle shift)
+    ucases = {"unit_64_64_s1": (64, 64, 25, 2, 8, 1, True), "unit_64_128_s2": (64, 128, 25, 2, 8, 2, True)}
+    for tag, (C, D, V, n, T, s, res) in ucases.items():
+        m = model_ref.fill_module_(ref_import.build(ns.TCN_GCN_unit, C, D, None, stride=s, residual=res, num_point=V)).double()
+        x, go = _f32_inputs((n, C, T, V), (n, D, T // s, V), 200 + C + D + s)
+        rec = _run(m, x, go, True)
+        rec["meta"] = np.array([C, D, V, n, T, s, int(res)])
+        np.savez_compressed(os.path.join(OUT, f"{tag}_train.npz"), **rec)
+
+    # ---- 5. full NTU-60 model, eval, with calibrated BN buffers stored alongside
+    m = model_ref.fill_module_(ref_import.build(ns.Model, num_class=60, num_point=25, num_person=2, graph=ns.GRAPH_NTU,
+                                                graph_args=dict(labeling_mode="spatial"))).double()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 16, 25, 2, generator=g).float().double()
+    bns = [mod for mod in m.modules() if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm)]
+    for b in bns:
+        b.momentum = 1.0
+    m.train()
+    with torch.no_grad():
+        m(x)
+    for b in bns:
+        b.momentum = 0.1
+    m.eval()
+    with torch.no_grad():
+        logits = m(x)
+    rec = {"x": _np(x).astype(np.float32), "logits": _np(logits)}
+    for k, b in m.named_buffers():
+        if b.dtype.is_floating_point:
+            rec["buf/" + k] = _np(b).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "model_ntu60_eval.npz"), **rec)
+
+    # ---- 6. the stand-alone op, from the scalar C oracle
+    rng = np.random.default_rng(6)
+    rec = {}
+    for stride in (1, 2):
+        n, c, h, w = 2, 6, 9, 5
+        x = rng.standard_normal((n, c, h, w)).astype(np.float32).astype(np.float64)
+        go = rng.standard_normal((n, c, h // stride, w)).astype(np.float32).astype(np.float64)
+        xpos = (rng.uniform(-1e-8, 1e-8, c)).astype(np.float32).astype(np.float64)
+        ypos = np.array([0.3, -1.7, 2.0, -3.0, 5.5, 0.0]) + (0.5 if stride != 1 else 0.0)
+        out = shift_c.shift_forward(x, xpos, ypos, stride)
+        gin = shift_c.shift_backward_input(go, xpos, ypos, x.shape, stride)
+        rx, ry = shift_c.shift_backward_pos_raw(x, go, xpos, ypos, stride)
+        _, gy = shift_c.shift_constraint(rx, ry)
+        for k, v in dict(x=x, go=go, xpos=xpos, ypos=ypos, out=out, gin=gin, raw_y=ry, gy=gy).items():
+            rec[f"s{stride}/{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "shift_op.npz"), **rec)
+    total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
+    print(f"wrote {len(os.listdir(OUT))} files, {total / 1e6:.2f} MB -> {OUT}")
+
+
+if __name__ == "__main__":
+    main()

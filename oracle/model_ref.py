@@ -52,9 +52,14 @@ class _Tf32Matmul(torch.autograd.Function):
         return ga, gw
 
 
+TF32_MIN_K = 64      # contractions narrower than this run in exact fp32 in the product (3-channel first layer)
+
+
 def contract(a, w):
     """a [..., K] @ w [K, N]"""
-    return _Tf32Matmul.apply(a, w) if TF32_EMULATION else torch.matmul(a, w)
+    if TF32_EMULATION and a.shape[-1] >= TF32_MIN_K:
+        return _Tf32Matmul.apply(a, w)
+    return torch.matmul(a, w)
 
 
 # --------------------------------------------------------------------------- index tables

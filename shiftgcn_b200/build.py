@@ -19,6 +19,7 @@ NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC",
+    "-I", os.path.join(os.path.dirname(_HERE), "include"),
 ]
 
 
@@ -34,7 +35,9 @@ def sources():
 
 
 def _headers_mtime():
-    return max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh")))
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    hdrs.append(os.path.join(os.path.dirname(_HERE), "include", "shiftgcn_b200.h"))
+    return max(os.path.getmtime(h) for h in hdrs)
 
 
 def _compile(src, verbose):

@@ -12,9 +12,9 @@ namespace sgcn {
 // ------------------------------------------------------------------------------------------------
 // Canonical operand tile ("block"): 128 rows x 32 fp32 (=128 B per row), 8-row groups of 1024 B,
 // the 16-byte chunk index XOR-ed with (row % 8)  == UMMA/TMA SWIZZLE_128B.
-//   * read as a K-major operand   (MN = rows,     K = the 32 channels):  SBO = 1024 B
-//   * read as an MN-major operand (MN = channels, K = rows):            LBO = block stride, SBO = 1024 B
-// A [128 x C] tile is C/32 consecutive blocks of kBlockBytes.
+//   * read as a K-major operand (MN = rows, K = the 32 channels): SBO = 1024 B.
+// A [128 x C] tile is C/32 consecutive blocks of kBlockBytes.  (The MN-major variant used by the weight-gradient
+// contraction has the same block shape but a different swizzle, see canon_off_mn.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kTileRows = 128;
 constexpr int kBlockCh = 32;
@@ -22,6 +22,17 @@ constexpr int kBlockBytes = kTileRows * kBlockCh * 4;  // 16 KiB
 
 __device__ __forceinline__ uint32_t canon_off(int row, int ch) {  // byte offset inside one block
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((ch >> 2) ^ (row & 7)) & 7) << 4) + ((ch & 3) << 2));
+}
+
+// MN-major 32-bit operands (channels contiguous, rows = contraction dimension) must use SWIZZLE_128B_BASE32B:
+// same 128-byte row pitch, but 32-byte chunks XOR-ed with (row % 4), atoms of 4 rows (512 B).
+__device__ __forceinline__ uint32_t canon_off_mn(int row, int ch) {
+  return (uint32_t)(row * 128 + ((((ch >> 3) ^ (row & 3)) & 3) << 5) + ((ch & 7) << 2));
+}
+
+template <bool MN>
+__device__ __forceinline__ uint32_t tile_off(int row, int ch) {
+  return MN ? canon_off_mn(row, ch) : canon_off(row, ch);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -85,14 +96,15 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
                : "memory");
 }
 
-// UMMA shared-memory matrix descriptor (SWIZZLE_128B, version 1).  lbo/sbo in bytes.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+// UMMA shared-memory matrix descriptor (version 1).  lbo/sbo in bytes.
+// layout: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (MN-major 32-bit tiles)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // layout type: SWIZZLE_128B
+  d |= (uint64_t)layout << 61;
   return d;
 }
 

@@ -123,14 +123,14 @@ __global__ void __launch_bounds__(kThreads, NCH == 1 ? 2 : 1) rowgemm_kernel(con
 
       // ---- build the operand chunk
       if (PRO == PRO_SPATIAL) {
-        build_spatial_chunk(sA, (const float*)sU, p.pro_a, K, kc * 64, V, ng, warp, lane);
+        build_spatial_chunk<false>(sA, (const float*)sU, p.pro_a, K, kc * 64, V, ng, warp, lane);
       } else if (PRO == PRO_DY) {
-        build_dy_chunk(sA, (const float*)sU, (const float*)(sU + kTileRows * 256), p.pro_a, p.pro_b, p.pro_c, K,
+        build_dy_chunk<false>(sA, (const float*)sU, (const float*)(sU + kTileRows * 256), p.pro_a, p.pro_b, p.pro_c, K,
                        kc * 64, V, ng, warp, lane);
       } else if (PRO == PRO_LERP) {
-        build_lerp_chunk(sA, p.in0, sLerp, sGrpT, K, kc * 64, V, p.T, g0, rows_valid, warp, lane);
+        build_lerp_chunk<false>(sA, p.in0, sLerp, sGrpT, K, kc * 64, V, p.T, g0, rows_valid, warp, lane);
       } else {
-        build_plain_chunk(sA, p.in0, K, kc * 64, row0, rows_valid, warp, lane);
+        build_plain_chunk<false>(sA, p.in0, K, kc * 64, row0, rows_valid, warp, lane);
       }
       fence_proxy_async();
       __syncthreads();

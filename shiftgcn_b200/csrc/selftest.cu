@@ -38,12 +38,12 @@ selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
     __syncthreads();
     for (int i = tid; i < 128 * M2; i += blockDim.x) {
       int r = i / M2, m = i % M2;
-      *(float*)(sa + (m >> 5) * kBlockBytes + canon_off(r, m & 31)) = to_tf32(a[i]);
+      *(float*)(sa + (m >> 5) * kBlockBytes + canon_off_mn(r, m & 31)) = to_tf32(a[i]);
     }
     (void)mblocks;
     for (int i = tid; i < 128 * N; i += blockDim.x) {
       int r = i / N, n = i % N;
-      *(float*)(sb + (n >> 5) * kBlockBytes + canon_off(r, n & 31)) = to_tf32(b[i]);
+      *(float*)(sb + (n >> 5) * kBlockBytes + canon_off_mn(r, n & 31)) = to_tf32(b[i]);
     }
   }
   fence_proxy_async();
@@ -75,8 +75,8 @@ selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
       const uint32_t idesc = umma_idesc_tf32(128, N, 1, 1);
       uint32_t acc = 0;
       for (int r8 = 0; r8 < 16; ++r8) {  // K = 128 rows, 8 per instruction
-        uint64_t ad = umma_desc(smem_u32(sa) + r8 * 1024, kBlockBytes, 1024);
-        uint64_t bd = umma_desc(smem_u32(sb) + r8 * 1024, kBlockBytes, 1024);
+        uint64_t ad = umma_desc(smem_u32(sa) + r8 * 1024, kBlockBytes, 512, 1);
+        uint64_t bd = umma_desc(smem_u32(sb) + r8 * 1024, kBlockBytes, 512, 1);
         umma_tf32(tmem_base, ad, bd, idesc, acc);
         acc = 1;
       }
@@ -104,7 +104,8 @@ selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
 extern "C" int sgcn_selftest_umma(const float* a, const float* b, float* d, int mode, int K, int N, int M2, void* stream) {
   using namespace sgcn;
   if (mode == 0) {
-    if (K % 32 != 0 || K < 32 || K > 256 || N % 16 != 0 || N < 16 || N > 256) return set_error("selftest: bad K/N");
+    if (K % 32 != 0 || K < 32 || K > 256 || N % 32 != 0 || N < 32 || N > 256) return set_error("selftest: bad K/N");
+    if ((size_t)K * (128 + N) * 4 > 200 * 1024) return set_error("selftest: operands do not fit in shared memory");
   } else {
     if (N % 32 != 0 || N < 32 || N > 256 || M2 < 1 || M2 > 128) return set_error("selftest: bad M/N");
   }

@@ -6,8 +6,9 @@
 //   temporal (autograd of model/shift_gcn.py:69):   A = dpre (grad wrt the conv output, pre-ReLU), B = p (shifted BN(h))
 //            -> temporal_linear.weight.grad [Cout, Cin]
 //
-// Both operands are canonical 128-row tiles read through MN-major UMMA descriptors (the row index is the
-// contraction dimension, 8 rows per instruction).  A CTA owns one (A-channel block, B-channel block) pair and
+// Both operands are 128-row tiles in the SWIZZLE_128B_BASE32B layout (the only one tcgen05 accepts for MN-major
+// 32-bit operands) read through MN-major UMMA descriptors: the row index is the contraction dimension, 8 rows
+// (two 4-row swizzle atoms) per instruction.  A CTA owns one (A-channel block, B-channel block) pair and
 // a strided subset of the row tiles, keeps its partial dW in TMEM across all of them and flushes it once with
 // atomics.  The M extent is always 128: when the A block has only 64 channels the upper 64 TMEM lanes hold
 // don't-care values that are never read back.
@@ -80,12 +81,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const SgcnWgrad p) {
         cp_async_commit();
         cp_async_wait_all();
         __syncthreads();
-        build_spatial_chunk(chunk, (const float*)sS, p.a_tab0, p.CA, a0 + ac, V, ng, warp, lane);
+        build_spatial_chunk<true>(chunk, (const float*)sS, p.a_tab0, p.CA, a0 + ac, V, ng, warp, lane);
         __syncthreads();
       } else {
-        build_plain_chunk(chunk, p.a_src, p.CA, a0 + ac, row0, rows_valid, warp, lane);
+        build_plain_chunk<true>(chunk, p.a_src, p.CA, a0 + ac, row0, rows_valid, warp, lane);
       }
-      if (rows_valid < G * V) zero_tail_rows(chunk, rows_valid, warp, lane);
+      if (rows_valid < G * V) zero_tail_rows<true>(chunk, rows_valid, warp, lane);
     }
     // ---- B operand
     for (int bc = 0; bc < NC; bc += 64) {
@@ -96,13 +97,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const SgcnWgrad p) {
         cp_async_commit();
         cp_async_wait_all();
         __syncthreads();
-        build_dy_chunk(chunk, (const float*)sS, (const float*)(sS + kTileRows * 256), p.b_tab0,
+        build_dy_chunk<true>(chunk, (const float*)sS, (const float*)(sS + kTileRows * 256), p.b_tab0,
                        p.b_tab1, p.b_tab2, p.CB, b0 + bc, V, ng, warp, lane);
         __syncthreads();
       } else {
-        build_lerp_chunk(chunk, p.b_src, sLerp, sGrpT, p.CB, b0 + bc, V, p.T, g0, rows_valid, warp, lane);
+        build_lerp_chunk<true>(chunk, p.b_src, sLerp, sGrpT, p.CB, b0 + bc, V, p.T, g0, rows_valid, warp, lane);
       }
-      if (rows_valid < G * V) zero_tail_rows(chunk, rows_valid, warp, lane);
+      if (rows_valid < G * V) zero_tail_rows<true>(chunk, rows_valid, warp, lane);
     }
     fence_proxy_async();
     __syncthreads();
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const SgcnWgrad p) {
       const uint32_t sa = smem_u32(sA), sb = smem_u32(sB);
 #pragma unroll
       for (int r8 = 0; r8 < 16; ++r8)
-        umma_tf32(tmem_base, umma_desc(sa + r8 * 1024, kBlockBytes, 1024), umma_desc(sb + r8 * 1024, kBlockBytes, 1024),
+        umma_tf32(tmem_base, umma_desc(sa + r8 * 1024, kBlockBytes, 512, 1), umma_desc(sb + r8 * 1024, kBlockBytes, 512, 1),
                   idesc, (first && r8 == 0) ? 0u : 1u);
       tc_commit(&bar_mma);
     }

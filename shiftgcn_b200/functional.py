@@ -212,8 +212,7 @@ class SpatialFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, res, W, bias, mask, gamma, beta, module):
         training = module.training
-        need_grad = torch.is_grad_enabled() and any(
-            t is not None and t.requires_grad for t in (x, res, W, bias, mask, gamma, beta))
+        need_grad = any(ctx.needs_input_grad)
         h, saved = spatial_forward(x, res, W, bias, mask, module.bn, training, module._ws,
                                    fuse_eval=(not training and not need_grad))
         ctx.module = module
@@ -265,8 +264,7 @@ class UnitFn(torch.autograd.Function):
         gcn, tcn = unit.gcn1, unit.tcn1
         training = unit.training
         n, T, V, C = x.shape
-        need_grad = torch.is_grad_enabled() and any(
-            t.requires_grad for t in (x, W, bias, mask, g1, b1, ga, ba, ypos_in, Wt, bt, ypos_out, gb, bb))
+        need_grad = any(ctx.needs_input_grad)
         h_stats = tcn._ws.get("bn_a", 2 * C, x.device) if training else None
         h, s_saved = spatial_forward(x, None, W, bias, mask, gcn.bn, training, gcn._ws,
                                      fuse_eval=(not training and not need_grad), h_stats=h_stats)

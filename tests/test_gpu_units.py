@@ -15,7 +15,12 @@ from util import check_ypos_grad, fill_pair, raw_pos_log, rel_err
 
 pytestmark = pytest.mark.gpu
 
-TOL_EMU = 2e-4
+# the few sub-blocks still served by library kernels (down / residual 1x1 convs) must not silently use TF32,
+# otherwise they would be compared against an oracle that does not emulate it
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+TOL_EMU = 1e-3      # TF32 rounding is discontinuous: ~1e-7 operand differences flip a few roundings (noise floor ~3e-4)
 TOL_TF32 = 1e-2
 
 
