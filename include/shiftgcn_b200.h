@@ -29,6 +29,9 @@ const char* sgcn_last_error(void);
 int sgcn_device_check(void);
 /* tcgen05 descriptor self test (tests only): mode 0: D[128,N] = A[128,K] * B[N,K]^T; mode 1: D[128,N] = A[128,M]^T * B[128,N] */
 int sgcn_selftest_umma(const float* a, const float* b, float* d, int mode, int K, int N, int M, void* stream);
+/* descriptor probe (tests only): D[128,N] = A*B, each operand K-major or MN-major with explicit swizzle / layout / LBO / SBO */
+int sgcn_selftest_probe(const float* a, const float* b, float* d, int K, int N, int a_mn, int b_mn, int swz, int layout,
+                        int lbo, int sbo, int kstep, void* stream);
 
 /* ---------------------------------------------------------------- stand-alone temporal shift (NCHW) ------- */
 /* Replaces shift_cuda.forward (shift_cuda.cpp:19-23 -> shift_cuda_kernel.cu:405-431, kernel K1 :12-76).

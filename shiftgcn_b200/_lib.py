@@ -45,6 +45,7 @@ SIGNATURES = {
     "sgcn_abi_version": [],
     "sgcn_device_check": [],
     "sgcn_selftest_umma": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "sgcn_selftest_probe": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "sgcn_shift_fwd_nchw_f32": [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
     "sgcn_shift_fwd_nchw_f64": [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
     "sgcn_shift_bwd_nchw_f32": [_vp] * 9 + [_ll, _i, _i, _i, _i, _vp],

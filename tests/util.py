@@ -13,6 +13,14 @@ def rel_err(a, b):
     return (a - b).abs().max().item() / denom
 
 
+def rel_l2(a, b):
+    """||a - b||_2 / ||b||_2 -- the metric for TF32-vs-exact GRADIENTS: TF32 rounding flips a ~1e-4 fraction of
+    ReLU masks, which changes those gradient entries by O(1) (max-norm meaningless) but the vector by O(1e-2)."""
+    a = torch.as_tensor(a).detach().double().cpu().reshape(-1)
+    b = torch.as_tensor(b).detach().double().cpu().reshape(-1)
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
 def fill_pair(cuda_module, ref_module, prefix=""):
     """identical deterministic non-degenerate weights in the CUDA module (fp32) and the oracle (fp64)"""
     model_ref.fill_module_(ref_module, prefix)
