@@ -104,6 +104,10 @@ def main():
         m(x)
     for b in bns:
         b.momentum = 0.1
+    with torch.no_grad():                      # the fixture stores the buffers in fp32: evaluate with exactly those values
+        for b in m.buffers():
+            if b.dtype.is_floating_point:
+                b.copy_(b.float().double())
     m.eval()
     with torch.no_grad():
         logits = m(x)

@@ -1,0 +1,119 @@
+"""Data-parallel training of the Shift-GCN path: one process per GPU, ONE NCCL all-reduce per step.
+
+Replaces the reference's ``nn.DataParallel`` wrapper (main.py:294-299: per-iteration scatter / replicate / gather)
+and its per-parameter SGD groups (main.py:301-322):
+
+  * parameters and gradients live in two flat fp32 buffers (``p.data`` / ``p.grad`` are views), so the gradient
+    exchange is a single ``all_reduce(AVG)`` of ~2.8 MB over NVLink instead of ~300 small ones;
+  * BatchNorm statistics stay local to each GPU, exactly like DataParallel (no SyncBN in the reference);
+  * the shift-position gradient is a SIGN (kernel K5, shift_cuda_kernel.cu:371-395).  The raw per-channel sums
+    travel in the same flat buffer and the constraint is applied AFTER the reduction, which gives the
+    single-GPU large-batch semantics (SURVEY.md App. E-7 documents how DataParallel differs: it sums the
+    already-constrained per-replica +-0.01 values);
+  * SGD with momentum / Nesterov and the reference's decay rules: 1e-4 everywhere (BN and biases included),
+    1e-3 for ``Linear_weight``, 0 for ``Feature_Mask`` (main.py:307-317), applied as a handful of flat tensor ops.
+
+The batch is sharded by the caller (each rank feeds its own samples); there is no collective on the data path.
+"""
+import torch
+import torch.distributed as dist
+
+
+def reference_weight_decay(name):
+    """main.py:307-317"""
+    if "Linear_weight" in name:
+        return 1e-3
+    if "Mask" in name:
+        return 0.0
+    return 1e-4
+
+
+class FlatSGDTrainer:
+    """Flat-buffer data-parallel SGD around a ``Model`` (or any module using this package's Shift modules)."""
+
+    def __init__(self, model, lr=0.1, momentum=0.9, nesterov=True, process_group=None, weight_decay_fn=None):
+        self.model = model
+        self.lr, self.momentum, self.nesterov = lr, momentum, nesterov
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        wd_fn = weight_decay_fn or reference_weight_decay
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        dev = self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        self.n_param = sum(sizes)
+        # raw shift-position sums ride behind the gradients: one slot per ypos element
+        self.ypos_slices = []                       # (grad_offset, raw_offset, count, owning Shift module)
+        shifts = {id(m.ypos): m for m in model.modules() if hasattr(m, "ypos") and hasattr(m, "xpos")}
+        raw_total, off = 0, 0
+        for p, sz in zip(self.params, sizes):
+            if id(p) in shifts:
+                self.ypos_slices.append((off, self.n_param + raw_total, sz, shifts[id(p)]))
+                raw_total += sz
+            off += sz
+        self.flat_param = torch.empty(self.n_param, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(self.n_param + raw_total, device=dev, dtype=torch.float32)
+        self.momentum_buf = torch.zeros(self.n_param, device=dev, dtype=torch.float32)
+        self.weight_decay = torch.empty(self.n_param, device=dev, dtype=torch.float32)
+        off = 0
+        for n, p, sz in zip(self.names, self.params, sizes):
+            self.flat_param[off:off + sz].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + sz].view_as(p.data)
+            p.grad = self.flat_grad[off:off + sz].view_as(p.data)
+            self.weight_decay[off:off + sz] = wd_fn(n)
+            off += sz
+        self.steps = 0
+        if self.world > 1:                           # replicas start from rank 0's weights and buffers
+            dist.broadcast(self.flat_param, 0, group=self.group)
+            for b in model.buffers():
+                dist.broadcast(b, 0, group=self.group)
+        for _, _, _, shift in self.ypos_slices:
+            shift._export_raw = True                 # functional.py stores the raw sums on the module
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def _collect_raw(self):
+        for _, raw_off, cnt, shift in self.ypos_slices:
+            raw = getattr(shift, "_raw_ypos_grad", None)
+            if raw is not None:
+                self.flat_grad[raw_off:raw_off + cnt].copy_(raw)
+
+    def reduce_gradients(self):
+        """one collective for everything, then the K5 constraint on the reduced raw sums"""
+        have_raw = all(getattr(s, "_raw_ypos_grad", None) is not None for *_, s in self.ypos_slices)
+        if have_raw:
+            self._collect_raw()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG if self.flat_grad.is_cuda else dist.ReduceOp.SUM,
+                            group=self.group)
+            if not self.flat_grad.is_cuda:           # gloo has no AVG
+                self.flat_grad.div_(self.world)
+        if have_raw:
+            for g_off, raw_off, cnt, _ in self.ypos_slices:
+                raw = self.flat_grad[raw_off:raw_off + cnt]
+                g = torch.where(raw != 0, torch.sign(raw) * 0.01, torch.full_like(raw, 0.0001))
+                self.flat_grad[g_off:g_off + cnt].copy_(g)
+
+    def step(self):
+        """torch.optim.SGD semantics (momentum buffer initialised with the first gradient, optional Nesterov)"""
+        g = self.flat_grad[:self.n_param]
+        d = torch.addcmul(g, self.weight_decay, self.flat_param)
+        if self.momentum != 0:
+            if self.steps == 0:
+                self.momentum_buf.copy_(d)
+            else:
+                self.momentum_buf.mul_(self.momentum).add_(d)
+            d = d.add(self.momentum_buf, alpha=self.momentum) if self.nesterov else self.momentum_buf
+        self.flat_param.add_(d, alpha=-self.lr)
+        self.steps += 1
+
+    def train_step(self, x, label, loss_fn=torch.nn.functional.cross_entropy):
+        """forward + backward + all-reduce + SGD on this rank's shard; returns the (local) loss tensor"""
+        self.zero_grad()
+        loss = loss_fn(self.model(x), label)
+        loss.backward()
+        self.reduce_gradients()
+        self.step()
+        return loss

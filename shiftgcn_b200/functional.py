@@ -247,7 +247,11 @@ class TemporalFn(torch.autograd.Function):
     def backward(ctx, gy):
         ga, Wt, gb = ctx.saved_tensors
         gy = gy.contiguous()
-        r = temporal_backward(ctx.saved, gy, ga, Wt.reshape(Wt.shape[0], Wt.shape[1]), gb, ctx.module._ws)
+        want_raw = getattr(ctx.module.shift_in, "_export_raw", False)
+        r = temporal_backward(ctx.saved, gy, ga, Wt.reshape(Wt.shape[0], Wt.shape[1]), gb, ctx.module._ws,
+                              want_raw=want_raw)
+        if want_raw:        # raw (pre-K5) means for the post-all-reduce constraint of dp.FlatSGDTrainer
+            ctx.module.shift_in._raw_ypos_grad, ctx.module.shift_out._raw_ypos_grad = r["raw_in"], r["raw_out"]
         gres = None
         if ctx.has_res:
             gres = ops.relu_mask_grad(gy, ctx.saved["y"]) if ctx.saved["relu"] else gy
@@ -283,8 +287,11 @@ class UnitFn(torch.autograd.Function):
         unit = ctx.unit
         gy = gy.contiguous()
         C = W.shape[0]
+        want_raw = getattr(unit.tcn1.shift_in, "_export_raw", False)
         t = temporal_backward(ctx.t_saved, gy, ga, Wt.reshape(C, C), gb, unit.tcn1._ws, spatial_saved=ctx.s_saved,
-                              spatial_ws=unit.gcn1._ws)
+                              spatial_ws=unit.gcn1._ws, want_raw=want_raw)
+        if want_raw:
+            unit.tcn1.shift_in._raw_ypos_grad, unit.tcn1.shift_out._raw_ypos_grad = t["raw_in"], t["raw_out"]
         s = spatial_backward(ctx.s_saved, t["gh"], W, mask, g1, True, unit.gcn1._ws, unit_res=(gy, ctx.t_saved["y"]))
         return (s["gx"], s["dW"], s["dbias"], s["dmask"], s["dgamma"], s["dbeta"], t["dgamma_a"], t["dbeta_a"],
                 t["gx_in"], t["gy_in"], t["dWt"], t["dbt"], t["gx_out"], t["gy_out"], t["dgamma_b"], t["dbeta_b"], None)

@@ -16,8 +16,35 @@ EPI_ROT_RAW, EPI_ROT_FUSED, EPI_LINEAR, EPI_SPATIAL_BWD = 0, 1, 2, 3
 WG_SPATIAL, WG_TEMPORAL = 0, 1
 
 
+LAUNCHES = 0          # kernels of this library enqueued so far (bench.py reports the per-step count)
+PROFILE = None        # when a list: (name, start_event, end_event, algorithmic_bytes) per C-ABI call
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _launch(name, nkernels, algo_bytes, fn, *args):
+    """call one C-ABI entry point; count its kernels; optionally bracket it with CUDA events (bench profiling pass)"""
+    global LAUNCHES
+    LAUNCHES += nkernels
+    if PROFILE is None:
+        _lib.check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(fn(*args), name)
+    e1.record()
+    PROFILE.append((name, e0, e1, algo_bytes))
+
+
+def _nbytes(*tensors):
+    return sum(t.numel() * t.element_size() for t in tensors if t is not None)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
 
 
 def _p(t, dtype=torch.float32, name="tensor"):
@@ -76,6 +103,7 @@ def shift_forward(inp, xpos, ypos, stride):
     if xpos.numel() != c or ypos.numel() != c:
         raise RuntimeError("xpos / ypos must have one entry per channel")
     out = torch.empty((n, c, h // stride, w), device=inp.device, dtype=dt)
+    _count(1)
     with torch.cuda.device(inp.device):
         _lib.check(fn(_p(inp, dt, "input"), _p(out, dt), _p(xpos, dt, "xpos"), _p(ypos, dt, "ypos"), n, c, h, w, stride,
                       _stream()), "shift forward")
@@ -102,6 +130,7 @@ def shift_backward(grad_output, inp, output, xpos, ypos, stride, return_raw=Fals
     gy = torch.empty(c, device=inp.device, dtype=dt)
     raw = torch.empty(2, c, device=inp.device, dtype=dt) if return_raw else None
     scratch = torch.zeros(2, c, device=inp.device, dtype=torch.float64)
+    _count(3)
     with torch.cuda.device(inp.device):
         _lib.check(fn(_p(grad_output, dt, "grad_output"), _p(inp, dt, "input"), _p(xpos, dt), _p(ypos, dt),
                       _p(grad_input, dt), _p(gx, dt), _p(gy, dt), _p(raw, dt), _d(scratch), n, c, h, w, stride,
@@ -114,6 +143,7 @@ def shift_backward(grad_output, inp, output, xpos, ypos, stride, return_raw=Fals
 # ------------------------------------------------------------------------------------------------ small helpers
 def weight_image(src, ld_n, ld_k, N, K):
     """canonical TF32 image of B[n][k] = src.flatten()[n*ld_n + k*ld_k]"""
+    _count()
     lib = _lib.load()
     img = torch.empty(N * K, device=src.device, dtype=torch.float32)
     _lib.check(lib.sgcn_prep_weight_image(_p(src, name="weight"), ld_n, ld_k, N, K, _p(img), _stream()), "weight image")
@@ -121,6 +151,7 @@ def weight_image(src, ld_n, ld_k, N, K):
 
 
 def mask_prepare(mask):
+    _count()
     lib = _lib.load()
     mm = torch.empty_like(mask)
     _lib.check(lib.sgcn_mask_prepare(_p(mask, name="Feature_Mask"), _p(mm), mask.numel(), _stream()), "mask prepare")
@@ -128,6 +159,7 @@ def mask_prepare(mask):
 
 
 def mask_grad_finalize(raw, mask):
+    _count()
     lib = _lib.load()
     dm = torch.empty_like(mask)
     _lib.check(lib.sgcn_mask_grad_finalize(_d(raw), _p(mask), _p(dm), mask.numel(), _stream()), "mask grad")
@@ -135,6 +167,7 @@ def mask_grad_finalize(raw, mask):
 
 
 def reduce_export(src, scale=1.0):
+    _count()
     lib = _lib.load()
     dst = torch.empty(src.shape, device=src.device, dtype=torch.float32)
     _lib.check(lib.sgcn_reduce_export(_d(src), _p(dst), src.numel(), float(scale), _stream()), "reduce export")
@@ -143,6 +176,7 @@ def reduce_export(src, scale=1.0):
 
 def bn_fwd_finalize(stats, gamma, beta, running_mean, running_var, nbt, features, count, momentum, eps, training):
     """-> (mean, invstd, scale, shift) fp32 [features]; updates running stats / num_batches_tracked when training"""
+    _count()
     lib = _lib.load()
     dev = gamma.device if gamma is not None else running_mean.device
     out = torch.empty(4, features, device=dev, dtype=torch.float32)
@@ -155,6 +189,7 @@ def bn_fwd_finalize(stats, gamma, beta, running_mean, running_var, nbt, features
 
 def tshift_bwd_finalize(sums, gamma, invstd, C, count, n_batch, training, input_shift=False, want_raw=False):
     """-> dict(dgamma, dbeta, k1, m1, m2, gx, gy[, raw])"""
+    _count()
     lib = _lib.load()
     out = torch.empty(8, C, device=gamma.device, dtype=torch.float32)
     fn = lib.sgcn_tshift_in_bwd_finalize if input_shift else lib.sgcn_tshift_bwd_finalize
@@ -166,6 +201,7 @@ def tshift_bwd_finalize(sums, gamma, invstd, C, count, n_batch, training, input_
 
 def bn1d_bwd_finalize(vd_sums, gamma, mean, invstd, V, D, count, training):
     """-> dict(dgamma, dbeta, alpha, beta, gamma, dbias)"""
+    _count()
     lib = _lib.load()
     out = torch.empty(5, V * D, device=gamma.device, dtype=torch.float32)
     dbias = torch.empty(D, device=gamma.device, dtype=torch.float32)
@@ -183,7 +219,8 @@ def rowgemm(pro, epi, *, in0, out, wimg, groups, V, K, N, T=1, in1=None, pro_a=N
                     pro_b=_p(pro_b), pro_c=_p(pro_c), bias=_p(bias), epi_a=_p(epi_a), epi_b=_p(epi_b), res=_p(res),
                     res2=_p(res2), res2m=_p(res2m), xin=_p(xin), stats=_d(stats), red0=_d(red0), groups=int(groups),
                     V=V, G=groups_per_tile(V), T=int(T), K=K, N=N, relu=int(relu))
-    _lib.check(lib.sgcn_rowgemm(ctypes.byref(p), pro, epi, _stream()), "rowgemm")
+    name = "rowgemm[%s/%s]" % (("spatial", "lerp", "plain", "dy")[pro], ("rot_raw", "rot_fused", "linear", "spatial_bwd")[epi])
+    _launch(name, 1, _nbytes(in0, in1, out, res, res2, res2m, xin), lib.sgcn_rowgemm, ctypes.byref(p), pro, epi, _stream())
 
 
 def wgrad(mode, *, a_src, b_src, dw, groups, V, CA, CB, T=1, a_tab0=None, b_src2=None, b_tab0=None, b_tab1=None,
@@ -192,14 +229,15 @@ def wgrad(mode, *, a_src, b_src, dw, groups, V, CA, CB, T=1, a_tab0=None, b_src2
     p = SgcnWgrad(a_src=_p(a_src), a_tab0=_p(a_tab0), b_src=_p(b_src), b_src2=_p(b_src2), b_tab0=_p(b_tab0),
                   b_tab1=_p(b_tab1), b_tab2=_p(b_tab2), dw=_p(dw), groups=int(groups), V=V, G=groups_per_tile(V),
                   T=int(T), CA=CA, CB=CB)
-    _lib.check(lib.sgcn_wgrad(ctypes.byref(p), mode, _stream()), "wgrad")
+    _launch("wgrad[%s]" % ("spatial", "temporal")[mode], 1, _nbytes(a_src, b_src, b_src2), lib.sgcn_wgrad,
+            ctypes.byref(p), mode, _stream())
 
 
 # ------------------------------------------------------------------------------------------------ SIMT kernels
 def bn_res_relu_fwd(z, res, h, scale, shift, stats_out, rows, V, D, relu=1):
     lib = _lib.load()
-    _lib.check(lib.sgcn_bn_res_relu_fwd(_p(z), _p(res), _p(h), _p(scale), _p(shift), _d(stats_out), int(rows), V, D,
-                                        int(relu), _stream()), "bn_res_relu_fwd")
+    _launch("bn_res_relu_fwd", 1, _nbytes(z, res, h), lib.sgcn_bn_res_relu_fwd, _p(z), _p(res), _p(h), _p(scale),
+            _p(shift), _d(stats_out), int(rows), V, D, int(relu), _stream())
 
 
 def tshift_fwd(mode, *, q, ypos_eff, n_samples, T_in, T_out, V, C, stride, res=None, out=None, scale=None, shift=None,
@@ -208,7 +246,8 @@ def tshift_fwd(mode, *, q, ypos_eff, n_samples, T_in, T_out, V, C, stride, res=N
     p = SgcnTShift(q=_p(q), res=_p(res), out=_p(out), ypos_eff=_p(ypos_eff), scale=_p(scale), shift=_p(shift),
                    stats=_d(stats), n_samples=int(n_samples), T_in=T_in, T_out=T_out, V=V, C=C, stride=stride,
                    relu=int(relu))
-    _lib.check(lib.sgcn_tshift_fwd(ctypes.byref(p), mode, _stream()), "tshift_fwd")
+    _launch("tshift_fwd[%s]" % ("stats", "apply")[mode], 1, _nbytes(q, res, out), lib.sgcn_tshift_fwd, ctypes.byref(p),
+            mode, _stream())
 
 
 def tshift_bwd(mode, *, q, gy, ypos_eff, mean, invstd, n_samples, T_in, T_out, V, C, stride, y=None, relu=0, k1=None,
@@ -217,7 +256,8 @@ def tshift_bwd(mode, *, q, gy, ypos_eff, mean, invstd, n_samples, T_in, T_out, V
     p = SgcnTShiftBwd(q=_p(q), gy=_p(gy), y=_p(y), ypos_eff=_p(ypos_eff), mean=_p(mean), invstd=_p(invstd), k1=_p(k1),
                       m1=_p(m1), m2=_p(m2), sums=_d(sums), dpre=_p(dpre), dbias=_d(dbias), n_samples=int(n_samples),
                       T_in=T_in, T_out=T_out, V=V, C=C, stride=stride, relu=int(relu))
-    _lib.check(lib.sgcn_tshift_bwd(ctypes.byref(p), mode, _stream()), "tshift_bwd")
+    _launch("tshift_bwd[%s]" % ("stats", "apply")[mode], 1, _nbytes(q, gy, y, dpre), lib.sgcn_tshift_bwd,
+            ctypes.byref(p), mode, _stream())
 
 
 def tshift_in_bwd(mode, *, dp, h, ypos_eff, mean, invstd, n_samples, T, V, C, scale=None, shift=None, k1=None, m1=None,
@@ -227,22 +267,23 @@ def tshift_in_bwd(mode, *, dp, h, ypos_eff, mean, invstd, n_samples, T, V, C, sc
                         scale=_p(scale), shift=_p(shift), k1=_p(k1), m1=_p(m1), m2=_p(m2), zmean=_p(zmean),
                         zinvstd=_p(zinvstd), sums=_d(sums), vd_sums=_d(vd_sums), gh=_p(gh), n_samples=int(n_samples),
                         T=T, V=V, C=C, relu_h=int(relu_h))
-    _lib.check(lib.sgcn_tshift_in_bwd(ctypes.byref(p), mode, _stream()), "tshift_in_bwd")
+    _launch("tshift_in_bwd[%s]" % ("stats", "apply")[mode], 1, _nbytes(dp, h, z, gh), lib.sgcn_tshift_in_bwd,
+            ctypes.byref(p), mode, _stream())
 
 
 def channel_stats(x, stats, rows, C):
     lib = _lib.load()
-    _lib.check(lib.sgcn_channel_stats(_p(x), _d(stats), int(rows), C, _stream()), "channel_stats")
+    _launch("channel_stats", 1, _nbytes(x), lib.sgcn_channel_stats, _p(x), _d(stats), int(rows), C, _stream())
 
 
 def relu_bn1d_bwd_stats(g, h, z, zmean, zinvstd, gh, vd_sums, groups, V, C):
     lib = _lib.load()
-    _lib.check(lib.sgcn_relu_bn1d_bwd_stats(_p(g), _p(h), _p(z), _p(zmean), _p(zinvstd), _p(gh), _d(vd_sums),
-                                            int(groups), V, C, _stream()), "relu_bn1d_bwd_stats")
+    _launch("relu_bn1d_bwd_stats", 1, _nbytes(g, h, z, gh), lib.sgcn_relu_bn1d_bwd_stats, _p(g), _p(h), _p(z), _p(zmean),
+            _p(zinvstd), _p(gh), _d(vd_sums), int(groups), V, C, _stream())
 
 
 def relu_mask_grad(g, y):
     lib = _lib.load()
     out = torch.empty_like(g)
-    _lib.check(lib.sgcn_relu_mask_grad(_p(g), _p(y), _p(out), g.numel(), _stream()), "relu_mask_grad")
+    _launch("relu_mask_grad", 1, _nbytes(g, y, out), lib.sgcn_relu_mask_grad, _p(g), _p(y), _p(out), g.numel(), _stream())
     return out
