@@ -42,27 +42,31 @@ class FlatSGDTrainer:
         self.params = [p for _, p in named]
         dev = self.params[0].device
         sizes = [p.numel() for p in self.params]
-        self.n_param = sum(sizes)
+        # every parameter starts on a 256-byte boundary inside the flat buffers (library kernels such as cuDNN's
+        # convolutions and our own vectorised loads assume at least 16-byte aligned tensors)
+        ALIGN = 64
+        offsets, off = [], 0
+        for sz in sizes:
+            offsets.append(off)
+            off += (sz + ALIGN - 1) // ALIGN * ALIGN
+        self.n_param = off
         # raw shift-position sums ride behind the gradients: one slot per ypos element
         self.ypos_slices = []                       # (grad_offset, raw_offset, count, owning Shift module)
         shifts = {id(m.ypos): m for m in model.modules() if hasattr(m, "ypos") and hasattr(m, "xpos")}
-        raw_total, off = 0, 0
-        for p, sz in zip(self.params, sizes):
+        raw_total = 0
+        for p, sz, off in zip(self.params, sizes, offsets):
             if id(p) in shifts:
                 self.ypos_slices.append((off, self.n_param + raw_total, sz, shifts[id(p)]))
                 raw_total += sz
-            off += sz
-        self.flat_param = torch.empty(self.n_param, device=dev, dtype=torch.float32)
+        self.flat_param = torch.zeros(self.n_param, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(self.n_param + raw_total, device=dev, dtype=torch.float32)
         self.momentum_buf = torch.zeros(self.n_param, device=dev, dtype=torch.float32)
-        self.weight_decay = torch.empty(self.n_param, device=dev, dtype=torch.float32)
-        off = 0
-        for n, p, sz in zip(self.names, self.params, sizes):
+        self.weight_decay = torch.zeros(self.n_param, device=dev, dtype=torch.float32)
+        for n, p, sz, off in zip(self.names, self.params, sizes, offsets):
             self.flat_param[off:off + sz].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off:off + sz].view_as(p.data)
             p.grad = self.flat_grad[off:off + sz].view_as(p.data)
             self.weight_decay[off:off + sz] = wd_fn(n)
-            off += sz
         self.steps = 0
         if self.world > 1:                           # replicas start from rank 0's weights and buffers
             dist.broadcast(self.flat_param, 0, group=self.group)
