@@ -206,6 +206,35 @@ def temporal_backward(saved, gy, gamma_a, Wt, gamma_b, ws, spatial_saved=None, s
 
 
 # ================================================================================================ autograd
+def _stash(ctx, **groups):
+    """Register every tensor of the given dicts through ctx.save_for_backward (outputs included: keeping them as plain
+    ctx attributes would create an output -> grad_fn -> ctx -> output reference cycle and leak a whole step of
+    activations until the cyclic GC runs); non-tensor entries stay on ctx."""
+    tensors, layout = [], {}
+    for gname, d in groups.items():
+        if d is None:
+            layout[gname] = None
+            continue
+        entries = {}
+        for k, v in d.items():
+            if torch.is_tensor(v):
+                entries[k] = ("t", len(tensors))
+                tensors.append(v)
+            else:
+                entries[k] = ("v", v)
+        layout[gname] = entries
+    ctx._layout = layout
+    ctx.save_for_backward(*tensors)
+
+
+def _unstash(ctx):
+    tensors = ctx.saved_tensors
+    out = {}
+    for gname, entries in ctx._layout.items():
+        out[gname] = None if entries is None else {k: (tensors[v] if kind == "t" else v) for k, (kind, v) in entries.items()}
+    return out
+
+
 class SpatialFn(torch.autograd.Function):
     """Shift_gcn.forward (model/shift_gcn.py:121-142) on rows; ``res`` = down(x0) rows or None for identity."""
 
@@ -216,16 +245,16 @@ class SpatialFn(torch.autograd.Function):
         h, saved = spatial_forward(x, res, W, bias, mask, module.bn, training, module._ws,
                                    fuse_eval=(not training and not need_grad))
         ctx.module = module
-        ctx.saved = saved
         if saved is not None:
             saved["identity_res"] = res is None
-            ctx.save_for_backward(W, mask, gamma)
+        _stash(ctx, s=saved, p=dict(W=W, mask=mask, gamma=gamma))
         return h
 
     @staticmethod
     def backward(ctx, g):
-        W, mask, gamma = ctx.saved_tensors
-        r = spatial_backward(ctx.saved, g.contiguous(), W, mask, gamma, False, ctx.module._ws)
+        st = _unstash(ctx)
+        p = st["p"]
+        r = spatial_backward(st["s"], g.contiguous(), p["W"], p["mask"], p["gamma"], False, ctx.module._ws)
         return r["gx"], r["gres"], r["dW"], r["dbias"], r["dmask"], r["dgamma"], r["dbeta"], None
 
 
@@ -238,23 +267,24 @@ class TemporalFn(torch.autograd.Function):
         y, saved = temporal_forward(h, res, relu, module.bn, ypos_in, Wt.reshape(Wt.shape[0], Wt.shape[1]), bt,
                                     ypos_out, module.bn2, module.shift_out.stride, module.training, module._ws, False)
         ctx.module = module
-        ctx.saved = saved
         ctx.has_res = res is not None
-        ctx.save_for_backward(ga, Wt, gb)
+        _stash(ctx, t=saved, p=dict(ga=ga, Wt=Wt, gb=gb))
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        ga, Wt, gb = ctx.saved_tensors
+        st = _unstash(ctx)
+        saved, p = st["t"], st["p"]
+        Wt = p["Wt"]
         gy = gy.contiguous()
         want_raw = getattr(ctx.module.shift_in, "_export_raw", False)
-        r = temporal_backward(ctx.saved, gy, ga, Wt.reshape(Wt.shape[0], Wt.shape[1]), gb, ctx.module._ws,
+        r = temporal_backward(saved, gy, p["ga"], Wt.reshape(Wt.shape[0], Wt.shape[1]), p["gb"], ctx.module._ws,
                               want_raw=want_raw)
         if want_raw:        # raw (pre-K5) means for the post-all-reduce constraint of dp.FlatSGDTrainer
             ctx.module.shift_in._raw_ypos_grad, ctx.module.shift_out._raw_ypos_grad = r["raw_in"], r["raw_out"]
         gres = None
         if ctx.has_res:
-            gres = ops.relu_mask_grad(gy, ctx.saved["y"]) if ctx.saved["relu"] else gy
+            gres = ops.relu_mask_grad(gy, saved["y"]) if saved["relu"] else gy
         return (r["gh"], gres, r["dgamma_a"], r["dbeta_a"], r["gx_in"], r["gy_in"], r["dWt"], r["dbt"], r["gx_out"],
                 r["gy_out"], r["dgamma_b"], r["dbeta_b"], None, None)
 
@@ -275,23 +305,24 @@ class UnitFn(torch.autograd.Function):
         y, t_saved = temporal_forward(h, x, 1, tcn.bn, ypos_in, Wt.reshape(C, C), bt, ypos_out, tcn.bn2, 1, training,
                                       tcn._ws, h_stats_ready=training)
         ctx.unit = unit
-        ctx.s_saved, ctx.t_saved = s_saved, t_saved
         if s_saved is not None:
             s_saved["identity_res"] = True
-        ctx.save_for_backward(W, mask, g1, ga, Wt, gb)
+        _stash(ctx, s=s_saved, t=t_saved, p=dict(W=W, mask=mask, g1=g1, ga=ga, Wt=Wt, gb=gb))
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        W, mask, g1, ga, Wt, gb = ctx.saved_tensors
+        st = _unstash(ctx)
+        s_saved, t_saved, p = st["s"], st["t"], st["p"]
         unit = ctx.unit
         gy = gy.contiguous()
-        C = W.shape[0]
+        C = p["W"].shape[0]
         want_raw = getattr(unit.tcn1.shift_in, "_export_raw", False)
-        t = temporal_backward(ctx.t_saved, gy, ga, Wt.reshape(C, C), gb, unit.tcn1._ws, spatial_saved=ctx.s_saved,
+        t = temporal_backward(t_saved, gy, p["ga"], p["Wt"].reshape(C, C), p["gb"], unit.tcn1._ws, spatial_saved=s_saved,
                               spatial_ws=unit.gcn1._ws, want_raw=want_raw)
         if want_raw:
             unit.tcn1.shift_in._raw_ypos_grad, unit.tcn1.shift_out._raw_ypos_grad = t["raw_in"], t["raw_out"]
-        s = spatial_backward(ctx.s_saved, t["gh"], W, mask, g1, True, unit.gcn1._ws, unit_res=(gy, ctx.t_saved["y"]))
+        s = spatial_backward(s_saved, t["gh"], p["W"], p["mask"], p["g1"], True, unit.gcn1._ws,
+                             unit_res=(gy, t_saved["y"]))
         return (s["gx"], s["dW"], s["dbias"], s["dmask"], s["dgamma"], s["dbeta"], t["dgamma_a"], t["dbeta_a"],
                 t["gx_in"], t["gy_in"], t["dWt"], t["dbt"], t["gx_out"], t["gy_out"], t["dgamma_b"], t["dbeta_b"], None)
