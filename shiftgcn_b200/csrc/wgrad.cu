@@ -165,7 +165,7 @@ extern "C" int sgcn_wgrad(const SgcnWgrad* pp, int mode, void* stream) {
   using namespace sgcn;
   if (!pp) return set_error("sgcn_wgrad: null params");
   const SgcnWgrad& p = *pp;
-  if (p.V < 8 || p.V > 40) return set_error("sgcn_wgrad: num_point must be in [8, 40]");
+  if (p.V < 25 || p.V > 40) return set_error("sgcn_wgrad: num_point must be in [25, 40]");
   if (p.G < 1 || p.G > 16 || p.G * p.V > kTileRows) return set_error("sgcn_wgrad: need G <= 16 and G*V <= 128");
   if ((p.CA != 64 && p.CA != 128 && p.CA != 256) || (p.CB != 64 && p.CB != 128 && p.CB != 256))
     return set_error("sgcn_wgrad: channel counts must be 64, 128 or 256");

@@ -69,8 +69,8 @@ def device_check():
 
 
 def groups_per_tile(V):
-    if V < 8 or V > 40:
-        raise RuntimeError(f"shiftgcn_b200 fused kernels support 8 <= num_point <= 40, got {V}")
+    if V < 25 or V > 40:
+        raise RuntimeError(f"shiftgcn_b200 fused kernels support 25 <= num_point <= 40, got {V}")
     return 128 // V
 
 
