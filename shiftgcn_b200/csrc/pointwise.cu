@@ -1,313 +1,563 @@
 // pointwise.cu -- bandwidth-bound SIMT kernels of the Shift-GCN hot path (channels-last rows [(n,t,v), C]).
 //
-// Thread mapping: threadIdx % C <-> channel (coalesced 128-byte warp accesses), threadIdx / C <-> row slot.
-// Cross-row reductions (BatchNorm statistics, position / bias gradients) are accumulated in registers,
-// combined across the block's row slots in shared memory and published with one double atomic per value.
+// "Walker" kernels: a thread owns ONE column (joint v, channel c) of one sample and walks along the frame
+// axis t over a chunk of frames.  Consequences:
+//   * lane <-> channel: every warp access is one coalesced 128-byte line, no index arithmetic per element
+//     (the row pointer advances by the frame pitch V*C), no integer division anywhere in the loops;
+//   * the fractional temporal shift is a two-tap filter along the walk direction, so the second tap of
+//     frame t is the first tap of frame t+1 and stays in a register: every tensor crosses L1 exactly once;
+//   * per-channel parameters (shift position, BatchNorm constants) live in registers for the whole walk;
+//   * cross-row reductions (BatchNorm statistics, position / bias gradients) accumulate in registers, are
+//     combined over the block's warps (= joints) in shared memory and published with one fp64 atomic per
+//     value and block.
+// Block = 32 channels x ceil(V/2) warps (each warp walks one or two joints); grid = channel blocks x samples x
+// frame chunks.
 //
 //   bn_res_relu_fwd     h = relu(BN1d(z) + res)  (+ per-channel stats of h)           model/shift_gcn.py:137-141, :66
 //   tshift_fwd          s = Shift_stride(q); stats of s  |  y = [relu](BN(s) + res)    :72-73, :161-162, K1
 //   tshift_bwd_stats    BN backward sums + position-gradient sums of shift_out          autograd of :72-73, K4
 //   tshift_bwd_apply    dpre = [q>0] * Shift^T(BN-bwd(g))  (+ conv-bias gradient)       K2/K3, autograd of :70-73
-//   tshift_in_bwd_stats du = Shift^T(dp); BN backward sums; position-gradient sums      K2, K4, autograd of :66-68
-//   tshift_in_bwd_apply gh = [h>0] * BN-bwd(du)  (+ per-(v,d) BN1d backward sums)        autograd of :66, :137-141
+//   tshift_in_bwd_stats BN backward sums + position-gradient sums of shift_in           K2, K4, autograd of :66-68
+//   tshift_in_bwd_apply gh = [h>0] * BN-bwd(Shift^T dp)  (+ per-(v,d) BN1d backward sums) autograd of :66, :137-141
+// (K1..K5 = model/Temporal_shift/cuda/shift_cuda_kernel.cu:12-76, 79-152, 156-256, 278-363, 371-395.)
 #include "capi_internal.h"
 #include "common.cuh"
 #include "pointwise.h"
 
 namespace sgcn {
 
-constexpr int kPwThreads = 256;
+constexpr int kMaxWarps = 20;     // ceil(V/2) warps, V <= 40
+constexpr int kUnroll = 4;        // frames in flight per thread (kernels with >= 3 loads per frame)
+constexpr int kUnrollWide = 8;    // ... with 2 loads per frame
+constexpr int kUnrollMax = 16;    // ... with a single load per frame (read-only statistics passes are latency bound)
 
-// combine per-thread partials over the row slots of a block, then one double atomic per channel
+// ------------------------------------------------------------------------------------------------ helpers
+struct Col {            // the walker's identity
+  int lane, warp, nw;   // lane = channel inside the 32-channel block
+  int c;                // channel
+  long long n;          // sample (or group-chunk index)
+  int chunk;            // frame chunk
+};
+
+__device__ __forceinline__ Col col_of(int C, int nchunks) {
+  Col k;
+  k.lane = threadIdx.x & 31;
+  k.warp = threadIdx.x >> 5;
+  k.nw = blockDim.x >> 5;
+  const int cblocks = C >> 5;
+  unsigned b = blockIdx.x;
+  const unsigned cb = b % cblocks;
+  b /= cblocks;
+  k.chunk = (int)(b % (unsigned)nchunks);
+  k.n = b / (unsigned)nchunks;
+  k.c = (int)cb * 32 + k.lane;
+  return k;
+}
+
+// combine per-thread partials over the block's warps, then one double atomic per (channel, value)
 template <int NV>
-__device__ __forceinline__ void block_reduce_channels(float (&v)[NV], double* __restrict__ dst, int dst_stride, int C,
-                                                      float* scratch /* [kPwThreads * NV] */) {
-  const int tid = threadIdx.x;
-  const int slots = kPwThreads / C;
-  __syncthreads();
+__device__ __forceinline__ void block_reduce_channels(const float (&v)[NV], double* __restrict__ dst, int c,
+                                                      float* scratch /* [kMaxWarps * 32 * NV] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) scratch[k * kPwThreads + tid] = v[k];
+  for (int k = 0; k < NV; ++k) scratch[(warp * NV + k) * 32 + lane] = v[k];
   __syncthreads();
-  if (tid < C) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      double s = 0.0;
-      for (int sl = 0; sl < slots; ++sl) s += (double)scratch[k * kPwThreads + sl * C + tid];
-      atomicAdd(dst + (size_t)tid * dst_stride + k, s);
-    }
+  for (int k = warp; k < NV; k += nw) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += (double)scratch[(w * NV + k) * 32 + lane];
+    atomicAdd(dst + (size_t)c * NV + k, s);
   }
 }
+
+// zero-padded frame tap: value of frame tt of the column whose frame 0 is at `base`.
+// The load itself is UNCONDITIONAL (row index clamped into [0, T)) and the padding is applied with a select:
+// a predicated / branched load makes ptxas consume each result right behind its LDG, which serialises the
+// loads of an unrolled batch (measured: 1 load in flight per warp instead of kUnroll).
+__device__ __forceinline__ float ldrow(const float* __restrict__ base, int tt, int T, int pitch) {
+  const int c = min(max(tt, 0), T - 1);
+  return __ldg(base + (size_t)c * (size_t)pitch);
+}
+__device__ __forceinline__ bool inside(int tt, int T) { return (unsigned)tt < (unsigned)T; }
+__device__ __forceinline__ float tap(const float* __restrict__ base, int tt, int T, int pitch) {
+  const float v = ldrow(base, tt, T, pitch);
+  return inside(tt, T) ? v : 0.f;
+}
+
+struct LerpCh {
+  int y1;
+  float f, g;    // weights of tap y1+1 and of tap y1  (g = 1 - f)
+};
+__device__ __forceinline__ LerpCh lerp_of(float ypos_eff) {
+  const float fl = floorf(ypos_eff);
+  const float f = ypos_eff - fl;
+  return {(int)fl, f, 1.f - f};
+}
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------------------------------------
 // h = relu(z * sc[v,d] + sh[v,d] + res)          stats_out[d] += {sum h, sum h^2}
-__global__ void __launch_bounds__(kPwThreads) bn_res_relu_fwd_kernel(const float* __restrict__ z,
-                                                                     const float* __restrict__ res,
-                                                                     float* __restrict__ h,
-                                                                     const float* __restrict__ sc,
-                                                                     const float* __restrict__ sh,
-                                                                     double* __restrict__ stats_out, long long rows,
-                                                                     int V, int D, int relu) {
-  __shared__ float scratch[kPwThreads * 2];
-  const int tid = threadIdx.x, d = tid % D, slot = tid / D, slots = kPwThreads / D;
+// walks row GROUPS (frames of any sample): groups [g0, g1) of the chunk
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) bn_res_relu_fwd_kernel(const float* __restrict__ z,
+                                                                         const float* __restrict__ res,
+                                                                         float* __restrict__ h,
+                                                                         const float* __restrict__ sc,
+                                                                         const float* __restrict__ sh,
+                                                                         double* __restrict__ stats_out,
+                                                                         long long groups, int gper, int nchunks, int V,
+                                                                         int D, int relu) {
+  __shared__ float scratch[kMaxWarps * 32 * 2];
+  const Col k = col_of(D, nchunks);
+  const long long g0 = (long long)k.chunk * gper;
+  const int ng = (int)((groups - g0) < gper ? (groups - g0) : gper);
+  const int pitch = V * D;
   float acc[2] = {0.f, 0.f};
-  for (long long r = (long long)blockIdx.x * slots + slot; r < rows; r += (long long)gridDim.x * slots) {
-    const int v = (int)(r % V);
-    const size_t o = (size_t)r * D + d;
-    float y = fmaf(z[o], __ldg(sc + v * D + d), __ldg(sh + v * D + d));
-    if (res) y += res[o];
-    if (relu) y = fmaxf(y, 0.f);
-    h[o] = y;
-    acc[0] += y;
-    acc[1] = fmaf(y, y, acc[1]);
-  }
-  if (stats_out) block_reduce_channels<2>(acc, stats_out, 2, D, scratch);
-}
-
-// ------------------------------------------------------------------------------------------------ temporal shift
-struct LerpCh {
-  int y1;
-  float fy;
-};
-__device__ __forceinline__ LerpCh lerp_of(float ypos_eff) {
-  const float f = floorf(ypos_eff);
-  return {(int)f, ypos_eff - f};
-}
-
-// value of the zero-padded row `t` of sample-plane `plane` ((n, t=0) row base), channel offset included in ptr
-__device__ __forceinline__ float tap_row(const float* __restrict__ base, int t, int T, size_t row_pitch) {
-  return (t >= 0 && t < T) ? __ldg(base + (size_t)t * row_pitch) : 0.f;
-}
-
-// MODE 0: stats[c] += {sum s, sum s^2};  MODE 1: out = [relu](s*sc + sh + res)
-template <int MODE>
-__global__ void __launch_bounds__(kPwThreads) tshift_fwd_kernel(const SgcnTShift p) {
-  __shared__ float scratch[kPwThreads * 2];
-  const int C = p.C, V = p.V, tid = threadIdx.x, c = tid % C, slot = tid / C, slots = kPwThreads / C;
-  const LerpCh L = lerp_of(p.ypos_eff[c]);
-  const float sc = MODE == 1 ? p.scale[c] : 0.f, sh = MODE == 1 ? p.shift[c] : 0.f;
-  const size_t pitch = (size_t)V * C;
-  const long long rows = p.n_samples * p.T_out * V;
-  float acc[2] = {0.f, 0.f};
-  for (long long r = (long long)blockIdx.x * slots + slot; r < rows; r += (long long)gridDim.x * slots) {
-    const long long grp = r / V;
-    const int v = (int)(r - grp * V);
-    const long long n = grp / p.T_out;
-    const int to = (int)(grp - n * p.T_out);
-    const float* base = p.q + ((size_t)n * p.T_in * V + v) * C + c;
-    const int ta = to * p.stride + L.y1;
-    const float s = tap_row(base, ta, p.T_in, pitch) * (1.f - L.fy) + tap_row(base, ta + 1, p.T_in, pitch) * L.fy;
-    if (MODE == 0) {
-      acc[0] += s;
-      acc[1] = fmaf(s, s, acc[1]);
-    } else {
-      const size_t o = (size_t)r * C + c;
-      float y = fmaf(s, sc, sh);
-      if (p.res) y += p.res[o];
-      p.out[o] = p.relu ? fmaxf(y, 0.f) : y;
+  for (int v = k.warp; v < V; v += k.nw) {
+    const float a = __ldg(sc + v * D + k.c), b = __ldg(sh + v * D + k.c);
+    const size_t o0 = ((size_t)g0 * V + v) * D + k.c;
+    const float* zp = z + o0;
+    const float* rp = res ? res + o0 : zp;                 // no residual: read z twice (L1 hit) and ignore it
+    const float rsel = res ? 1.f : 0.f;
+    float* hp = h + o0;
+    for (int g = 0; g < ng; g += kUnroll) {
+      float zv[kUnroll], rv[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int gg = min(g + u, ng - 1);                 // tail iterations re-read the last row (results unused)
+        zv[u] = __ldg(zp + (size_t)gg * pitch);
+        rv[u] = __ldg(rp + (size_t)gg * pitch);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (g + u < ng) {
+          float y = fmaf(rv[u], rsel, fmaf(zv[u], a, b));
+          if (relu) y = fmaxf(y, 0.f);
+          hp[(size_t)(g + u) * pitch] = y;
+          acc[0] += y;
+          acc[1] = fmaf(y, y, acc[1]);
+        }
     }
   }
-  if (MODE == 0) block_reduce_channels<2>(acc, p.stats, 2, C, scratch);
+  if (stats_out) block_reduce_channels<2>(acc, stats_out, k.c, scratch);
 }
 
+// ------------------------------------------------------------------------------------------------ temporal shift, forward
+// s(to) = g * Q(to*stride + y1) + f * Q(to*stride + y1 + 1), Q zero padded           (K1 with xpos = 0)
+// MODE 0: stats[c] += {sum s, sum s^2};  MODE 1: out = [relu](s*sc + sh + res)
+template <int MODE, bool S1>
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_fwd_kernel(const SgcnTShift p, int tper, int nchunks) {
+  __shared__ float scratch[kMaxWarps * 32 * 2];
+  const Col k = col_of(p.C, nchunks);
+  const int C = p.C, V = p.V, Ti = p.T_in, To = p.T_out, st = S1 ? 1 : p.stride;
+  const int pitch = V * C;
+  const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
+  const float sc = MODE == 1 ? __ldg(p.scale + k.c) : 0.f, sh = MODE == 1 ? __ldg(p.shift + k.c) : 0.f;
+  const int to0 = k.chunk * tper, to1 = min(To, to0 + tper);
+  constexpr int U = MODE == 0 ? kUnrollWide : kUnroll;
+  float acc[2] = {0.f, 0.f};
+  for (int v = k.warp; v < V; v += k.nw) {
+    const float* qb = p.q + ((size_t)k.n * Ti * V + v) * C + k.c;
+    const size_t ob = ((size_t)k.n * To * V + v) * C + k.c;
+    const float* resb = (MODE == 1 && p.res) ? p.res + ob : qb;   // no residual: any valid address, value ignored
+    float qa = S1 ? tap(qb, to0 + L.y1, Ti, pitch) : 0.f;
+    for (int to = to0; to < to1; to += U) {
+      float q0[S1 ? 1 : U], q1[U], rv[MODE == 1 ? U : 1];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int tc = min(to + u, to1 - 1);
+        const int ta = tc * st + L.y1;
+        q1[u] = tap(qb, ta + 1, Ti, pitch);
+        if (!S1) q0[u] = tap(qb, ta, Ti, pitch);
+        if (MODE == 1) rv[u] = __ldg(resb + (size_t)tc * pitch);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (to + u < to1) {
+          const float a = S1 ? qa : q0[S1 ? 0 : u];
+          const float s = fmaf(L.f, q1[u], L.g * a);
+          qa = q1[u];
+          if (MODE == 0) {
+            acc[0] += s;
+            acc[1] = fmaf(s, s, acc[1]);
+          } else {
+            float y = fmaf(s, sc, sh);
+            if (p.res) y += rv[MODE == 1 ? u : 0];
+            if (p.relu) y = fmaxf(y, 0.f);
+            p.out[ob + (size_t)(to + u) * pitch] = y;
+          }
+        }
+    }
+  }
+  if (MODE == 0) block_reduce_channels<2>(acc, p.stats, k.c, scratch);
+}
+
+// ------------------------------------------------------------------------------------------------ output shift + BN, backward
 // sums5[c] += { g, g*shat, g*dq, dq, shat*dq }   with g = gy*[y>0] (if relu), s = Shift(q), shat = (s-mean)*invstd,
 // dq = Q(ta+1) - Q(ta)  (d s / d ypos, K4 with xpos = 0)
-__global__ void __launch_bounds__(kPwThreads) tshift_bwd_stats_kernel(const SgcnTShiftBwd p) {
-  __shared__ float scratch[kPwThreads * 5];
-  const int C = p.C, V = p.V, tid = threadIdx.x, c = tid % C, slot = tid / C, slots = kPwThreads / C;
-  const LerpCh L = lerp_of(p.ypos_eff[c]);
-  const float mean = p.mean[c], invstd = p.invstd[c];
-  const size_t pitch = (size_t)V * C;
-  const long long rows = p.n_samples * p.T_out * V;
+template <bool S1>
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_bwd_stats_kernel(const SgcnTShiftBwd p, int tper, int nchunks) {
+  __shared__ float scratch[kMaxWarps * 32 * 5];
+  const Col k = col_of(p.C, nchunks);
+  const int C = p.C, V = p.V, Ti = p.T_in, To = p.T_out, st = S1 ? 1 : p.stride;
+  const int pitch = V * C;
+  const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
+  const float mean = __ldg(p.mean + k.c), invstd = __ldg(p.invstd + k.c);
+  const int to0 = k.chunk * tper, to1 = min(To, to0 + tper);
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long long r = (long long)blockIdx.x * slots + slot; r < rows; r += (long long)gridDim.x * slots) {
-    const long long grp = r / V;
-    const int v = (int)(r - grp * V);
-    const long long n = grp / p.T_out;
-    const int to = (int)(grp - n * p.T_out);
-    const float* base = p.q + ((size_t)n * p.T_in * V + v) * C + c;
-    const int ta = to * p.stride + L.y1;
-    const float q0 = tap_row(base, ta, p.T_in, pitch), q1 = tap_row(base, ta + 1, p.T_in, pitch);
-    const float s = q0 * (1.f - L.fy) + q1 * L.fy;
-    const float shat = (s - mean) * invstd;
-    const float dq = q1 - q0;
-    const size_t o = (size_t)r * C + c;
-    float g = p.gy[o];
-    if (p.relu && !(p.y[o] > 0.f)) g = 0.f;
-    acc[0] += g;
-    acc[1] = fmaf(g, shat, acc[1]);
-    acc[2] = fmaf(g, dq, acc[2]);
-    acc[3] += dq;
-    acc[4] = fmaf(shat, dq, acc[4]);
-  }
-  block_reduce_channels<5>(acc, p.sums, 5, C, scratch);
-}
-
-// ds(n,t',v,c) = k1*(g - m1 - shat*m2)
-__device__ __forceinline__ float ds_at(const SgcnTShiftBwd& p, const float* __restrict__ qbase, long long n, int to,
-                                       int v, int c, const LerpCh& L, float mean, float invstd, float k1, float m1,
-                                       float m2, size_t pitch) {
-  const size_t o = (((size_t)n * p.T_out + to) * p.V + v) * p.C + c;
-  float g = __ldg(p.gy + o);
-  if (p.relu && !(__ldg(p.y + o) > 0.f)) g = 0.f;
-  const int ta = to * p.stride + L.y1;
-  const float s = tap_row(qbase, ta, p.T_in, pitch) * (1.f - L.fy) + tap_row(qbase, ta + 1, p.T_in, pitch) * L.fy;
-  return k1 * (g - m1 - (s - mean) * invstd * m2);
-}
-
-// dpre(n,t,v,c) = [q > 0] * ( (1-fy)*ds[(t-y1)/stride] + fy*ds[(t-y1-1)/stride] )   (taps exist only when divisible)
-// dbias[c] += dpre
-__global__ void __launch_bounds__(kPwThreads) tshift_bwd_apply_kernel(const SgcnTShiftBwd p) {
-  __shared__ float scratch[kPwThreads];
-  const int C = p.C, V = p.V, tid = threadIdx.x, c = tid % C, slot = tid / C, slots = kPwThreads / C;
-  const LerpCh L = lerp_of(p.ypos_eff[c]);
-  const float mean = p.mean[c], invstd = p.invstd[c], k1 = p.k1[c], m1 = p.m1[c], m2 = p.m2[c];
-  const size_t pitch = (size_t)V * C;
-  const long long rows = p.n_samples * p.T_in * V;
-  const int st = p.stride;
-  float acc[1] = {0.f};
-  for (long long r = (long long)blockIdx.x * slots + slot; r < rows; r += (long long)gridDim.x * slots) {
-    const long long grp = r / V;
-    const int v = (int)(r - grp * V);
-    const long long n = grp / p.T_in;
-    const int t = (int)(grp - n * p.T_in);
-    const float* qbase = p.q + ((size_t)n * p.T_in * V + v) * C + c;
-    const size_t o = (size_t)r * C + c;
-    float d = 0.f;
-    if (p.q[o] > 0.f) {
-      const int r0 = t - L.y1, r1 = t - L.y1 - 1;     // output-row coordinates times stride
-      if (r0 >= 0 && r0 % st == 0 && r0 / st < p.T_out)
-        d = (1.f - L.fy) * ds_at(p, qbase, n, r0 / st, v, c, L, mean, invstd, k1, m1, m2, pitch);
-      if (r1 >= 0 && r1 % st == 0 && r1 / st < p.T_out)
-        d = fmaf(L.fy, ds_at(p, qbase, n, r1 / st, v, c, L, mean, invstd, k1, m1, m2, pitch), d);
+  for (int v = k.warp; v < V; v += k.nw) {
+    const float* qb = p.q + ((size_t)k.n * Ti * V + v) * C + k.c;
+    const size_t ob = ((size_t)k.n * To * V + v) * C + k.c;
+    const float* yb = p.relu ? p.y + ob : p.gy + ob;            // without ReLU the mask source is irrelevant
+    float qa = S1 ? tap(qb, to0 + L.y1, Ti, pitch) : 0.f;
+    for (int to = to0; to < to1; to += kUnrollWide) {
+      float q0[S1 ? 1 : kUnrollWide], q1[kUnrollWide], gv[kUnrollWide], yv[kUnrollWide];
+#pragma unroll
+      for (int u = 0; u < kUnrollWide; ++u) {
+        const int tc = min(to + u, to1 - 1);
+        const int ta = tc * st + L.y1;
+        q1[u] = tap(qb, ta + 1, Ti, pitch);
+        if (!S1) q0[u] = tap(qb, ta, Ti, pitch);
+        gv[u] = __ldg(p.gy + ob + (size_t)tc * pitch);
+        yv[u] = __ldg(yb + (size_t)tc * pitch);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnrollWide; ++u)
+        if (to + u < to1) {
+          const float a = S1 ? qa : q0[S1 ? 0 : u];
+          const float s = fmaf(L.f, q1[u], L.g * a);
+          const float dq = q1[u] - a;
+          qa = q1[u];
+          const float shat = (s - mean) * invstd;
+          const float g = (!p.relu || yv[u] > 0.f) ? gv[u] : 0.f;
+          acc[0] += g;
+          acc[1] = fmaf(g, shat, acc[1]);
+          acc[2] = fmaf(g, dq, acc[2]);
+          acc[3] += dq;
+          acc[4] = fmaf(shat, dq, acc[4]);
+        }
     }
-    p.dpre[o] = d;
-    acc[0] += d;
   }
-  block_reduce_channels<1>(acc, p.dbias, 1, C, scratch);
+  block_reduce_channels<5>(acc, p.sums, k.c, scratch);
 }
 
-// du = Shift_1^T(dp);  sums3[c] += { du, du*hhat, dp * dU }  with dU = U(t+y1+1) - U(t+y1), U = BN(h) zero padded
-__global__ void __launch_bounds__(kPwThreads) tshift_in_bwd_stats_kernel(const SgcnTShiftInBwd p) {
-  __shared__ float scratch[kPwThreads * 3];
-  const int C = p.C, V = p.V, T = p.T, tid = threadIdx.x, c = tid % C, slot = tid / C, slots = kPwThreads / C;
-  const LerpCh L = lerp_of(p.ypos_eff[c]);
-  const float mean = p.mean[c], invstd = p.invstd[c], sc = p.scale[c], sh = p.shift[c];
-  const size_t pitch = (size_t)V * C;
-  const long long rows = p.n_samples * T * V;
+struct BwdCh {
+  float mean, invstd, k1, m1, m2;
+};
+// ds(to) = k1*(g - m1 - shat*m2) for an output frame inside [0, T_out), else 0
+__device__ __forceinline__ float ds_eval(bool valid, float g, float y, int relu, float qa, float qb, const LerpCh& L,
+                                         const BwdCh& B) {
+  if (!valid) return 0.f;
+  if (relu && !(y > 0.f)) g = 0.f;
+  const float s = fmaf(L.f, qb, L.g * qa);
+  return B.k1 * (g - B.m1 - (s - B.mean) * B.invstd * B.m2);
+}
+
+// stride 1:  dpre(t) = [Q(t) > 0] * ( g*ds(t-y1) + f*ds(t-y1-1) ),  ds(to) uses s(to) = g*Q(to+y1) + f*Q(to+y1+1)
+// walk over input frames t; to = t - y1; the previous ds and the tap Q(t+1) slide along in registers
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_bwd_apply_s1_kernel(const SgcnTShiftBwd p, int tper,
+                                                                            int nchunks) {
+  __shared__ float scratch[kMaxWarps * 32];
+  const Col k = col_of(p.C, nchunks);
+  const int C = p.C, V = p.V, T = p.T_in;
+  const int pitch = V * C;
+  const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
+  const BwdCh B = {__ldg(p.mean + k.c), __ldg(p.invstd + k.c), __ldg(p.k1 + k.c), __ldg(p.m1 + k.c), __ldg(p.m2 + k.c)};
+  const int relu = p.relu;
+  const int t0 = k.chunk * tper, t1 = min(T, t0 + tper);
+  float acc[1] = {0.f};
+  for (int v = k.warp; v < V; v += k.nw) {
+    const size_t cb = ((size_t)k.n * T * V + v) * C + k.c;
+    const float* qb = p.q + cb;
+    const float* gb = p.gy + cb;
+    const float* yb = relu ? p.y + cb : gb;
+    float* db = p.dpre + cb;
+    // warm-up: ds of output frame to = t0 - y1 - 1
+    float qa = tap(qb, t0, T, pitch);
+    float ds_prev;
+    {
+      const int to = t0 - L.y1 - 1;
+      ds_prev = ds_eval(inside(to, T), ldrow(gb, to, T, pitch), ldrow(yb, to, T, pitch), relu,
+                        tap(qb, t0 - 1, T, pitch), qa, L, B);
+    }
+    for (int t = t0; t < t1; t += kUnroll) {
+      float q1[kUnroll], gv[kUnroll], yv[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int tc = min(t + u, t1 - 1);
+        const int to = tc - L.y1;
+        q1[u] = tap(qb, tc + 1, T, pitch);
+        gv[u] = ldrow(gb, to, T, pitch);
+        yv[u] = ldrow(yb, to, T, pitch);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (t + u < t1) {
+          const int to = t + u - L.y1;
+          const float ds = ds_eval((unsigned)to < (unsigned)T, gv[u], yv[u], relu, qa, q1[u], L, B);
+          const float d = (qa > 0.f) ? fmaf(L.f, ds_prev, L.g * ds) : 0.f;
+          db[(size_t)(t + u) * pitch] = d;
+          acc[0] += d;
+          ds_prev = ds;
+          qa = q1[u];
+        }
+    }
+  }
+  block_reduce_channels<1>(acc, p.dbias, k.c, scratch);
+}
+
+// stride 2 (K3): output frame to feeds input frames t = 2*to + y1 (weight g) and t + 1 (weight f); frames that no
+// output frame touches get 0.  Walk over output frames.
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_bwd_apply_s2_kernel(const SgcnTShiftBwd p, int tper,
+                                                                            int nchunks) {
+  __shared__ float scratch[kMaxWarps * 32];
+  const Col k = col_of(p.C, nchunks);
+  const int C = p.C, V = p.V, Ti = p.T_in, To = p.T_out;
+  const int pitch = V * C;
+  const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
+  const BwdCh B = {__ldg(p.mean + k.c), __ldg(p.invstd + k.c), __ldg(p.k1 + k.c), __ldg(p.m1 + k.c), __ldg(p.m2 + k.c)};
+  const int relu = p.relu;
+  const int to0 = k.chunk * tper, to1 = min(To, to0 + tper);
+  float acc[1] = {0.f};
+  for (int v = k.warp; v < V; v += k.nw) {
+    const float* qb = p.q + ((size_t)k.n * Ti * V + v) * C + k.c;
+    float* db = p.dpre + ((size_t)k.n * Ti * V + v) * C + k.c;
+    const size_t ob = ((size_t)k.n * To * V + v) * C + k.c;
+    const float* yb = relu ? p.y + ob : p.gy + ob;
+    if (k.chunk == 0)                                     // frames before the first touched one
+      for (int t = 0; t < min(Ti, L.y1); ++t) db[(size_t)t * pitch] = 0.f;
+    if (k.chunk == nchunks - 1)                           // frames after the last touched one
+      for (int t = max(0, 2 * To + L.y1); t < Ti; ++t) db[(size_t)t * pitch] = 0.f;
+    for (int to = to0; to < to1; to += kUnroll) {
+      float q0[kUnroll], q1[kUnroll], gv[kUnroll], yv[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int tc = min(to + u, to1 - 1);
+        const int ta = tc * 2 + L.y1;
+        q0[u] = tap(qb, ta, Ti, pitch);
+        q1[u] = tap(qb, ta + 1, Ti, pitch);
+        gv[u] = __ldg(p.gy + ob + (size_t)tc * pitch);
+        yv[u] = __ldg(yb + (size_t)tc * pitch);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (to + u < to1) {
+          const int ta = (to + u) * 2 + L.y1;
+          const float ds = ds_eval(true, gv[u], yv[u], relu, q0[u], q1[u], L, B);
+          if ((unsigned)ta < (unsigned)Ti) {
+            const float d = (q0[u] > 0.f) ? L.g * ds : 0.f;
+            db[(size_t)ta * pitch] = d;
+            acc[0] += d;
+          }
+          if ((unsigned)(ta + 1) < (unsigned)Ti) {
+            const float d = (q1[u] > 0.f) ? L.f * ds : 0.f;
+            db[(size_t)(ta + 1) * pitch] = d;
+            acc[0] += d;
+          }
+        }
+    }
+  }
+  block_reduce_channels<1>(acc, p.dbias, k.c, scratch);
+}
+
+// ------------------------------------------------------------------------------------------------ BN + input shift, backward
+// p = Shift_1(U), U = BN(h) zero padded; du = Shift_1^T(dp).  Re-indexed over the frame r of dp:
+//   sum_t du            = sum_r dp(r) * ( g*[r+y1 in range] + f*[r+y1+1 in range] )
+//   sum_t du * hhat(t)  = sum_r dp(r) * ( g*hhat(r+y1) + f*hhat(r+y1+1) )          (hhat zero padded)
+//   d/dypos             = sum_r dp(r) * ( U(r+y1+1) - U(r+y1) )
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_in_bwd_stats_kernel(const SgcnTShiftInBwd p, int tper,
+                                                                            int nchunks) {
+  __shared__ float scratch[kMaxWarps * 32 * 3];
+  const Col k = col_of(p.C, nchunks);
+  const int C = p.C, V = p.V, T = p.T;
+  const int pitch = V * C;
+  const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
+  const float mean = __ldg(p.mean + k.c), invstd = __ldg(p.invstd + k.c), sc = __ldg(p.scale + k.c),
+              sh = __ldg(p.shift + k.c);
+  const int t0 = k.chunk * tper, t1 = min(T, t0 + tper);
   float acc[3] = {0.f, 0.f, 0.f};
-  for (long long r = (long long)blockIdx.x * slots + slot; r < rows; r += (long long)gridDim.x * slots) {
-    const long long grp = r / V;
-    const int v = (int)(r - grp * V);
-    const long long n = grp / T;
-    const int t = (int)(grp - n * T);
-    const size_t pb = ((size_t)n * T * V + v) * C + c;
-    const float* dpb = p.dp + pb;
-    const float* hb = p.h + pb;
-    const float du = (1.f - L.fy) * tap_row(dpb, t - L.y1, T, pitch) + L.fy * tap_row(dpb, t - L.y1 - 1, T, pitch);
-    const size_t o = (size_t)r * C + c;
-    const float hv = p.h[o];
-    const int ta = t + L.y1;
-    const float u0 = (ta >= 0 && ta < T) ? fmaf(sc, __ldg(hb + (size_t)ta * pitch), sh) : 0.f;
-    const float u1 = (ta + 1 >= 0 && ta + 1 < T) ? fmaf(sc, __ldg(hb + (size_t)(ta + 1) * pitch), sh) : 0.f;
-    acc[0] += du;
-    acc[1] = fmaf(du, (hv - mean) * invstd, acc[1]);
-    acc[2] = fmaf(p.dp[o], u1 - u0, acc[2]);
+  for (int v = k.warp; v < V; v += k.nw) {
+    const size_t cb = ((size_t)k.n * T * V + v) * C + k.c;
+    const float* dpb = p.dp + cb;
+    const float* hb = p.h + cb;
+    float ha = ldrow(hb, t0 + L.y1, T, pitch);               // validity is applied per use below
+    for (int r = t0; r < t1; r += kUnrollWide) {
+      float dv[kUnrollWide], h1[kUnrollWide];
+#pragma unroll
+      for (int u = 0; u < kUnrollWide; ++u) {
+        const int rc = min(r + u, t1 - 1);
+        dv[u] = __ldg(dpb + (size_t)rc * pitch);
+        h1[u] = ldrow(hb, rc + L.y1 + 1, T, pitch);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnrollWide; ++u)
+        if (r + u < t1) {
+          const int ta = r + u + L.y1;
+          const bool ia = (unsigned)ta < (unsigned)T, ib = (unsigned)(ta + 1) < (unsigned)T;
+          const float ua = ia ? fmaf(sc, ha, sh) : 0.f, ub = ib ? fmaf(sc, h1[u], sh) : 0.f;
+          const float na = ia ? (ha - mean) * invstd : 0.f, nb = ib ? (h1[u] - mean) * invstd : 0.f;
+          acc[0] = fmaf(dv[u], (ia ? L.g : 0.f) + (ib ? L.f : 0.f), acc[0]);
+          acc[1] = fmaf(dv[u], fmaf(L.f, nb, L.g * na), acc[1]);
+          acc[2] = fmaf(dv[u], ub - ua, acc[2]);
+          ha = h1[u];
+        }
+    }
   }
-  block_reduce_channels<3>(acc, p.sums, 3, C, scratch);
+  block_reduce_channels<3>(acc, p.sums, k.c, scratch);
 }
 
-// gh = [h > 0] * k*(du - m1 - hhat*m2);   per-(v,d) sums for the BN1d backward: { gh, gh * zhat }
-__global__ void __launch_bounds__(kPwThreads) tshift_in_bwd_apply_kernel(const SgcnTShiftInBwd p) {
-  const int C = p.C, V = p.V, T = p.T, tid = threadIdx.x, c = tid % C, slot = tid / C, slots = kPwThreads / C;
-  const LerpCh L = lerp_of(p.ypos_eff[c]);
-  const float mean = p.mean[c], invstd = p.invstd[c], k = p.k1[c], m1 = p.m1[c], m2 = p.m2[c];
-  const size_t pitch = (size_t)V * C;
-  const long long groups = p.n_samples * T;
-  // joints are the outer loop so that the per-(v,c) sums live in two registers
-  for (int v = slot; v < V; v += slots) {
-    const float zmean = p.z ? __ldg(p.zmean + v * C + c) : 0.f, zinv = p.z ? __ldg(p.zinvstd + v * C + c) : 0.f;
+// gh(t) = [h(t) > 0] * k*(du(t) - m1 - hhat(t)*m2),  du(t) = g*dp(t-y1) + f*dp(t-y1-1);
+// per-(v,c) sums for the BN1d backward of the spatial unit: { gh, gh * zhat }
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_in_bwd_apply_kernel(const SgcnTShiftInBwd p, int tper,
+                                                                            int nchunks) {
+  const Col k = col_of(p.C, nchunks);
+  const int C = p.C, V = p.V, T = p.T;
+  const int pitch = V * C;
+  const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
+  const float mean = __ldg(p.mean + k.c), invstd = __ldg(p.invstd + k.c), kk = __ldg(p.k1 + k.c),
+              m1 = __ldg(p.m1 + k.c), m2 = __ldg(p.m2 + k.c);
+  const int t0 = k.chunk * tper, t1 = min(T, t0 + tper);
+  const bool has_z = p.z != nullptr;
+  for (int v = k.warp; v < V; v += k.nw) {
+    const size_t cb = ((size_t)k.n * T * V + v) * C + k.c;
+    const float* dpb = p.dp + cb;
+    const float* hb = p.h + cb;
+    const float* zb = has_z ? p.z + cb : hb;
+    float* gb = p.gh + cb;
+    const float zmean = has_z ? __ldg(p.zmean + v * C + k.c) : 0.f, zinv = has_z ? __ldg(p.zinvstd + v * C + k.c) : 0.f;
     float s0 = 0.f, s1 = 0.f;
-    for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-      const long long n = grp / T;
-      const int t = (int)(grp - n * T);
-      const float* dpb = p.dp + ((size_t)n * T * V + v) * C + c;
-      const float du = (1.f - L.fy) * tap_row(dpb, t - L.y1, T, pitch) + L.fy * tap_row(dpb, t - L.y1 - 1, T, pitch);
-      const size_t o = ((size_t)grp * V + v) * C + c;
-      const float hv = p.h[o];
-      float g = k * (du - m1 - (hv - mean) * invstd * m2);
-      if (p.relu_h && !(hv > 0.f)) g = 0.f;
-      p.gh[o] = g;
-      if (p.z) {
-        s0 += g;
-        s1 = fmaf(g, (p.z[o] - zmean) * zinv, s1);
+    float dprev = tap(dpb, t0 - L.y1 - 1, T, pitch);
+    for (int t = t0; t < t1; t += kUnroll) {
+      float d0[kUnroll], hv[kUnroll], zv[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int tc = min(t + u, t1 - 1);
+        d0[u] = tap(dpb, tc - L.y1, T, pitch);
+        hv[u] = __ldg(hb + (size_t)tc * pitch);
+        zv[u] = __ldg(zb + (size_t)tc * pitch);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (t + u < t1) {
+          const float du = fmaf(L.f, dprev, L.g * d0[u]);
+          dprev = d0[u];
+          float g = kk * (du - m1 - (hv[u] - mean) * invstd * m2);
+          if (p.relu_h && !(hv[u] > 0.f)) g = 0.f;
+          gb[(size_t)(t + u) * pitch] = g;
+          s0 += g;
+          s1 = fmaf(g, (zv[u] - zmean) * zinv, s1);
+        }
+    }
+    if (has_z) {
+      atomicAdd(p.vd_sums + 2 * ((size_t)v * C + k.c), (double)s0);
+      atomicAdd(p.vd_sums + 2 * ((size_t)v * C + k.c) + 1, (double)s1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ group walkers
+// stats[c] += { sum x, sum x^2 }   (BatchNorm2d statistics of a stand-alone Shift_tcn input, model/shift_gcn.py:66)
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) channel_stats_kernel(const float* __restrict__ x,
+                                                                       double* __restrict__ stats, long long groups,
+                                                                       int gper, int nchunks, int V, int C) {
+  __shared__ float scratch[kMaxWarps * 32 * 2];
+  const Col k = col_of(C, nchunks);
+  const long long g0 = (long long)k.chunk * gper;
+  const int ng = (int)((groups - g0) < gper ? (groups - g0) : gper);
+  const int pitch = V * C;
+  float acc[2] = {0.f, 0.f};
+  for (int v = k.warp; v < V; v += k.nw) {
+    const float* xp = x + ((size_t)g0 * V + v) * C + k.c;
+    for (int g = 0; g < ng; g += kUnrollMax) {
+      float xv[kUnrollMax];
+#pragma unroll
+      for (int u = 0; u < kUnrollMax; ++u) {
+        const float val = __ldg(xp + (size_t)min(g + u, ng - 1) * pitch);
+        xv[u] = (g + u < ng) ? val : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kUnrollMax; ++u) {
+        acc[0] += xv[u];
+        acc[1] = fmaf(xv[u], xv[u], acc[1]);
       }
     }
-    if (p.z) {
-      atomicAdd(p.vd_sums + 2 * ((size_t)v * C + c), (double)s0);
-      atomicAdd(p.vd_sums + 2 * ((size_t)v * C + c) + 1, (double)s1);
-    }
   }
-}
-
-// stats[c] += { sum x, sum x^2 }   (BatchNorm2d statistics of a stand-alone Shift_tcn input, model/shift_gcn.py:66)
-__global__ void __launch_bounds__(kPwThreads) channel_stats_kernel(const float* __restrict__ x,
-                                                                   double* __restrict__ stats, long long rows, int C) {
-  __shared__ float scratch[kPwThreads * 2];
-  const int tid = threadIdx.x, c = tid % C, slot = tid / C, slots = kPwThreads / C;
-  float acc[2] = {0.f, 0.f};
-  for (long long r = (long long)blockIdx.x * slots + slot; r < rows; r += (long long)gridDim.x * slots) {
-    const float v = x[(size_t)r * C + c];
-    acc[0] += v;
-    acc[1] = fmaf(v, v, acc[1]);
-  }
-  block_reduce_channels<2>(acc, stats, 2, C, scratch);
+  block_reduce_channels<2>(acc, stats, k.c, scratch);
 }
 
 // gh = g * [h > 0];  vd_sums[v,c] += { gh, gh * zhat }      (stand-alone Shift_gcn backward, model/shift_gcn.py:137-141)
-__global__ void __launch_bounds__(kPwThreads) relu_bn1d_bwd_stats_kernel(const float* __restrict__ g,
-                                                                         const float* __restrict__ h,
-                                                                         const float* __restrict__ z,
-                                                                         const float* __restrict__ zmean,
-                                                                         const float* __restrict__ zinvstd,
-                                                                         float* __restrict__ gh,
-                                                                         double* __restrict__ vd_sums, long long groups,
-                                                                         int V, int C) {
-  const int tid = threadIdx.x, c = tid % C, slot = tid / C, slots = kPwThreads / C;
-  for (int v = slot; v < V; v += slots) {
-    const float zm = __ldg(zmean + v * C + c), zi = __ldg(zinvstd + v * C + c);
+__global__ void __launch_bounds__(kMaxWarps * 32, 2) relu_bn1d_bwd_stats_kernel(const float* __restrict__ g,
+                                                                             const float* __restrict__ h,
+                                                                             const float* __restrict__ z,
+                                                                             const float* __restrict__ zmean,
+                                                                             const float* __restrict__ zinvstd,
+                                                                             float* __restrict__ gh,
+                                                                             double* __restrict__ vd_sums,
+                                                                             long long groups, int gper, int nchunks,
+                                                                             int V, int C) {
+  const Col k = col_of(C, nchunks);
+  const long long g0 = (long long)k.chunk * gper;
+  const int ng = (int)((groups - g0) < gper ? (groups - g0) : gper);
+  const int pitch = V * C;
+  for (int v = k.warp; v < V; v += k.nw) {
+    const float zm = __ldg(zmean + v * C + k.c), zi = __ldg(zinvstd + v * C + k.c);
+    const size_t o0 = ((size_t)g0 * V + v) * C + k.c;
     float s0 = 0.f, s1 = 0.f;
-    for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-      const size_t o = ((size_t)grp * V + v) * C + c;
-      const float gv = (h[o] > 0.f) ? g[o] : 0.f;
-      gh[o] = gv;
-      s0 += gv;
-      s1 = fmaf(gv, (z[o] - zm) * zi, s1);
+    for (int gi = 0; gi < ng; gi += kUnroll) {
+      float gv[kUnroll], hv[kUnroll], zv[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const size_t o = o0 + (size_t)min(gi + u, ng - 1) * pitch;
+        gv[u] = __ldg(g + o);
+        hv[u] = __ldg(h + o);
+        zv[u] = __ldg(z + o);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (gi + u < ng) {
+          const float val = (hv[u] > 0.f) ? gv[u] : 0.f;
+          gh[o0 + (size_t)(gi + u) * pitch] = val;
+          s0 += val;
+          s1 = fmaf(val, (zv[u] - zm) * zi, s1);
+        }
     }
-    atomicAdd(vd_sums + 2 * ((size_t)v * C + c), (double)s0);
-    atomicAdd(vd_sums + 2 * ((size_t)v * C + c) + 1, (double)s1);
+    atomicAdd(vd_sums + 2 * ((size_t)v * C + k.c), (double)s0);
+    atomicAdd(vd_sums + 2 * ((size_t)v * C + k.c) + 1, (double)s1);
   }
 }
 
 // out = g * [y > 0]
-__global__ void __launch_bounds__(kPwThreads) relu_mask_grad_kernel(const float4* __restrict__ g,
-                                                                    const float4* __restrict__ y,
-                                                                    float4* __restrict__ out, long long n4) {
+__global__ void __launch_bounds__(256) relu_mask_grad_kernel(const float4* __restrict__ g, const float4* __restrict__ y,
+                                                             float4* __restrict__ out, long long n4) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = g[i], b = y[i];
     out[i] = make_float4(b.x > 0.f ? a.x : 0.f, b.y > 0.f ? a.y : 0.f, b.z > 0.f ? a.z : 0.f, b.w > 0.f ? a.w : 0.f);
   }
 }
 
-static int pw_grid(long long work_items, int per_block) {
-  long long b = (work_items + per_block - 1) / per_block;
-  long long cap = (long long)num_sms() * 8;
-  if (b > cap) b = cap;
-  if (b < 1) b = 1;
-  return (int)b;
+// ------------------------------------------------------------------------------------------------ launch geometry
+struct Geo {
+  int threads, nchunks, per;
+  unsigned grid;
+};
+// `outer` independent walks (samples) of `len` steps each, split into chunks so that the grid has a few waves
+static Geo geometry(int C, int V, long long outer, long long len, int min_per) {
+  Geo g;
+  g.threads = 32 * ceil_div(V, 2);
+  const long long base = (long long)(C / 32) * (outer > 0 ? outer : 1);
+  const long long want = (long long)num_sms() * 8;            // ~2 waves of 4 resident blocks per SM
+  long long nch = (want + base - 1) / base;
+  const long long max_ch = (len + min_per - 1) / min_per;
+  if (nch > max_ch) nch = max_ch;
+  if (nch < 1) nch = 1;
+  g.per = (int)((len + nch - 1) / nch);
+  g.nchunks = (int)((len + g.per - 1) / g.per);
+  g.grid = (unsigned)(base * g.nchunks);
+  return g;
 }
 
-static int check_c(int C) {
+static int check_cv(int C, int V) {
   if (C != 64 && C != 128 && C != 256) return set_error("pointwise: channel count must be 64, 128 or 256");
+  if (V < 1 || V > 2 * kMaxWarps) return set_error("pointwise: num_point must be in [1, 40]");
   return 0;
 }
 
@@ -318,26 +568,30 @@ using namespace sgcn;
 extern "C" int sgcn_bn_res_relu_fwd(const float* z, const float* res, float* h, const float* scale, const float* shift,
                                     double* stats_out, long long rows, int V, int D, int relu, void* stream) {
   if (!z || !h || !scale || !shift) return set_error("sgcn_bn_res_relu_fwd: null pointer");
-  if (int rc = check_c(D)) return rc;
+  if (int rc = check_cv(D, V)) return rc;
   if (rows <= 0) return 0;
-  bn_res_relu_fwd_kernel<<<pw_grid(rows, kPwThreads / D * 8), kPwThreads, 0, (cudaStream_t)stream>>>(
-      z, res, h, scale, shift, stats_out, rows, V, D, relu);
+  if (rows % V != 0) return set_error("sgcn_bn_res_relu_fwd: rows must be a multiple of V");
+  const long long groups = rows / V;
+  const Geo g = geometry(D, V, 1, groups, 8);
+  bn_res_relu_fwd_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(z, res, h, scale, shift, stats_out, groups,
+                                                                        g.per, g.nchunks, V, D, relu);
   return check_launch("bn_res_relu_fwd_kernel");
 }
 
 extern "C" int sgcn_tshift_fwd(const SgcnTShift* p, int mode, void* stream) {
   if (!p || !p->q || !p->ypos_eff) return set_error("sgcn_tshift_fwd: null pointer");
-  if (int rc = check_c(p->C)) return rc;
+  if (int rc = check_cv(p->C, p->V)) return rc;
   if (p->stride < 1 || p->T_out != p->T_in / p->stride) return set_error("sgcn_tshift_fwd: T_out must be T_in / stride");
-  const long long rows = p->n_samples * p->T_out * p->V;
-  if (rows <= 0) return 0;
-  const int grid = pw_grid(rows, kPwThreads / p->C * 8);
+  if (p->n_samples <= 0 || p->T_out <= 0) return 0;
+  const Geo g = geometry(p->C, p->V, p->n_samples, p->T_out, 8);
   if (mode == 0) {
     if (!p->stats) return set_error("sgcn_tshift_fwd(stats): null stats");
-    tshift_fwd_kernel<0><<<grid, kPwThreads, 0, (cudaStream_t)stream>>>(*p);
+    if (p->stride == 1) tshift_fwd_kernel<0, true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
+    else tshift_fwd_kernel<0, false><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
   } else {
     if (!p->out || !p->scale || !p->shift) return set_error("sgcn_tshift_fwd(apply): null pointer");
-    tshift_fwd_kernel<1><<<grid, kPwThreads, 0, (cudaStream_t)stream>>>(*p);
+    if (p->stride == 1) tshift_fwd_kernel<1, true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
+    else tshift_fwd_kernel<1, false><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
   }
   return check_launch("tshift_fwd_kernel");
 }
@@ -345,57 +599,79 @@ extern "C" int sgcn_tshift_fwd(const SgcnTShift* p, int mode, void* stream) {
 extern "C" int sgcn_tshift_bwd(const SgcnTShiftBwd* p, int mode, void* stream) {
   if (!p || !p->q || !p->gy || !p->ypos_eff || !p->mean || !p->invstd) return set_error("sgcn_tshift_bwd: null pointer");
   if (p->relu && !p->y) return set_error("sgcn_tshift_bwd: relu mask needs y");
-  if (int rc = check_c(p->C)) return rc;
+  if (int rc = check_cv(p->C, p->V)) return rc;
   if (p->stride < 1 || p->T_out != p->T_in / p->stride) return set_error("sgcn_tshift_bwd: T_out must be T_in / stride");
+  if (p->n_samples <= 0) return 0;
   if (mode == 0) {
     if (!p->sums) return set_error("sgcn_tshift_bwd(stats): null sums");
-    const long long rows = p->n_samples * p->T_out * p->V;
-    if (rows <= 0) return 0;
-    tshift_bwd_stats_kernel<<<pw_grid(rows, kPwThreads / p->C * 8), kPwThreads, 0, (cudaStream_t)stream>>>(*p);
+    if (p->T_out <= 0) return 0;
+    const Geo g = geometry(p->C, p->V, p->n_samples, p->T_out, 8);
+    if (p->stride == 1) tshift_bwd_stats_kernel<true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
+    else tshift_bwd_stats_kernel<false><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
     return check_launch("tshift_bwd_stats_kernel");
   }
   if (!p->dpre || !p->dbias || !p->k1 || !p->m1 || !p->m2) return set_error("sgcn_tshift_bwd(apply): null pointer");
-  const long long rows = p->n_samples * p->T_in * p->V;
-  if (rows <= 0) return 0;
-  tshift_bwd_apply_kernel<<<pw_grid(rows, kPwThreads / p->C * 8), kPwThreads, 0, (cudaStream_t)stream>>>(*p);
-  return check_launch("tshift_bwd_apply_kernel");
+  if (p->stride == 1) {
+    const Geo g = geometry(p->C, p->V, p->n_samples, p->T_in, 8);
+    tshift_bwd_apply_s1_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
+    return check_launch("tshift_bwd_apply_s1_kernel");
+  }
+  if (p->stride == 2) {   // the reference's backward exists for strides 1 and 2 only (shift_cuda_kernel.cu:156-256)
+    if (p->T_out <= 0) return set_error("sgcn_tshift_bwd(apply): empty output");
+    const Geo g = geometry(p->C, p->V, p->n_samples, p->T_out, 8);
+    tshift_bwd_apply_s2_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
+    return check_launch("tshift_bwd_apply_s2_kernel");
+  }
+  return set_error("sgcn_tshift_bwd(apply): stride must be 1 or 2 (as in the reference's backward kernels)");
 }
 
 extern "C" int sgcn_tshift_in_bwd(const SgcnTShiftInBwd* p, int mode, void* stream) {
   if (!p || !p->dp || !p->h || !p->ypos_eff || !p->mean || !p->invstd) return set_error("sgcn_tshift_in_bwd: null pointer");
-  if (int rc = check_c(p->C)) return rc;
-  const long long rows = p->n_samples * p->T * p->V;
-  if (rows <= 0) return 0;
+  if (int rc = check_cv(p->C, p->V)) return rc;
+  if (p->n_samples <= 0 || p->T <= 0) return 0;
   if (mode == 0) {
     if (!p->sums || !p->scale || !p->shift) return set_error("sgcn_tshift_in_bwd(stats): null pointer");
-    tshift_in_bwd_stats_kernel<<<pw_grid(rows, kPwThreads / p->C * 8), kPwThreads, 0, (cudaStream_t)stream>>>(*p);
+    const Geo g = geometry(p->C, p->V, p->n_samples, p->T, 8);
+    tshift_in_bwd_stats_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
     return check_launch("tshift_in_bwd_stats_kernel");
   }
   if (!p->gh || !p->k1 || !p->m1 || !p->m2) return set_error("sgcn_tshift_in_bwd(apply): null pointer");
   if (p->z && (!p->zmean || !p->zinvstd || !p->vd_sums)) return set_error("sgcn_tshift_in_bwd(apply): null BN1d tables");
-  const long long groups = p->n_samples * p->T;
-  long long grid = groups < (long long)num_sms() * 4 ? groups : (long long)num_sms() * 4;
-  tshift_in_bwd_apply_kernel<<<(unsigned)grid, kPwThreads, 0, (cudaStream_t)stream>>>(*p);
+  const Geo g = geometry(p->C, p->V, p->n_samples, p->T, 16);
+  tshift_in_bwd_apply_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
   return check_launch("tshift_in_bwd_apply_kernel");
 }
 
 extern "C" int sgcn_channel_stats(const float* x, double* stats, long long rows, int C, void* stream) {
   if (!x || !stats) return set_error("sgcn_channel_stats: null pointer");
-  if (int rc = check_c(C)) return rc;
+  if (C != 64 && C != 128 && C != 256) return set_error("pointwise: channel count must be 64, 128 or 256");
   if (rows <= 0) return 0;
-  channel_stats_kernel<<<pw_grid(rows, kPwThreads / C * 8), kPwThreads, 0, (cudaStream_t)stream>>>(x, stats, rows, C);
-  return check_launch("channel_stats_kernel");
+  // any row order works for per-channel statistics: walk pseudo-groups of 32 rows
+  const int V = 32;
+  const long long groups = rows / V;
+  if (groups > 0) {
+    const Geo g = geometry(C, V, 1, groups, 8);
+    channel_stats_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(x, stats, groups, g.per, g.nchunks, V, C);
+    if (int rc = check_launch("channel_stats_kernel")) return rc;
+  }
+  const int tail = (int)(rows - groups * V);
+  if (tail > 0) {
+    channel_stats_kernel<<<C / 32, 32 * ceil_div(tail, 2), 0, (cudaStream_t)stream>>>(x + (size_t)groups * V * C, stats,
+                                                                                     1, 1, 1, tail, C);
+    return check_launch("channel_stats_kernel(tail)");
+  }
+  return 0;
 }
 
 extern "C" int sgcn_relu_bn1d_bwd_stats(const float* g, const float* h, const float* z, const float* zmean,
                                         const float* zinvstd, float* gh, double* vd_sums, long long groups, int V,
                                         int C, void* stream) {
   if (!g || !h || !z || !zmean || !zinvstd || !gh || !vd_sums) return set_error("sgcn_relu_bn1d_bwd_stats: null pointer");
-  if (int rc = check_c(C)) return rc;
+  if (int rc = check_cv(C, V)) return rc;
   if (groups <= 0) return 0;
-  long long grid = groups < (long long)num_sms() * 4 ? groups : (long long)num_sms() * 4;
-  relu_bn1d_bwd_stats_kernel<<<(unsigned)grid, kPwThreads, 0, (cudaStream_t)stream>>>(g, h, z, zmean, zinvstd, gh,
-                                                                                     vd_sums, groups, V, C);
+  const Geo geo = geometry(C, V, 1, groups, 16);
+  relu_bn1d_bwd_stats_kernel<<<geo.grid, geo.threads, 0, (cudaStream_t)stream>>>(g, h, z, zmean, zinvstd, gh, vd_sums,
+                                                                                groups, geo.per, geo.nchunks, V, C);
   return check_launch("relu_bn1d_bwd_stats_kernel");
 }
 
@@ -403,7 +679,10 @@ extern "C" int sgcn_relu_mask_grad(const float* g, const float* y, float* out, l
   if (!g || !y || !out) return set_error("sgcn_relu_mask_grad: null pointer");
   if (numel % 4 != 0) return set_error("sgcn_relu_mask_grad: numel must be a multiple of 4");
   if (numel <= 0) return 0;
-  relu_mask_grad_kernel<<<pw_grid(numel / 4, kPwThreads * 4), kPwThreads, 0, (cudaStream_t)stream>>>(
-      (const float4*)g, (const float4*)y, (float4*)out, numel / 4);
+  long long blocks = (numel / 4 + 1023) / 1024;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  relu_mask_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)g, (const float4*)y,
+                                                                           (float4*)out, numel / 4);
   return check_launch("relu_mask_grad_kernel");
 }
