@@ -6,20 +6,23 @@
 //   temporal (autograd of model/shift_gcn.py:69):   A = dpre (grad wrt the conv output, pre-ReLU), B = p (shifted BN(h))
 //            -> temporal_linear.weight.grad [Cout, Cin]
 //
-// Warp-specialised, persistent: one CTA per SM owns an (A-channel block, B-channel block) pair (<= 128 x 128) and a
-// strided subset of the row tiles; its partial dW stays in TMEM for the whole kernel and is flushed once.
+// Warp-specialised, persistent: one CTA per SM walks a strided subset of the row tiles and keeps its partial dW
+// -- the WHOLE [CA x CB] matrix, up to 2 x 256 TMEM columns -- in tensor memory for the entire kernel, so every
+// activation element is read from HBM exactly once; one coalesced atomic flush at the end.
 //   warp 0            issues tcgen05.mma (one lane), owns the TMEM allocation
-//   3 builder groups  of 8 warps; group g builds tiles g, g+3, ... of this CTA into operand stage g:
-//                     global loads (lane <-> channel, 128-byte coalesced, ~30 independent loads in flight per thread
-//                     -- the register file is the staging buffer) -> prologue math -> TF32 -> swizzled smem
+//   builder groups    of 8 warps; group g builds tiles g, g+NG, ... of this CTA into operand stage g:
+//                     global loads (lane <-> channel, 128-byte coalesced, 20-40 independent loads in flight per thread
+//                     -- the register file is the staging buffer) -> prologue math -> TF32 -> swizzled smem.
+//                     The plain A operand of the temporal case is copied by cp.async straight into the swizzled
+//                     layout (the tensor core reads fp32 bit patterns as TF32).
 //   full[s] / free[s] mbarriers per stage: 256 builder arrivals / one tcgen05.commit
-// While one group waits for its loads the other two are computing or their stages are being consumed, so HBM
-// always has ~2 tiles of requests in flight per SM.
+// While one group waits for its loads the others are computing or their stages are being consumed, so HBM always
+// has about two tiles of requests in flight per SM.
 //
 // Both operands are MN-major (the row index is the contraction dimension, channels contiguous) in the
 // SWIZZLE_128B_BASE32B layout -- the only one tcgen05 accepts for MN-major 32-bit operands: blocks of
-// [KR rows x 32 channels], 128 B per row, 32-byte chunks XOR-ed with (row % 4).  The M extent of the MMA is always
-// 128: when the A block has only 64 channels the upper 64 TMEM lanes hold don't-care values that are never read.
+// [KR rows x 32 channels], 128 B per row, 32-byte chunks XOR-ed with (row % 4).  The M extent of every MMA is 128:
+// when A has only 64 channels the upper 64 TMEM lanes hold don't-care values that are never read.
 #include "capi_internal.h"
 #include "common.cuh"
 #include "wgrad.h"
@@ -28,67 +31,77 @@ namespace sgcn {
 
 enum { WG_SPATIAL = 0, WG_TEMPORAL = 1 };
 
-constexpr int kWgGroups = 3;
+constexpr int kWgMaxGroups = 3;
 constexpr int kWgGroupThreads = 256;
-constexpr int kWgThreads = 32 + kWgGroups * kWgGroupThreads;   // 800
-constexpr int kWgGMax = 5;                                     // groups per tile (V >= 25)
+constexpr int kWgThreads = 32 + kWgMaxGroups * kWgGroupThreads;   // 800
+constexpr int kWgSmemBudget = 200 * 1024;
 
 struct WgGeom {
-  int MC, NC;         // channels of the A / B block of one CTA
   int G;              // row groups per tile
-  int KR;             // tile rows rounded up to the MMA K granularity (8)
+  int KR;             // tile rows = G * VP  (VP = joints padded to a multiple of 8)
   int blk;            // bytes of one [KR x 32] operand block
   int stage;          // bytes of one operand stage (A blocks then B blocks)
+  int nstages;        // operand stages == builder groups
 };
 
+__host__ __device__ constexpr int wg_vp(int V) { return ((V + 7) / 8) * 8; }
+
+// largest tile (G in {4,3,2,1}) that leaves room for three stages (two for the widest layers)
 __host__ __device__ inline WgGeom wg_geom(int CA, int CB, int V) {
   WgGeom g;
-  g.MC = CA < 128 ? CA : 128;
-  g.NC = CB < 128 ? CB : 128;
-  g.G = (g.MC + g.NC <= 128 ? 128 : 64) / V;
-  if (g.G < 1) g.G = 1;
-  if (g.G > kWgGMax) g.G = kWgGMax;
-  g.KR = (g.G * V + 7) & ~7;
-  g.blk = g.KR * 128;
-  g.stage = ((g.MC + g.NC) / 32) * g.blk;
+  const int cands[4] = {4, 3, 2, 1};
+  for (int i = 0; i < 4; ++i) {
+    g.G = cands[i];
+    g.KR = g.G * wg_vp(V);
+    g.blk = g.KR * 128;
+    g.stage = ((CA + CB) / 32) * g.blk;
+    g.nstages = kWgSmemBudget / g.stage;
+    if (g.nstages > kWgMaxGroups) g.nstages = kWgMaxGroups;
+    if (g.KR <= 128 && g.nstages >= (g.G == 1 ? 1 : 3)) break;
+  }
   return g;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void sts_tf32(uint8_t* p, float v) { *(float*)p = to_tf32(v); }
 
-__device__ __forceinline__ void sts_tf32(uint8_t* base, uint32_t off, float v) { *(float*)(base + off) = to_tf32(v); }
-
-template <int MODE>
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p) {
+// Tile row order: row(g, v) = g * VP + v.  The contraction runs over rows, so any order works as long as A and B
+// agree; this one makes the swizzle phase (row & 3) of every row a builder thread writes equal to (warp & 3),
+// i.e. all shared-memory offsets are "per-thread constant + compile-time immediate".
+template <int MODE, int V, int G>
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p, const WgGeom geo) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int V = p.V, CA = p.CA, CB = p.CB;
-  const WgGeom geo = wg_geom(CA, CB, V);
-  const int G = geo.G, MC = geo.MC, NC = geo.NC;
-  const int nb = CB / NC, npairs = (CA / MC) * nb;
-  const int pair = blockIdx.x % npairs, split = blockIdx.x / npairs, nsplit = gridDim.x / npairs;
-  const int a0 = (pair / nb) * MC, b0 = (pair % nb) * NC;
-  const uint32_t ablocks = MC / 32;
+  const int CA = p.CA, CB = p.CB;
+  constexpr int KV = (V + 7) / 8;                           // joint slots per builder warp
+  constexpr int VP = KV * 8;
+  constexpr int KR = G * VP;
+  constexpr int BLK = KR * 128;
+  const uint32_t ablocks = CA / 32, bblocks = CB / 32;
+  const int mblocks = (CA + 127) / 128;
+  const int NG = geo.nstages;
+  const uint32_t stage_bytes = (ablocks + bblocks) * BLK;
 
-  __shared__ uint64_t bar_full[kWgGroups], bar_free[kWgGroups], bar_done;
+  __shared__ uint64_t bar_full[kWgMaxGroups], bar_free[kWgMaxGroups], bar_done;
   __shared__ uint32_t tmem_base_s;
 
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
-    for (int s = 0; s < kWgGroups; ++s) {
+    for (int s = 0; s < kWgMaxGroups; ++s) {
       mbar_init(&bar_full[s], kWgGroupThreads);
       mbar_init(&bar_free[s], 1);
     }
     mbar_init(&bar_done, 1);
     fence_mbar_init();
   }
-  const uint32_t tmem_cols = NC <= 64 ? 64u : 128u;
+  const int need_cols = mblocks * CB;
+  const uint32_t tmem_cols = need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u));
   if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
-  {  // padding rows (and the never-written upper A blocks) must be finite zeros
-    const int n16 = kWgGroups * geo.stage / 16;
+  {  // padding rows (joints V..VP-1) must be finite zeros; they are never written afterwards
+    const int n16 = NG * (int)stage_bytes / 16;
     for (int i = tid; i < n16; i += kWgThreads) ((float4*)smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   fence_proxy_async();
@@ -98,166 +111,213 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p)
   const uint32_t tmem_base = tmem_base_s;
 
   const long long ntiles = (p.groups + G - 1) / G;
+  const long long split = blockIdx.x, nsplit = gridDim.x;
   const long long my_tiles = split < ntiles ? (ntiles - split + nsplit - 1) / nsplit : 0;
 
   if (warp == 0) {
     // ================================================================ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(128, NC, 1, 1);
-      const int ksteps = geo.KR / 8;
+      const uint32_t idesc = umma_idesc_tf32(128, CB, 1, 1);
       for (long long j = 0; j < my_tiles; ++j) {
-        const int s = (int)(j % kWgGroups);
-        mbar_wait(&bar_full[s], (uint32_t)((j / kWgGroups) & 1));
+        const int s = (int)(j % NG);
+        mbar_wait(&bar_full[s], (uint32_t)((j / NG) & 1));
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem) + (uint32_t)s * (uint32_t)geo.stage;
-        const uint32_t sb = sa + ablocks * (uint32_t)geo.blk;
-        for (int ks = 0; ks < ksteps; ++ks)
-          umma_tf32(tmem_base, umma_desc(sa + ks * 1024, (uint32_t)geo.blk, 512, 1),
-                    umma_desc(sb + ks * 1024, (uint32_t)geo.blk, 512, 1), idesc, (j | ks) ? 1u : 0u);
+        const uint32_t sa = smem_u32(smem) + (uint32_t)s * stage_bytes;
+        const uint32_t sb = sa + ablocks * (uint32_t)BLK;
+        for (int mb = 0; mb < mblocks; ++mb)
+#pragma unroll
+          for (int ks = 0; ks < KR / 8; ++ks)
+            umma_tf32(tmem_base + (uint32_t)(mb * CB), umma_desc(sa + (uint32_t)mb * 4u * BLK + ks * 1024, BLK, 512, 1),
+                      umma_desc(sb + ks * 1024, BLK, 512, 1), idesc, (j | ks) ? 1u : 0u);
         tc_commit(&bar_free[s]);
       }
       tc_commit(&bar_done);
     }
     __syncwarp();
-  } else {
+  } else if ((tid - 32) / kWgGroupThreads < NG) {
     // ================================================================ builders
-    const int gt = tid - 32;
-    const int grp = gt / kWgGroupThreads;                 // builder group == operand stage
-    const int w = (gt % kWgGroupThreads) >> 5;            // warp inside the group, 0..7
-    uint8_t* sA = smem + (size_t)grp * geo.stage;
-    uint8_t* sB = sA + (size_t)ablocks * geo.blk;
-    // MN-major swizzle: offset(row, ch) = row*128 + (((ch>>3) ^ (row&3)) << 5) + ((ch&7) << 2)
-    const uint32_t lane_lo = (uint32_t)((lane & 7) << 2), lane_hi = (uint32_t)(lane >> 3);
-    const long long last_group = p.groups - 1;
+    const int gt = (tid - 32) % kWgGroupThreads;
+    const int grp = (tid - 32) / kWgGroupThreads;          // builder group == operand stage
+    const int w = gt >> 5;                                  // warp inside the group, 0..7
+    uint8_t* sA = smem + (size_t)grp * stage_bytes;
+    uint8_t* sB = sA + (size_t)ablocks * BLK;
+    // offset of (row = g*VP + 8*slot + w, channel = lane) inside a block: thread constant + (g*VP + 8*slot)*128
+    const uint32_t toff = (uint32_t)w * 128u + ((((uint32_t)lane >> 3) ^ ((uint32_t)w & 3u)) << 5) + (((uint32_t)lane & 7u) << 2);
+    const int T = p.T;
 
-    for (long long j = grp; j < my_tiles; j += kWgGroups) {
+    for (long long j = grp; j < my_tiles; j += NG) {
       const long long tile = split + j * nsplit;
       const long long g0 = tile * G;
       const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
-      const int rows_valid = ng * V;
-      const long long row0 = g0 * V;
-      const long long use = j / kWgGroups;
+      const long long use = j / NG;
       if (use > 0) mbar_wait(&bar_free[grp], (uint32_t)((use - 1) & 1));   // the MMAs of the previous use are done
 
       if (MODE == WG_TEMPORAL) {
-        // ---- A = dpre rows as they are: rows r = w + 8 i share the swizzle phase r & 3 == w & 3
-        const uint32_t cw = ((lane_hi ^ (uint32_t)(w & 3)) << 5) + lane_lo;
-        for (uint32_t blk = 0; blk < ablocks; ++blk) {
-          const float* src = p.a_src + (size_t)row0 * CA + a0 + blk * 32 + lane;
-          uint8_t* dst = sA + (size_t)blk * geo.blk + cw;
-          float val[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r = min(w + 8 * i, rows_valid - 1);
-            val[i] = __ldg(src + (size_t)r * CA);
+        // ---- A = dpre rows as they are: 16-byte cp.async pieces straight into the swizzled blocks
+        {
+          const int ppr = CA >> 2;                           // 16-byte pieces per row (16, 32 or 64)
+          const int k = gt & (ppr - 1);                      // this thread's piece inside a row
+          const uint32_t kk = (uint32_t)k & 7u;
+          const uint32_t poff = ((uint32_t)k >> 3) * BLK + ((kk & 1u) << 4);
+          const float* src = p.a_src + (size_t)g0 * V * CA + (size_t)k * 4;
+          const int rstep = kWgGroupThreads / ppr;
+          for (int q = gt / ppr; q < ng * V; q += rstep) {   // q = g*V + v
+            const int g = q / V, v = q - g * V;
+            const uint32_t r = (uint32_t)(g * VP + v);
+            cp_async16(sA + poff + r * 128u + ((((kk >> 1) ^ (r & 3u))) << 5), src + (size_t)q * CA);
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r = w + 8 * i;
-            if (r < rows_valid) sts_tf32(dst, (uint32_t)r * 128u, val[i]);
-          }
+          cp_async_commit();
         }
         // ---- B = p[(g,v), c] = (1-f) U(t+y1) + f U(t+y1+1),  U = sa*h + sb inside the sample, 0 outside
-        for (uint32_t blk = 0; blk < (uint32_t)NC / 32; ++blk) {
-          const int c = b0 + blk * 32 + lane;
+        const int t0 = (int)(g0 % T);                        // frame of the tile's first group
+        const bool straddle = t0 + ng > T;                   // the tile crosses into the next sample (warp uniform)
+        const int rel_lo = (int)(-g0 < -(1 << 20) ? -(1 << 20) : -g0);                     // clamp window of the
+        const long long room = p.groups - 1 - g0;                                          // tap frame groups,
+        const int rel_hi = (int)(room > (1 << 20) ? (1 << 20) : room);                     // relative to g0
+        for (uint32_t blk = 0; blk < bblocks; ++blk) {
+          const int c = (int)blk * 32 + lane;
           const float ypos = __ldg(p.b_tab2 + c), sa = __ldg(p.b_tab0 + c), sb = __ldg(p.b_tab1 + c);
           const float fl = floorf(ypos);
           const int y1 = (int)fl;
           const float f = ypos - fl, f0 = 1.f - f;
-          uint8_t* dst = sB + (size_t)blk * geo.blk;
-          const int t0 = (int)(g0 % p.T);                    // frame of the tile's first group
-          for (int v = w; v < V; v += 8) {
-            float L[kWgGMax + 1];
+          const float* src = p.b_src + ((size_t)g0 * V + w) * CB + c;     // (group g0, joint w, channel c)
+          const int gstride = V * CB;
+          uint8_t* dst = sB + (size_t)blk * BLK + toff;
+          float L[KV][G + 1];
 #pragma unroll
-            for (int k = 0; k <= kWgGMax; ++k) {
-              long long gi = g0 + y1 + k;                    // frame group of tap k (validity applied below)
-              gi = gi < 0 ? 0 : (gi > last_group ? last_group : gi);
-              L[k] = (k <= ng) ? __ldg(p.b_src + ((size_t)gi * V + v) * CB + c) : 0.f;
+          for (int sl = 0; sl < KV; ++sl) {
+            const int v = min(w + 8 * sl, V - 1);
+#pragma unroll
+            for (int k = 0; k <= G; ++k) {
+              const int rel = min(max(y1 + k, rel_lo), rel_hi);
+              L[sl][k] = __ldg(src + (long long)rel * gstride + (v - w) * CB);
             }
+          }
+          if (!straddle) {
+            bool ok[G + 1];
 #pragma unroll
-            for (int g = 0; g < kWgGMax; ++g)
-              if (g < ng) {
-                int t = t0 + g;                              // tiles may straddle a sample boundary
-                if (t >= p.T) t -= p.T;
-                const float u0 = ((unsigned)(t + y1) < (unsigned)p.T) ? fmaf(sa, L[g], sb) : 0.f;
-                const float u1 = ((unsigned)(t + y1 + 1) < (unsigned)p.T) ? fmaf(sa, L[g + 1], sb) : 0.f;
-                const uint32_t r = (uint32_t)(g * V + v);
-                sts_tf32(dst, r * 128u + ((lane_hi ^ (r & 3)) << 5) + lane_lo, fmaf(f, u1, f0 * u0));
+            for (int k = 0; k <= G; ++k) ok[k] = (unsigned)(t0 + y1 + k) < (unsigned)T;
+#pragma unroll
+            for (int sl = 0; sl < KV; ++sl)
+              if (w + 8 * sl < V) {
+                float U[G + 1];
+#pragma unroll
+                for (int k = 0; k <= G; ++k) U[k] = ok[k] ? fmaf(sa, L[sl][k], sb) : 0.f;
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+                  if (g < ng) sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(f, U[g + 1], f0 * U[g]));
+              }
+          } else {
+#pragma unroll
+            for (int sl = 0; sl < KV; ++sl)
+              if (w + 8 * sl < V) {
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+                  if (g < ng) {
+                    int t = t0 + g;
+                    if (t >= T) t -= T;
+                    const float u0 = ((unsigned)(t + y1) < (unsigned)T) ? fmaf(sa, L[sl][g], sb) : 0.f;
+                    const float u1 = ((unsigned)(t + y1 + 1) < (unsigned)T) ? fmaf(sa, L[sl][g + 1], sb) : 0.f;
+                    sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(f, u1, f0 * u0));
+                  }
               }
           }
         }
+        cp_async_wait_all();
       } else {
         // ---- A = xm[(g,u), c] = x[g, (u+c) % V, c] * maskmul[u, c]          (model/shift_gcn.py:127-129)
         for (uint32_t blk = 0; blk < ablocks; ++blk) {
-          const int c = a0 + blk * 32 + lane;
+          const int c = (int)blk * 32 + lane;
           const int cm = c % V;
-          uint8_t* dst = sA + (size_t)blk * geo.blk;
-          for (int u = w; u < V; u += 8) {
+          const float* src = p.a_src + (size_t)g0 * V * CA + c;
+          const int gstride = V * CA;
+          uint8_t* dst = sA + (size_t)blk * BLK + toff;
+          float val[KV][G], mm[KV];
+#pragma unroll
+          for (int sl = 0; sl < KV; ++sl) {
+            const int u = min(w + 8 * sl, V - 1);
             int sv = u + cm;
             if (sv >= V) sv -= V;
-            const float mm = __ldg(p.a_tab0 + u * CA + c);
-            const float* src = p.a_src + ((size_t)row0 + sv) * CA + c;
-            float val[kWgGMax];
+            mm[sl] = __ldg(p.a_tab0 + u * CA + c);
 #pragma unroll
-            for (int g = 0; g < kWgGMax; ++g) val[g] = __ldg(src + (size_t)min(g, ng - 1) * V * CA);
-#pragma unroll
-            for (int g = 0; g < kWgGMax; ++g)
-              if (g < ng) {
-                const uint32_t r = (uint32_t)(g * V + u);
-                sts_tf32(dst, r * 128u + ((lane_hi ^ (r & 3)) << 5) + lane_lo, val[g] * mm);
-              }
+            for (int g = 0; g < G; ++g) val[sl][g] = __ldg(src + min(g, ng - 1) * gstride + sv * CA);
           }
+#pragma unroll
+          for (int sl = 0; sl < KV; ++sl)
+            if (w + 8 * sl < V) {
+#pragma unroll
+              for (int g = 0; g < G; ++g)
+                if (g < ng) sts_tf32(dst + (g * VP + 8 * sl) * 128, val[sl][g] * mm[sl]);
+            }
         }
         // ---- B = dy[(g,u), d] = dz[g, (u+d) % V, d],  dz = alpha*gh + beta*z + gamma   (BN1d backward folded
         //      into three per-(v,d) tables; inverse of the shift_out gather, model/shift_gcn.py:135-137)
-        for (uint32_t blk = 0; blk < (uint32_t)NC / 32; ++blk) {
-          const int d = b0 + blk * 32 + lane;
+        for (uint32_t blk = 0; blk < bblocks; ++blk) {
+          const int d = (int)blk * 32 + lane;
           const int dm = d % V;
-          uint8_t* dst = sB + (size_t)blk * geo.blk;
-          for (int u = w; u < V; u += 8) {
-            int sv = u + dm;
-            if (sv >= V) sv -= V;
-            const float al = __ldg(p.b_tab0 + sv * CB + d), be = __ldg(p.b_tab1 + sv * CB + d),
-                        ga = __ldg(p.b_tab2 + sv * CB + d);
-            const size_t o = ((size_t)row0 + sv) * CB + d;
-            float gv[kWgGMax], zv[kWgGMax];
+          const size_t o = (size_t)g0 * V * CB + d;
+          const int gstride = V * CB;
+          uint8_t* dst = sB + (size_t)blk * BLK + toff;
+          constexpr int KH = (KV + 1) / 2;                   // two half passes keep the batch at <= 2*G*KH loads
 #pragma unroll
-            for (int g = 0; g < kWgGMax; ++g) {
-              const size_t og = o + (size_t)min(g, ng - 1) * V * CB;
-              gv[g] = __ldg(p.b_src + og);
-              zv[g] = __ldg(p.b_src2 + og);
+          for (int half = 0; half < 2; ++half) {
+            float gv[KH][G], zv[KH][G], al[KH], be[KH], ga[KH];
+#pragma unroll
+            for (int i = 0; i < KH; ++i) {
+              const int sl = half * KH + i;
+              const int u = min(w + 8 * sl, V - 1);
+              int sv = u + dm;
+              if (sv >= V) sv -= V;
+              al[i] = __ldg(p.b_tab0 + sv * CB + d);
+              be[i] = __ldg(p.b_tab1 + sv * CB + d);
+              ga[i] = __ldg(p.b_tab2 + sv * CB + d);
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                const size_t og = o + (size_t)(min(g, ng - 1) * gstride + sv * CB);
+                gv[i][g] = __ldg(p.b_src + og);
+                zv[i][g] = __ldg(p.b_src2 + og);
+              }
             }
 #pragma unroll
-            for (int g = 0; g < kWgGMax; ++g)
-              if (g < ng) {
-                const uint32_t r = (uint32_t)(g * V + u);
-                sts_tf32(dst, r * 128u + ((lane_hi ^ (r & 3)) << 5) + lane_lo, fmaf(al, gv[g], fmaf(be, zv[g], ga)));
+            for (int i = 0; i < KH; ++i) {
+              const int sl = half * KH + i;
+              if (sl < KV && w + 8 * sl < V) {
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+                  if (g < ng) sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(al[i], gv[i][g], fmaf(be[i], zv[i][g], ga[i])));
               }
+            }
           }
         }
       }
-      if (rows_valid < G * V) {   // partial last tile: rows of missing groups may hold an earlier tile
-        const int nblk = (MC + NC) / 32;
-        for (int r = rows_valid + w; r < G * V; r += 8)
-          for (int blk = 0; blk < nblk; ++blk) *(float*)(sA + (size_t)blk * geo.blk + r * 128 + lane * 4) = 0.f;
+      if (ng < G) {   // partial last tile: rows of missing groups may hold an earlier tile
+        const int nblk = (int)(ablocks + bblocks);
+        for (int r = ng * VP + w; r < KR; r += 8)
+          for (int blk = 0; blk < nblk; ++blk) *(float*)(sA + (size_t)blk * BLK + r * 128 + lane * 4) = 0.f;
       }
       fence_proxy_async();
       mbar_arrive(&bar_full[grp]);
     }
 
-    // ================================================================ flush: TMEM lane = A channel
+    // ================================================================ flush (warps 1..4): TMEM lane = A channel.
+    // Transposed through shared memory so that the atomics of a warp hit 32 consecutive addresses.
     if (warp >= 1 && warp <= 4 && my_tiles > 0) {
-      mbar_wait(&bar_done, 0);
+      mbar_wait(&bar_done, 0);          // every MMA has completed: the operand stages are free to be reused
       tc_fence_after();
       const int q = warp & 3;                               // TMEM lane quarter this warp may read
-      const int ch = q * 32 + lane;
-      for (int c0 = 0; c0 < NC; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        if (ch < MC) {
-          float* dst = p.dw + (size_t)(a0 + ch) * CB + b0 + c0;
+      float* tr = (float*)smem + q * (32 * 33);
+      for (int mb = 0; mb < mblocks; ++mb) {
+        const int ch0 = mb * 128 + q * 32;
+        if (ch0 >= CA) continue;                            // (warp-uniform)
+        for (int c0 = 0; c0 < CB; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * CB + c0), v);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) atomicAdd(dst + k, v[k]);
+          for (int k = 0; k < 32; ++k) tr[lane * 33 + k] = v[k];
+          __syncwarp();
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) atomicAdd(p.dw + (size_t)(ch0 + r) * CB + c0 + lane, tr[r * 33 + lane]);
+          __syncwarp();
         }
       }
     }
@@ -267,25 +327,41 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p)
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-template <int MODE>
-static int launch_wgrad(const SgcnWgrad& p, cudaStream_t s) {
-  const WgGeom geo = wg_geom(p.CA, p.CB, p.V);
-  const int npairs = (p.CA / geo.MC) * (p.CB / geo.NC);
-  const size_t smem = 1024 + (size_t)kWgGroups * geo.stage + 64;
-  auto kern = wgrad_kernel<MODE>;
+template <int MODE, int V, int G>
+static int launch_wgrad_vg(const SgcnWgrad& p, const WgGeom& geo, cudaStream_t s) {
+  const size_t smem = 1024 + (size_t)geo.nstages * geo.stage + 64;
+  auto kern = wgrad_kernel<MODE, V, G>;
   static thread_local size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error("wgrad smem attribute", e);
     configured = smem;
   }
-  const long long ntiles = (p.groups + geo.G - 1) / geo.G;
+  const long long ntiles = (p.groups + G - 1) / G;
   if (ntiles == 0) return 0;
-  long long nsplit = num_sms() / npairs;
-  if (nsplit < 1) nsplit = 1;
-  if (nsplit > ntiles) nsplit = ntiles;
-  kern<<<(unsigned)(nsplit * npairs), kWgThreads, smem, s>>>(p);
+  long long grid = num_sms();
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, kWgThreads, smem, s>>>(p, geo);
   return check_launch("wgrad_kernel");
+}
+
+template <int MODE, int V>
+static int launch_wgrad_v(const SgcnWgrad& p, cudaStream_t s) {
+  const WgGeom geo = wg_geom(p.CA, p.CB, V);
+  if (geo.nstages < 1) return set_error("sgcn_wgrad: operand stage does not fit in shared memory");
+  switch (geo.G) {
+    case 4: return launch_wgrad_vg<MODE, V, 4>(p, geo, s);
+    case 3: return launch_wgrad_vg<MODE, V, 3>(p, geo, s);
+    case 2: return launch_wgrad_vg<MODE, V, 2>(p, geo, s);
+    default: return launch_wgrad_vg<MODE, V, 1>(p, geo, s);
+  }
+}
+
+template <int MODE>
+static int launch_wgrad(const SgcnWgrad& p, cudaStream_t s) {
+  if (p.V == 25) return launch_wgrad_v<MODE, 25>(p, s);
+  if (p.V == 33) return launch_wgrad_v<MODE, 33>(p, s);
+  return set_error("sgcn_wgrad: num_point must be 25 (NTU) or 33 (MediaPipe)");
 }
 
 }  // namespace sgcn
@@ -294,7 +370,6 @@ extern "C" int sgcn_wgrad(const SgcnWgrad* pp, int mode, void* stream) {
   using namespace sgcn;
   if (!pp) return set_error("sgcn_wgrad: null params");
   const SgcnWgrad& p = *pp;
-  if (p.V < 25 || p.V > 40) return set_error("sgcn_wgrad: num_point must be in [25, 40]");
   if ((p.CA != 64 && p.CA != 128 && p.CA != 256) || (p.CB != 64 && p.CB != 128 && p.CB != 256))
     return set_error("sgcn_wgrad: channel counts must be 64, 128 or 256");
   if (!p.a_src || !p.b_src || !p.dw) return set_error("sgcn_wgrad: null tensor");

@@ -112,7 +112,7 @@ class Shift_tcn(nn.Module):
 
     def fused_supported(self, x):
         c, v = x.shape[1], x.shape[3]
-        if not (self.in_channels == self.out_channels == c and c in FUSED_CHANNELS and 25 <= v <= 40):
+        if not (self.in_channels == self.out_channels == c and c in FUSED_CHANNELS and v in (25, 33)):
             return False
         if x.shape[2] // self.shift_out.stride < 1:
             return False
@@ -174,7 +174,7 @@ class Shift_gcn(nn.Module):
 
     def fused_supported(self, x0):
         return (self.in_channels in FUSED_CHANNELS and self.out_channels in FUSED_CHANNELS
-                and x0.shape[1] == self.in_channels and x0.shape[3] == self.num_point and 25 <= self.num_point <= 40)
+                and x0.shape[1] == self.in_channels and x0.shape[3] == self.num_point and self.num_point in (25, 33))
 
     def _args(self):
         return (self.Linear_weight, self.Linear_bias, self.Feature_Mask, self.bn.weight, self.bn.bias)
