@@ -503,6 +503,8 @@ static int launch_nch(const SgcnRowGemm& p, cudaStream_t s) {
   }
 }
 
+int spatial_bwd_launch(const SgcnRowGemm& p, cudaStream_t s);      // spatial_bwd.cu
+
 }  // namespace sgcn
 
 extern "C" int sgcn_rowgemm(const SgcnRowGemm* pp, int pro, int epi, void* stream) {
@@ -532,6 +534,7 @@ extern "C" int sgcn_rowgemm(const SgcnRowGemm* pp, int pro, int epi, void* strea
   if (pro == PRO_DY && epi == EPI_SPATIAL_BWD) {
     if (!p.in1 || !p.pro_a || !p.pro_b || !p.pro_c || !p.epi_a || !p.xin || !p.red0)
       return set_error("spatial bwd: null tensor / table");
+    if (p.V == 25 || p.V == 33) return spatial_bwd_launch(p, s);      // warp-specialised kernel (spatial_bwd.cu)
     return launch_nch<PRO_DY, EPI_SPATIAL_BWD>(p, s);
   }
   return set_error("sgcn_rowgemm: unsupported prologue/epilogue combination");

@@ -121,3 +121,31 @@ class FlatSGDTrainer:
         self.reduce_gradients()
         self.step()
         return loss
+
+    # ------------------------------------------------------------------------------------------------ CUDA graph
+    def capture(self, x, label, loss_fn=torch.nn.functional.cross_entropy, warmup=3):
+        """Capture one whole training step (zero-grad, forward, loss, backward, all-reduce, K5, SGD) into a CUDA
+        graph.  Every kernel of this library is stream-ordered and allocation-free, so the step replays with a
+        single launch; ``x`` / ``label`` fix the shapes.  ``warmup`` eager steps run first (they are real steps)."""
+        if not x.is_cuda:
+            raise RuntimeError("capture needs CUDA tensors")
+        self._static_x = x.clone()
+        self._static_y = label.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):              # also initialises the momentum buffer (steps == 0 branch)
+                self.train_step(self._static_x, self._static_y, loss_fn)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self.train_step(self._static_x, self._static_y, loss_fn)
+        return self
+
+    def replay(self, x, label):
+        """one captured step on new data (copied into the static buffers on the current stream)"""
+        self._static_x.copy_(x, non_blocking=True)
+        self._static_y.copy_(label, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss
