@@ -503,7 +503,9 @@ static int launch_nch(const SgcnRowGemm& p, cudaStream_t s) {
   }
 }
 
-int spatial_bwd_launch(const SgcnRowGemm& p, cudaStream_t s);      // spatial_bwd.cu
+int spatial_bwd_launch(const SgcnRowGemm& p, cudaStream_t s);            // spatial_bwd.cu
+int spatial_fwd_launch(const SgcnRowGemm& p, int fused, cudaStream_t s);  // spatial_fwd.cu
+int temporal_gemm_launch(const SgcnRowGemm& p, int lerp, cudaStream_t s); // temporal_gemm.cu
 
 }  // namespace sgcn
 
@@ -518,23 +520,32 @@ extern "C" int sgcn_rowgemm(const SgcnRowGemm* pp, int pro, int epi, void* strea
   if (p.groups < 0) return set_error("sgcn_rowgemm: negative group count");
   if (!p.in0 || !p.out || !p.wimg) return set_error("sgcn_rowgemm: null tensor");
   cudaStream_t s = (cudaStream_t)stream;
+  // warp-specialised kernels (fused_gemm.cuh, spatial_bwd.cu) cover the skeletons of the reference's configs;
+  // other joint counts in [25, 40] keep the generic kernel of this file
+  const bool fast = p.V == 25 || p.V == 33;
   if (pro == PRO_SPATIAL && epi == EPI_ROT_RAW) {
     if (!p.pro_a || !p.stats) return set_error("spatial fwd: null mask / stats");
+    if (fast) return spatial_fwd_launch(p, 0, s);
     return launch_nch<PRO_SPATIAL, EPI_ROT_RAW>(p, s);
   }
   if (pro == PRO_SPATIAL && epi == EPI_ROT_FUSED) {
     if (!p.pro_a || !p.epi_a || !p.epi_b) return set_error("spatial fwd (fused): null table");
+    if (fast) return spatial_fwd_launch(p, 1, s);
     return launch_nch<PRO_SPATIAL, EPI_ROT_FUSED>(p, s);
   }
   if (pro == PRO_LERP && epi == EPI_LINEAR) {
     if (!p.pro_a || !p.pro_b || !p.pro_c || p.T < 1) return set_error("temporal fwd: null table / bad T");
+    if (fast && p.K == p.N) return temporal_gemm_launch(p, 1, s);
     return launch_nch<PRO_LERP, EPI_LINEAR>(p, s);
   }
-  if (pro == PRO_PLAIN && epi == EPI_LINEAR) return launch_nch<PRO_PLAIN, EPI_LINEAR>(p, s);
+  if (pro == PRO_PLAIN && epi == EPI_LINEAR) {
+    if (fast && p.K == p.N) return temporal_gemm_launch(p, 0, s);
+    return launch_nch<PRO_PLAIN, EPI_LINEAR>(p, s);
+  }
   if (pro == PRO_DY && epi == EPI_SPATIAL_BWD) {
     if (!p.in1 || !p.pro_a || !p.pro_b || !p.pro_c || !p.epi_a || !p.xin || !p.red0)
       return set_error("spatial bwd: null tensor / table");
-    if (p.V == 25 || p.V == 33) return spatial_bwd_launch(p, s);      // warp-specialised kernel (spatial_bwd.cu)
+    if (fast) return spatial_bwd_launch(p, s);
     return launch_nch<PRO_DY, EPI_SPATIAL_BWD>(p, s);
   }
   return set_error("sgcn_rowgemm: unsupported prologue/epilogue combination");

@@ -1,0 +1,26 @@
+// temporal_gemm.cu -- instantiations of the warp-specialised row-GEMM (fused_gemm.cuh) for the 1x1 convolution of the
+// temporal unit: forward with the BN + fractional temporal shift prologue (model/shift_gcn.py:66-70) and the plain
+// backward-data contraction.
+#include "fused_gemm.cuh"
+
+namespace sgcn {
+
+template <int PRO, int V>
+static int temporal_gemm_v(const SgcnRowGemm& p, cudaStream_t s) {
+  using namespace fg;
+  if (p.K != p.N) return set_error("temporal 1x1 convolution: in and out channels must match");
+  switch (p.K) {
+    case 64: return launch<PRO, EPI_LINEAR, V, 64, 64>(p, s);
+    case 128: return launch<PRO, EPI_LINEAR, V, 128, 128>(p, s);
+    case 256: return launch<PRO, EPI_LINEAR, V, 256, 256>(p, s);
+    default: return set_error("temporal 1x1 convolution: channels must be 64, 128 or 256");
+  }
+}
+
+int temporal_gemm_launch(const SgcnRowGemm& p, int lerp, cudaStream_t s) {
+  if (p.V == 25) return lerp ? temporal_gemm_v<fg::PRO_LERP, 25>(p, s) : temporal_gemm_v<fg::PRO_PLAIN, 25>(p, s);
+  if (p.V == 33) return lerp ? temporal_gemm_v<fg::PRO_LERP, 33>(p, s) : temporal_gemm_v<fg::PRO_PLAIN, 33>(p, s);
+  return set_error("temporal 1x1 convolution: num_point must be 25 (NTU) or 33 (MediaPipe)");
+}
+
+}  // namespace sgcn
