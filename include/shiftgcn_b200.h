@@ -85,7 +85,7 @@ int sgcn_rowgemm(const SgcnRowGemm* params, int prologue, int epilogue, void* st
 
 typedef struct SgcnWgrad {
   const float* a_src;   /* SPATIAL: unit input x [rows, CA]            | TEMPORAL: dpre [rows, CA] (grad wrt conv output) */
-  const float* a_tab0;  /* SPATIAL: tanh(mask)+1 [V, CA]                                                              */
+  const float* a_tab0;  /* SPATIAL: joint-rotated mask multiplier [V, CA] (maskmul_rot of sgcn_mask_prepare_rot)            */
   const float* b_src;   /* SPATIAL: grad wrt gcn output gh [rows, CB]  | TEMPORAL: tcn input h [rows, CB]              */
   const float* b_src2;  /* SPATIAL: pre-BN output z [rows, CB]                                                         */
   const float* b_tab0;  /* SPATIAL: alpha [V, CB]                      | TEMPORAL: BN scale [CB]                       */
@@ -199,6 +199,9 @@ int sgcn_bn1d_bwd_finalize(double* vd_sums, const float* gamma, const float* mea
 
 /* maskmul = tanh(mask) + 1 */
 int sgcn_mask_prepare(const float* mask, float* maskmul, int n, void* stream);
+/* same, plus the table seen from the SOURCE joint of the shift_in gather (model/shift_gcn.py:127-129):
+ * maskmul_rot[v, c] = maskmul[(v - c) mod V, c] -- what kernels that load x[., v, c] rows and scatter them need */
+int sgcn_mask_prepare_rot(const float* mask, float* maskmul, float* maskmul_rot, int V, int C, void* stream);
 /* dmask = raw * (1 - tanh(mask)^2); raw cleared */
 int sgcn_mask_grad_finalize(double* raw, const float* mask, float* dmask, int n, void* stream);
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "sgcn_tshift_in_bwd_finalize": [_vp] * 11 + [_i, _d, _d, _i, _vp],
     "sgcn_bn1d_bwd_finalize": [_vp] * 10 + [_i, _i, _d, _i, _vp],
     "sgcn_mask_prepare": [_vp, _vp, _i, _vp],
+    "sgcn_mask_prepare_rot": [_vp, _vp, _vp, _i, _i, _vp],
     "sgcn_mask_grad_finalize": [_vp, _vp, _vp, _i, _vp],
     "sgcn_prep_weight_image": [_vp, _ll, _ll, _i, _i, _vp, _vp],
     "sgcn_reduce_export": [_vp, _vp, _i, _d, _vp],

@@ -4,18 +4,21 @@
 //
 // Activations live channels-last: a logical (n, C, T, V) tensor is the row-major matrix [(n,t,v), C].  A CTA (one
 // per SM, persistent) processes tiles of G whole (n,t) groups (G*V <= 128 rows), so the joint shifts of the spatial
-// unit are permutations inside the tile.  Three warp roles, connected by mbarrier pipelines:
+// unit are permutations inside the tile.  Seven warpgroups, four roles (register budgets set with setmaxnreg):
 //
-//   builder warps    each thread owns ONE source slot (joint, 4 channels) of the 64-channel chunk and walks the
-//                    tile's groups with 128-bit loads (the next chunk's loads are issued before the current chunk is
-//                    processed, so ~2 chunks of requests are always in flight), applies the prologue and scatters
-//                    TF32 values into the K-major SWIZZLE_128B operand chunk (2 buffers, full / free barriers)
-//   MMA warp         one lane issues tcgen05.mma kind::tf32 (M = 128, N = out channels, fp32 accumulators in TMEM,
-//                    2 accumulator buffers) and streams weight chunks with cp.async.bulk when W exceeds 64 KiB
-//   epilogue warps   TMEM -> XOR-swizzled smem staging (8 warps), then each thread owns ONE destination slot
-//                    (joint, 4 channels): gathers its four values from the staging tile (this is where the output
-//                    rotation happens), applies the fused tail and stores 128 bits; cross-tile reductions
-//                    (BatchNorm statistics) stay in registers for the whole kernel
+//   builders   12 warps  stream raw [rows x 64 channel] chunks of the input into shared memory with 16-byte
+//                        cp.async (two chunks in flight, no registers involved), then run the prologue as a
+//                        shared -> shared pass with lane <-> channel: whatever row a lane reads (joint shift:
+//                        row (u+c) % V, temporal shift: frame t + floor(ypos_c)), the bank is the channel, so the
+//                        gathers are conflict free; results go TF32-rounded into the K-major SWIZZLE_128B operand
+//                        chunk.  PRO_PLAIN has no prologue: cp.async writes the operand layout directly.
+//   MMA        1 lane    tcgen05.mma kind::tf32 (M = 128 rows, N = out channels, fp32 accumulators in TMEM,
+//                        two accumulator buffers)
+//   W loader   1 lane    when the weight image exceeds 64 KiB: streams its 32-channel blocks with cp.async.bulk
+//                        (TMA) through a two-stage ring, decoupled from the MMA issuer
+//   epilogue   12 warps  TMEM -> XOR-swizzled smem staging (8 warps), then lane <-> channel again: the output
+//                        rotation is a conflict-free row gather from the staging tile, global stores are whole
+//                        128-byte row segments; BatchNorm statistics stay in registers for the whole kernel
 //
 // Variants (template PRO x EPI), with the reference code each one replaces:
 //   PRO_SPATIAL  x[r,(u+c)%V,c] * (tanh(mask)+1)            model/shift_gcn.py:123-129
@@ -35,11 +38,13 @@ namespace fg {
 enum { PRO_SPATIAL = 0, PRO_LERP = 1, PRO_PLAIN = 2 };
 enum { EPI_ROT_RAW = 0, EPI_ROT_FUSED = 1, EPI_LINEAR = 2 };
 
-constexpr int kEpiWarps = 13, kBldWarps = 13;
+constexpr int kEpiWarps = 12, kBldWarps = 12;
 constexpr int kEpiThreads = kEpiWarps * 32, kBldThreads = kBldWarps * 32;
-constexpr int kMmaWarp = kEpiWarps;
-constexpr int kThreads = (kEpiWarps + 1 + kBldWarps) * 32;       // 864
+constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1;   // warps 12..15: MMA, W loader, two spares
+constexpr int kBld0 = kEpiWarps + 4;                             // first builder warp
+constexpr int kThreads = (kEpiWarps + 4 + kBldWarps) * 32;       // 896
 constexpr int kChunkBytes = 128 * 64 * 4;                        // one [128 x 64] fp32 operand chunk / staging tile
+constexpr int kRegsEpi = 88, kRegsBld = 64, kRegsMma = 40;       // 384*88 + 384*64 + 128*40 <= 896*72
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -47,182 +52,96 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg((const float4*)p); }
-__device__ __forceinline__ float f4get(const float4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
-
-// staging tile [128 rows][64 cols] fp32, 16-byte chunks XOR-ed with (row & 15)
-__device__ __forceinline__ uint32_t stage_off(uint32_t row, uint32_t c4, uint32_t j) {
-  return row * 256u + ((c4 ^ (row & 15u)) << 4) + (j << 2);
+__device__ __forceinline__ void bld_sync() { asm volatile("bar.sync 2, %0;" ::"n"(kBldThreads) : "memory"); }
+template <int R>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-// K-major SWIZZLE_128B operand chunk (two 32-channel blocks): byte offset of (row, 16-byte chunk c4 of 16)
-__device__ __forceinline__ uint32_t op_off(uint32_t row, uint32_t c4) {
-  return (c4 >> 3) * (uint32_t)kBlockBytes + (row >> 3) * 1024u + (row & 7u) * 128u + (((c4 & 7u) ^ (row & 7u)) << 4);
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg((const float4*)p); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 template <int PRO, int EPI, int V, int K, int N>
 struct Cfg {
   static constexpr int G = 128 / V;
   static constexpr int KC = K / 64, NCH = N / 64;
-  static constexpr bool kWRes = (K * N * 4) <= 65536;
-  static constexpr int kWBytes = kWRes ? K * N * 4 : N * 256;
-  static constexpr int kSlots = V * 16;                            // (joint, 4-channel group) slots of a 64-wide chunk
-  static constexpr int kEpiRounds = (kSlots + kEpiThreads - 1) / kEpiThreads;
-  static constexpr int kBldRounds = (kSlots + kBldThreads - 1) / kBldThreads;
-  static constexpr int kWin = 3;                                   // LERP: largest tap spread handled with 128-bit loads
-  static constexpr int kLoads = PRO == PRO_LERP ? G + kWin : G;    // float4 registers of one builder work item
-  static constexpr bool kPrefetch = PRO != PRO_LERP;               // double-buffer the builder loads in registers
-  static constexpr size_t kSmem = 1024 + kWBytes + 3 * kChunkBytes + 64;
+  // weights: resident image, or 32-channel blocks streamed through a two-stage ring (the temporal-shift variant
+  // gives shared memory to its wider raw tiles instead)
+  static constexpr bool kWRes = (K * N * 4) <= (PRO == PRO_LERP ? 32768 : 65536);
+  static constexpr int kWStage = N * 128;                          // one streamed 32-channel weight block
+  static constexpr int kWBytes = kWRes ? K * N * 4 : 2 * kWStage;
+  // lane <-> channel work split: a warp owns (joint, 32-channel half) pairs k * 12 + warp, k < kJ
+  static constexpr int kPairs = 2 * V;
+  static constexpr int kJ = (kPairs + kBldWarps - 1) / kBldWarps;  // kBldWarps == kEpiWarps
+  // flattened 16-byte pieces of a [rows x 64] chunk: piece = thread + 384 * i  ->  row = (thread >> 4) + 24 * i
+  static constexpr int kTileRows = G * V;
+  static constexpr int kWin = PRO == PRO_LERP ? (K == 64 ? 3 : 2) : 0;   // distinct floor(ypos) values the raw tile covers
+  static constexpr int kRawRows = (G + kWin) * V;
+  static constexpr int kRawBytes = PRO == PRO_PLAIN ? 0 : kRawRows * 256;
+  static constexpr int kStBytes = EPI == EPI_LINEAR ? 128 * 32 * 4 : kChunkBytes;   // epilogue staging tile
+  // HBM latency x bandwidth needs >= 64 KiB of loads in flight per SM: spend what is left on input stages
+  static constexpr int kAvail = 232448 - 1600 - kWBytes - kStBytes;
+  static constexpr int kRaw2 = PRO == PRO_PLAIN ? 0 : (kAvail - 2 * kChunkBytes) / kRawBytes;
+  static constexpr int kRaw1 = PRO == PRO_PLAIN ? 0 : (kAvail - kChunkBytes) / kRawBytes;
+  static constexpr int kOpStages = PRO == PRO_PLAIN ? (kAvail / kChunkBytes < 4 ? kAvail / kChunkBytes : 4) : (kRaw2 >= 3 ? 2 : 1);
+  static constexpr int kRawStages = PRO == PRO_PLAIN ? 0 : ((kOpStages == 2 ? kRaw2 : kRaw1) < 4 ? (kOpStages == 2 ? kRaw2 : kRaw1) : 4);
+  static constexpr size_t kSmem = 1024 + kWBytes + kOpStages * kChunkBytes + kStBytes + kRawStages * kRawBytes + 64;
+  static_assert(PRO == PRO_PLAIN || kRawStages >= 2, "need at least two raw stages");
+  static_assert(kSmem <= 232448 - 512, "shared memory budget");
 };
-
-// ------------------------------------------------------------------------------------------------ builder work item
-template <int PRO, int V, int K, int G, int NL>
-struct Item {
-  float4 v[NL];
-  long long g0;
-  int slot, kc, ng;
-  // LERP only
-  int lo, span;
-};
-
-template <int PRO, int EPI, int V, int K, int N>
-__device__ __forceinline__ void issue_loads(const SgcnRowGemm& p, long long tile, int kc, int slot,
-                                            Item<PRO, V, K, Cfg<PRO, EPI, V, K, N>::G, Cfg<PRO, EPI, V, K, N>::kLoads>& it) {
-  using C = Cfg<PRO, EPI, V, K, N>;
-  constexpr int G = C::G;
-  it.g0 = tile * G;
-  it.ng = (int)((p.groups - it.g0) < G ? (p.groups - it.g0) : G);
-  it.slot = slot;
-  it.kc = kc;
-  const int sv = min(slot, C::kSlots - 1) >> 4, c4 = slot & 15;
-  const int c = kc * 64 + c4 * 4;
-  if (PRO == PRO_LERP) {
-    const float4 yp = ldg4(p.pro_c + c);
-    const int y0 = (int)floorf(yp.x), y1 = (int)floorf(yp.y), y2 = (int)floorf(yp.z), y3 = (int)floorf(yp.w);
-    it.lo = min(min(y0, y1), min(y2, y3));
-    it.span = max(max(y0, y1), max(y2, y3)) + 1 - it.lo;           // taps lo .. lo+span
-    const long long last = p.groups - 1;
-#pragma unroll
-    for (int k = 0; k < C::kLoads; ++k) {
-      long long gi = it.g0 + it.lo + k;
-      gi = gi < 0 ? 0 : (gi > last ? last : gi);
-      it.v[k] = ldg4(p.in0 + ((size_t)gi * V + sv) * K + c);
-    }
-  } else {
-    const size_t o = ((size_t)it.g0 * V + sv) * K + c;
-#pragma unroll
-    for (int g = 0; g < G; ++g) it.v[g] = ldg4(p.in0 + o + (size_t)min(g, it.ng - 1) * V * K);
-  }
-}
-
-template <int PRO, int EPI, int V, int K, int N>
-__device__ __forceinline__ void build_item(const SgcnRowGemm& p, uint8_t* op,
-                                           const Item<PRO, V, K, Cfg<PRO, EPI, V, K, N>::G, Cfg<PRO, EPI, V, K, N>::kLoads>& it) {
-  using C = Cfg<PRO, EPI, V, K, N>;
-  constexpr int G = C::G;
-  if (it.slot >= C::kSlots) return;
-  const int sv = it.slot >> 4, c4 = it.slot & 15;
-  const int c = it.kc * 64 + c4 * 4;
-  if (PRO == PRO_PLAIN) {
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-      if (g < it.ng) {
-        const float4 x = it.v[g];
-        *(float4*)(op + op_off((uint32_t)(g * V + sv), (uint32_t)c4)) = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
-      }
-  } else if (PRO == PRO_SPATIAL) {
-    // xm[(g,u), c] = x[g, (u+c) % V, c] * maskmul[u, c]: the loaded source joint sv feeds u_j = (sv - c - j) mod V
-    int u[4];
-    u[0] = sv - c % V;
-    if (u[0] < 0) u[0] += V;
-#pragma unroll
-    for (int j = 1; j < 4; ++j) {
-      u[j] = u[j - 1] - 1;
-      if (u[j] < 0) u[j] += V;
-    }
-    float mm[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) mm[j] = __ldg(p.pro_a + u[j] * K + c + j);
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-      if (g < it.ng) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *(float*)(op + op_off((uint32_t)(g * V + u[j]), (uint32_t)c4) + j * 4) = to_tf32(f4get(it.v[g], j) * mm[j]);
-      }
-  } else {  // PRO_LERP
-    // p[(g,v), c] = (1-f) U(t+y1) + f U(t+y1+1),  U = sa*h + sb inside the sample, 0 outside   (K1 with xpos = 0)
-    const float4 yp = ldg4(p.pro_c + c), sa = ldg4(p.pro_a + c), sb = ldg4(p.pro_b + c);
-    const int T = p.T;
-    const int t0 = (int)(it.g0 % T);
-    const long long last = p.groups - 1;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float ypos = f4get(yp, j), a = f4get(sa, j), b = f4get(sb, j);
-      const float fl = floorf(ypos);
-      const int y1 = (int)fl;
-      const float f = ypos - fl, f0 = 1.f - f;
-      const int idx = y1 - it.lo;                                  // 0 .. span-1
-#pragma unroll
-      for (int g = 0; g < G; ++g)
-        if (g < it.ng) {
-          float h0, h1;
-          if (it.span <= C::kWin) {                                // both taps are inside the 128-bit window
-            const float w0 = f4get(it.v[g], j), w1 = f4get(it.v[g + 1], j), w2 = f4get(it.v[g + 2], j), w3 = f4get(it.v[g + 3], j);
-            h0 = idx == 0 ? w0 : (idx == 1 ? w1 : w2);
-            h1 = idx == 0 ? w1 : (idx == 1 ? w2 : w3);
-          } else {                                                 // widely spread shift positions: scalar taps
-            long long ga = it.g0 + g + y1, gb = ga + 1;
-            ga = ga < 0 ? 0 : (ga > last ? last : ga);
-            gb = gb < 0 ? 0 : (gb > last ? last : gb);
-            h0 = __ldg(p.in0 + ((size_t)ga * V + sv) * K + c + j);
-            h1 = __ldg(p.in0 + ((size_t)gb * V + sv) * K + c + j);
-          }
-          int t = t0 + g;                                          // frame of this group (tiles may straddle samples)
-          if (t >= T) t %= T;
-          const float u0 = ((unsigned)(t + y1) < (unsigned)T) ? fmaf(a, h0, b) : 0.f;
-          const float u1 = ((unsigned)(t + y1 + 1) < (unsigned)T) ? fmaf(a, h1, b) : 0.f;
-          *(float*)(op + op_off((uint32_t)(g * V + sv), (uint32_t)c4) + j * 4) = to_tf32(fmaf(f, u1, f0 * u0));
-        }
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int PRO, int EPI, int V, int K, int N>
 __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGemm p) {
   using C = Cfg<PRO, EPI, V, K, N>;
-  constexpr int G = C::G, KC = C::KC, NCH = C::NCH;
+  constexpr int G = C::G, KC = C::KC, NCH = C::NCH, OS = C::kOpStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sW = smem;
-  uint8_t* sOp = sW + C::kWBytes;                                  // 2 operand chunks
-  uint8_t* sSt = sOp + 2 * kChunkBytes;                            // epilogue staging
-  __shared__ uint64_t op_full[2], op_free[2], acc_full[2], acc_free[2], w_full, w_free;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr int RS = C::kRawStages;
+  const uint32_t sW = smem0;
+  const uint32_t sOp = sW + C::kWBytes;
+  const uint32_t sSt = sOp + OS * kChunkBytes;
+  const uint32_t sRaw = sSt + C::kStBytes;
+  __shared__ uint64_t op_full[4], op_free[4], acc_full[2], acc_free[2], w_full[2], w_free[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ int lerp_hist[16], lerp_lo_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&op_full[i], kBldThreads);
       mbar_init(&op_free[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_free[i], 8 * 32);
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_free[i], 1);
     }
-    mbar_init(&w_full, 1);
-    mbar_init(&w_free, 1);
     fence_mbar_init();
   }
+  if (tid < 16) lerp_hist[tid] = 0;
   constexpr uint32_t tmem_cols = 2 * N <= 128 ? 128u : (2 * N <= 256 ? 256u : 512u);
   if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, tmem_cols);
   if (C::kWRes) {
-    for (int i = tid; i < C::kWBytes / 16; i += kThreads) cp_async16(sW + (size_t)i * 16, (const uint8_t*)p.wimg + (size_t)i * 16);
+    for (int i = tid; i < C::kWBytes / 16; i += kThreads) cp16(sW + (uint32_t)i * 16u, (const uint8_t*)p.wimg + (size_t)i * 16);
     cp_async_commit();
     cp_async_wait_all();
     fence_proxy_async();
@@ -233,196 +152,376 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
   const uint32_t tmem_base = tmem_base_s;
 
   const long long ntiles = (p.groups + G - 1) / G;
-  const long long my_tiles = (long long)blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int my_tiles = (long long)blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int total_chunks = my_tiles * KC;
 
-  if (warp == kMmaWarp) {
-    // ================================================================================ MMA issuer
-    if (lane == 0) {
+  if (warp >= kMmaWarp && warp < kBld0) {
+    reg_dec<kRegsMma>();
+    if (warp == kMmaWarp && lane == 0) {
+      // ================================================================================ MMA issuer
       const uint32_t idesc = umma_idesc_tf32(128, N, 0, 0);
-      const long long total_chunks = my_tiles * KC;
-      if (!C::kWRes && total_chunks > 0) {
-        mbar_expect_tx(&w_full, C::kWBytes);
-        bulk_load(sW, p.wimg, C::kWBytes, &w_full);
-      }
-      long long q = 0;
-      for (long long ti = 0; ti < my_tiles; ++ti) {
-        const int buf = (int)(ti & 1);
+      // K-major SWIZZLE_128B descriptors differ only in the 14-bit start-address field (bytes >> 4) of the low word
+      const uint64_t d0 = umma_desc(0, 16, 1024);
+      const uint32_t dhi = (uint32_t)(d0 >> 32), dlo = (uint32_t)d0;
+      int q = 0;
+#pragma unroll 1
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int buf = ti & 1;
         if (ti >= 2) mbar_wait(&acc_free[buf], (uint32_t)(((ti >> 1) - 1) & 1));
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * N);
+#pragma unroll 1
         for (int kc = 0; kc < KC; ++kc, ++q) {
-          const int s = (int)(q & 1);
-          mbar_wait(&op_full[s], (uint32_t)((q >> 1) & 1));
-          if (!C::kWRes) mbar_wait(&w_full, (uint32_t)(q & 1));
+          const int s = q % OS;
+          mbar_wait(&op_full[s], (uint32_t)((q / OS) & 1));
           tc_fence_after();
-          const uint32_t a0 = smem_u32(sOp) + (uint32_t)s * kChunkBytes;
-          const uint32_t w0 = smem_u32(sW) + (C::kWRes ? (uint32_t)kc * (uint32_t)N * 256u : 0u);
+          const uint32_t a_lo = dlo | ((sOp + (uint32_t)s * kChunkBytes) >> 4);
 #pragma unroll
-          for (int k8 = 0; k8 < 8; ++k8) {
-            const uint32_t blk = k8 >> 2, sub = k8 & 3;
-            umma_tf32(acc, umma_desc(a0 + blk * kBlockBytes + sub * 32, 16, 1024),
-                      umma_desc(w0 + blk * (uint32_t)N * 128u + sub * 32, 16, 1024), idesc, (kc | k8) ? 1u : 0u);
+          for (int blk = 0; blk < 2; ++blk) {
+            uint32_t w0;
+            if (C::kWRes) {
+              w0 = sW + (uint32_t)(kc * 2 + blk) * (uint32_t)C::kWStage;
+            } else {
+              const int h = 2 * q + blk;                            // streamed 32-channel weight block
+              mbar_wait(&w_full[h & 1], (uint32_t)((h >> 1) & 1));
+              tc_fence_after();
+              w0 = sW + (uint32_t)(h & 1) * (uint32_t)C::kWStage;
+            }
+            const uint32_t b_lo = dlo | (w0 >> 4);
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub)
+              umma_tf32(acc, ((uint64_t)dhi << 32) | (a_lo + (uint32_t)(blk * (kBlockBytes >> 4) + sub * 2)),
+                        ((uint64_t)dhi << 32) | (b_lo + (uint32_t)(sub * 2)), idesc, (kc | blk | sub) ? 1u : 0u);
+            if (!C::kWRes) tc_commit(&w_free[blk]);
           }
           tc_commit(&op_free[s]);
-          if (!C::kWRes) {
-            tc_commit(&w_free);
-            if (q + 1 < total_chunks) {                   // single weight buffer: reload once these MMAs have read it
-              mbar_wait(&w_free, (uint32_t)(q & 1));
-              const int kn = (kc + 1) % KC;
-              mbar_expect_tx(&w_full, C::kWBytes);
-              bulk_load(sW, (const uint8_t*)p.wimg + (size_t)kn * C::kWBytes, C::kWBytes, &w_full);
-            }
-          }
         }
         tc_commit(&acc_full[buf]);
       }
+    } else if (warp == kLoadWarp && lane == 0 && !C::kWRes) {
+      // ================================================================================ weight loader (TMA ring)
+      const int total_blocks = 2 * total_chunks;
+      for (int h = 0; h < total_blocks; ++h) {
+        const int s = h & 1;
+        if (h >= 2) mbar_wait(&w_free[s], (uint32_t)(((h >> 1) - 1) & 1));
+        mbar_expect_tx(&w_full[s], C::kWStage);
+        bulk_load(sW + (uint32_t)s * (uint32_t)C::kWStage, (const uint8_t*)p.wimg + (size_t)(h % (2 * KC)) * C::kWStage,
+                  C::kWStage, &w_full[s]);
+      }
     }
     __syncwarp();
-  } else if (warp > kMmaWarp) {
+  } else if (warp >= kBld0) {
     // ================================================================================ builders
-    // work items = (chunk q, round rd) in order; the loads of item i+1 are issued before item i is processed
-    const int bt = tid - (kMmaWarp + 1) * 32;
-    constexpr int R = C::kBldRounds;
-    const long long total_items = my_tiles * KC * R;
-    Item<PRO, V, K, G, C::kLoads> cur, nxt;
-    auto issue = [&](long long item, Item<PRO, V, K, G, C::kLoads>& it) {
-      const long long q = item / R;
-      const int rd = (int)(item - q * R);
-      const long long ti = q / KC;
-      const int kc = (int)(q - ti * KC);
-      issue_loads<PRO, EPI, V, K, N>(p, blockIdx.x + ti * gridDim.x, kc, bt + rd * kBldThreads, it);
-    };
-    if (total_items > 0) issue(0, cur);
-    for (long long item = 0; item < total_items; ++item) {
-      if (C::kPrefetch && item + 1 < total_items) issue(item + 1, nxt);
-      const long long q = item / R;
-      const int rd = (int)(item - q * R);
-      const int s = (int)(q & 1);
-      if (rd == 0 && q >= 2) mbar_wait(&op_free[s], (uint32_t)(((q >> 1) - 1) & 1));
-      build_item<PRO, EPI, V, K, N>(p, sOp + (size_t)s * kChunkBytes, cur);
-      if (rd == R - 1) {
-        fence_proxy_async();
-        mbar_arrive(&op_full[s]);
+    reg_dec<kRegsBld>();
+    const int bt = tid - kBld0 * 32, bw = bt >> 5;
+    const uint32_t lq = (uint32_t)lane >> 2;
+    const int prow = bt >> 4, pc4 = bt & 15;                       // this thread's 16-byte piece of rows prow + 24*i
+    constexpr int kPieces = (C::kRawRows + 23) / 24;               // copies per thread and chunk (PLAIN: tile rows)
+
+    if constexpr (PRO == PRO_PLAIN) {
+      // cp.async straight into the swizzled operand stage (the tensor core reads the fp32 bit patterns as TF32)
+      const uint32_t dst0 = (uint32_t)(pc4 >> 3) * kBlockBytes + (uint32_t)prow * 128u + ((((uint32_t)pc4 ^ (uint32_t)prow) & 7u) << 4);
+      auto issue = [&](int q) {                                    // row & 7 is invariant under +24, so is the swizzle
+        const int ti = q / KC, kc = q - ti * KC;
+        const long long g0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * G;
+        const int nrow = (int)((p.groups - g0) < G ? (p.groups - g0) : G) * V;
+        const float* src = p.in0 + ((size_t)g0 * V + prow) * K + kc * 64 + pc4 * 4;
+        const uint32_t dst = sOp + (uint32_t)(q % OS) * kChunkBytes + dst0;
+#pragma unroll
+        for (int i = 0; i < kPieces; ++i)
+          if (prow + 24 * i < nrow) cp16(dst + (uint32_t)i * 3072u, src + (size_t)i * 24 * K);
+      };
+      for (int j = 0; j < OS - 1; ++j) {
+        if (j < total_chunks) issue(j);
+        cp_async_commit();
       }
-      if (C::kPrefetch) cur = nxt;
-      else if (item + 1 < total_items) issue(item + 1, cur);
+      for (int q = 0; q < total_chunks; ++q) {
+        const int qn = q + OS - 1;                                 // refill the stage chunk q-1 has just left
+        if (qn < total_chunks) {
+          if (q >= 1) mbar_wait(&op_free[(q - 1) % OS], (uint32_t)(((q - 1) / OS) & 1));
+          issue(qn);
+        }
+        cp_async_commit();
+        cp_wait<OS - 1>();
+        fence_proxy_async();
+        mbar_arrive(&op_full[q % OS]);
+      }
+    } else {
+      // ---- raw chunk copies (16-byte pieces, dense rows of 64 floats)
+      int lerp_lo = 0;
+      if constexpr (PRO == PRO_LERP) {
+        // window of floor(ypos) values the raw tile covers: the kWin consecutive values holding most channels
+        for (int c = bt; c < K; c += kBldThreads) {
+          const int fl = (int)floorf(__ldg(p.pro_c + c));
+          if (fl >= -8 && fl < 8) atomicAdd(&lerp_hist[fl + 8], 1);
+        }
+        bld_sync();
+        if (bt == 0) {
+          int best = 0, bestn = -1;
+          for (int lo = 0; lo + C::kWin <= 16; ++lo) {
+            int n = 0;
+            for (int j = 0; j < C::kWin; ++j) n += lerp_hist[lo + j];
+            if (n > bestn) bestn = n, best = lo;
+          }
+          lerp_lo_s = best - 8;
+        }
+        bld_sync();
+        lerp_lo = lerp_lo_s;
+      }
+      auto issue = [&](int q) {
+        const int ti = q / KC, kc = q - ti * KC;
+        const long long g0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * G;
+        const uint32_t dst = sRaw + (uint32_t)(q % RS) * C::kRawBytes + (uint32_t)prow * 256u + (uint32_t)pc4 * 16u;
+        const long long gfirst = g0 + lerp_lo;                     // first group of the raw tile
+        if (PRO == PRO_SPATIAL || (gfirst >= 0 && gfirst + G + C::kWin <= p.groups)) {
+          const int nrow = PRO == PRO_SPATIAL ? (int)((p.groups - g0) < G ? (p.groups - g0) : G) * V : C::kRawRows;
+          const float* src = p.in0 + ((size_t)gfirst * V + prow) * K + kc * 64 + pc4 * 4;
+#pragma unroll
+          for (int i = 0; i < kPieces; ++i)
+            if (prow + 24 * i < nrow) cp16(dst + (uint32_t)i * 6144u, src + (size_t)i * 24 * K);
+        } else {                                                   // first / last tiles of the tensor: clamp the groups
+#pragma unroll 1
+          for (int i = 0; i < kPieces; ++i) {
+            const int row = prow + 24 * i;
+            if (row < C::kRawRows) {
+              const int gr = row / V;
+              long long gi = gfirst + gr;
+              gi = gi < 0 ? 0 : (gi >= p.groups ? p.groups - 1 : gi);
+              cp16(dst + (uint32_t)i * 6144u, p.in0 + ((size_t)gi * V + (row - gr * V)) * K + kc * 64 + pc4 * 4);
+            }
+          }
+        }
+      };
+      const uint32_t opb = sOp + (uint32_t)(lane & 3) * 4u;
+      for (int j = 0; j < RS; ++j) {
+        if (j < total_chunks) issue(j);
+        cp_async_commit();
+      }
+      for (int q = 0; q < total_chunks; ++q) {
+        const int ti = q / KC, kc = q - ti * KC;
+        const long long g0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * G;
+        const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
+        cp_wait<RS - 1>();
+        bld_sync();                                                // every thread's pieces of chunk q have landed
+        const int os = q % OS;
+        if (q >= OS) mbar_wait(&op_free[os], (uint32_t)(((q / OS) - 1) & 1));
+        const uint32_t raw = sRaw + (uint32_t)(q % RS) * C::kRawBytes + (uint32_t)lane * 4u;
+        const uint32_t ob = opb + (uint32_t)os * kChunkBytes;
+
+        if constexpr (PRO == PRO_SPATIAL) {
+          // xm[(g,u), c] = x[g, (u+c) % V, c] * maskmul[u, c]
+#pragma unroll
+          for (int k = 0; k < C::kJ; ++k) {
+            const int pi = k * kBldWarps + bw;
+            if (pi < C::kPairs) {
+              const int u = pi >> 1, half = pi & 1, c = kc * 64 + half * 32 + lane;
+              int sv = u + c % V;
+              if (sv >= V) sv -= V;
+              const float mm = __ldg(p.pro_a + u * K + c);
+              const uint32_t rb = raw + (uint32_t)(sv * 256 + half * 128);
+              const uint32_t b = ob + (uint32_t)(half * kBlockBytes + u * 128);
+              float s[G];
+#pragma unroll
+              for (int g = 0; g < G; ++g) s[g] = lds32(rb + (uint32_t)(g * V * 256));
+#pragma unroll
+              for (int g = 0; g < G; ++g)   // row r = g*V + u: 128-byte pitch, 16-byte chunk XOR-ed with (r & 7)
+                if (g < ng) sts32(b + (((lq ^ (uint32_t)(u + g * V)) & 7u) << 4) + (uint32_t)(g * V * 128), to_tf32(s[g] * mm));
+            }
+          }
+        } else {
+          // p[(g,v), c] = (1-f) U(t+y1) + f U(t+y1+1),  U = sa*h + sb inside the sample, 0 outside   (K1 with xpos = 0)
+          const int T = p.T;
+          const int t0 = p.groups < (1ll << 31) ? (int)((unsigned)g0 % (unsigned)T) : (int)(g0 % T);
+          const bool interior = ng == G && t0 + lerp_lo >= 0 && t0 + G - 1 + lerp_lo + C::kWin < T && t0 + G <= T;
+          {
+            const int half = bw & 1;                               // pairs k*12 + bw keep the parity of bw
+            const int c = kc * 64 + half * 32 + lane;
+            const float ypos = __ldg(p.pro_c + c), sa = __ldg(p.pro_a + c), sb = __ldg(p.pro_b + c);
+            const float fl = floorf(ypos);
+            const int y1 = (int)fl, idx = y1 - lerp_lo;
+            const float f = ypos - fl, a1 = sa * f, a0 = sa - a1;
+            const bool inwin = idx >= 0 && idx < C::kWin;
+#pragma unroll
+            for (int k = 0; k < C::kJ; ++k) {
+              const int pi = k * kBldWarps + bw;
+              if (pi < C::kPairs) {
+                const int v = pi >> 1;
+                const uint32_t b = ob + (uint32_t)(half * kBlockBytes + v * 128);
+                float s[G + 1];
+                if (inwin) {
+                  const uint32_t rb = raw + (uint32_t)((idx * V + v) * 256 + half * 128);
+#pragma unroll
+                  for (int g = 0; g <= G; ++g) s[g] = lds32(rb + (uint32_t)(g * V * 256));
+                } else {                                           // shift position outside the staged window: global taps
+                  const long long last = p.groups - 1;
+#pragma unroll
+                  for (int g = 0; g <= G; ++g) {
+                    long long gi = g0 + g + y1;
+                    gi = gi < 0 ? 0 : (gi > last ? last : gi);
+                    s[g] = __ldg(p.in0 + ((size_t)gi * V + v) * K + c);
+                  }
+                }
+                if (interior && inwin) {                           // every tap inside the sample: affine commutes with the lerp
+#pragma unroll
+                  for (int g = 0; g < G; ++g)
+                    sts32(b + (((lq ^ (uint32_t)(v + g * V)) & 7u) << 4) + (uint32_t)(g * V * 128),
+                          to_tf32(fmaf(a0, s[g], fmaf(a1, s[g + 1], sb))));
+                } else {
+                  const float b1 = sb * f, b0 = sb - b1;
+#pragma unroll
+                  for (int g = 0; g < G; ++g)
+                    if (g < ng) {
+                      int t = t0 + g;                              // frame of this group (tiles may straddle samples)
+                      if (t >= T) t -= T;
+                      const float u0 = ((unsigned)(t + y1) < (unsigned)T) ? fmaf(a0, s[g], b0) : 0.f;
+                      const float u1 = ((unsigned)(t + y1 + 1) < (unsigned)T) ? fmaf(a1, s[g + 1], b1) : 0.f;
+                      sts32(b + (((lq ^ (uint32_t)(v + g * V)) & 7u) << 4) + (uint32_t)(g * V * 128), to_tf32(u0 + u1));
+                    }
+                }
+              }
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&op_full[os]);
+        bld_sync();                                                // raw stage q % RS is free again
+        if (q + RS < total_chunks) issue(q + RS);
+        cp_async_commit();
+      }
     }
   } else {
     // ================================================================================ epilogue
+    reg_inc<kRegsEpi>();
     const int et = tid;                                            // 0 .. kEpiThreads-1
     const float* res = p.res ? p.res : p.in0;                      // absent residual: alias a valid tensor (branch-free loads)
     const float rsel = p.res ? 1.f : 0.f;
-    constexpr int NACC = EPI == EPI_ROT_RAW ? NCH * C::kEpiRounds : 1;
-    float s1[NACC][4], s2[NACC][4];
+    constexpr int NACC = EPI == EPI_ROT_RAW ? NCH * C::kJ : 1;
+    float s1[NACC], s2[NACC];
 #pragma unroll
-    for (int a = 0; a < NACC; ++a)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) s1[a][c] = 0.f, s2[a][c] = 0.f;
+    for (int a = 0; a < NACC; ++a) s1[a] = 0.f, s2[a] = 0.f;
+    const uint32_t stb = sSt + (uint32_t)(lane & 3) * 4u;
 
-    for (long long ti = 0; ti < my_tiles; ++ti) {
-      const long long tile = blockIdx.x + ti * gridDim.x;
-      const long long g0 = tile * G;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const long long g0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * G;
       const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
       const size_t row0 = (size_t)g0 * V;
-      const int buf = (int)(ti & 1);
+      const int buf = ti & 1;
+      int wv = warp;                                               // opaque per tile: keeps the per-(pair, chunk) address
+      asm volatile("" : "+r"(wv));                                 // set from being hoisted out of the tile loop (registers)
       if (warp < 8) {    // only the TMEM readers (who gate acc_free) wait for the accumulator, see spatial_bwd.cu
         mbar_wait(&acc_full[buf], (uint32_t)((ti >> 1) & 1));
         tc_fence_after();
       }
+      if constexpr (EPI == EPI_LINEAR) {
+        // 32 output channels per step through a [128 x 32] staging tile (128-byte rows, 16-byte chunk ^ (row & 7)):
+        // piece = thread + 384*i  ->  row = (thread >> 3) + 48*i, chunk = thread & 7
+        const int lrow = et >> 3, lc = et & 7;
+        const int nrow = ng * V;
+#pragma unroll
+        for (int st = 0; st < 2 * NCH; ++st) {
+          if (warp < 8) {   // TMEM -> staging: lane quarter (warp & 3), 16-column half (warp >> 2)
+            const int qd = warp & 3, hf = warp >> 2;
+            const uint32_t row = (uint32_t)(qd * 32 + lane);
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * N + st * 32 + hf * 16), v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              sts128(sSt + row * 128u + ((((uint32_t)(hf * 4 + i)) ^ (row & 7u)) << 4), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+            if (st == 2 * NCH - 1) {                               // last read of this accumulator buffer
+              tc_fence_before();
+              mbar_arrive(&acc_free[buf]);
+            }
+          }
+          epi_sync();
+          const int d = st * 32 + lc * 4;
+          const float4 bias = p.bias ? ldg4(p.bias + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float* optr = p.out + (row0 + lrow) * N + d;
+          const uint32_t sb = sSt + (uint32_t)lrow * 128u + ((((uint32_t)lc) ^ ((uint32_t)lrow & 7u)) << 4);
+#pragma unroll
+          for (int i = 0; i < (C::kTileRows + 47) / 48; ++i)
+            if (lrow + 48 * i < nrow) {                            // (row & 7) is invariant under +48
+              float4 y = lds128(sb + (uint32_t)(i * 48 * 128));
+              y.x += bias.x, y.y += bias.y, y.z += bias.z, y.w += bias.w;
+              if (p.relu) y.x = fmaxf(y.x, 0.f), y.y = fmaxf(y.y, 0.f), y.z = fmaxf(y.z, 0.f), y.w = fmaxf(y.w, 0.f);
+              *(float4*)(optr + (size_t)i * 48 * N) = y;
+            }
+          epi_sync();                                              // staging is reused by the next step / tile
+        }
+      } else {
 #pragma unroll
       for (int nc = 0; nc < NCH; ++nc) {
         if (warp < 8) {   // TMEM -> staging: lane quarter (warp & 3), column half (warp >> 2)
           const int qd = warp & 3, hf = warp >> 2;
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * N + nc * 64 + hf * 32), v);
           const uint32_t row = (uint32_t)(qd * 32 + lane);
+          const uint32_t rb = sSt + row * 256u;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *(float4*)(sSt + stage_off(row, (uint32_t)(hf * 8 + i), 0)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int h2 = 0; h2 < 2; ++h2) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * N + nc * 64 + hf * 32 + h2 * 16), v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              sts128(rb + ((((uint32_t)(hf * 8 + h2 * 4 + i)) ^ (row & 15u)) << 4), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+          }
           if (nc == NCH - 1) {                                     // last read of this accumulator buffer
             tc_fence_before();
             mbar_arrive(&acc_free[buf]);
           }
         }
         epi_sync();
+        {
+          // z[(g,v), d] = y[(g, (v-d) % V), d] + bias: lane <-> channel d, the warp owns (joint v, half) pairs
 #pragma unroll
-        for (int rd = 0; rd < C::kEpiRounds; ++rd) {
-          const int slot = et + rd * kEpiThreads;
-          if (slot < C::kSlots) {
-            const int v = slot >> 4, c4 = slot & 15;
-            const int d = nc * 64 + c4 * 4;
-            const float4 bias = p.bias ? ldg4(p.bias + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const size_t o = (row0 + v) * N + d;
-            if (EPI == EPI_LINEAR) {
-#pragma unroll
-              for (int g = 0; g < G; ++g)
-                if (g < ng) {
-                  float4 y = *(const float4*)(sSt + stage_off((uint32_t)(g * V + v), (uint32_t)c4, 0));
-                  y.x += bias.x, y.y += bias.y, y.z += bias.z, y.w += bias.w;
-                  if (p.relu) y.x = fmaxf(y.x, 0.f), y.y = fmaxf(y.y, 0.f), y.z = fmaxf(y.z, 0.f), y.w = fmaxf(y.w, 0.f);
-                  *(float4*)(p.out + o + (size_t)g * V * N) = y;
-                }
-            } else {
-              // z[(g,v), d+j] = y[(g, (v-d-j) % V), d+j] + bias
-              int u[4];
-              u[0] = v - d % V;
-              if (u[0] < 0) u[0] += V;
-#pragma unroll
-              for (int j = 1; j < 4; ++j) {
-                u[j] = u[j - 1] - 1;
-                if (u[j] < 0) u[j] += V;
-              }
-              float4 sc, sh, rv[G];
+          for (int k = 0; k < C::kJ; ++k) {
+            const int pi = k * kEpiWarps + wv;
+            if (pi < C::kPairs) {
+              const int v = pi >> 1, half = pi & 1;
+              const int d = nc * 64 + half * 32 + lane;
+              int u = v - d % V;
+              if (u < 0) u += V;
+              const float bias = p.bias ? __ldg(p.bias + d) : 0.f;
+              const size_t o = (row0 + v) * N + d;
+              float* optr = p.out + o;
+              const uint32_t sb = stb + (uint32_t)u * 256u;
+              const uint32_t c4 = (uint32_t)(half * 8 + (lane >> 2));
+              float sc = 0.f, sh = 0.f, rv[G];
               if (EPI == EPI_ROT_FUSED) {
-                sc = ldg4(p.epi_a + v * N + d);
-                sh = ldg4(p.epi_b + v * N + d);
+                sc = __ldg(p.epi_a + v * N + d);
+                sh = __ldg(p.epi_b + v * N + d);
+                const float* rptr = res + o;
 #pragma unroll
-                for (int g = 0; g < G; ++g) rv[g] = ldg4(res + o + (size_t)min(g, ng - 1) * V * N);
+                for (int g = 0; g < G; ++g)
+                  if (g < ng) rv[g] = __ldg(rptr + g * V * N);
               }
 #pragma unroll
               for (int g = 0; g < G; ++g)
-                if (g < ng) {
-                  float4 z;
-                  z.x = *(const float*)(sSt + stage_off((uint32_t)(g * V + u[0]), (uint32_t)c4, 0)) + bias.x;
-                  z.y = *(const float*)(sSt + stage_off((uint32_t)(g * V + u[1]), (uint32_t)c4, 1)) + bias.y;
-                  z.z = *(const float*)(sSt + stage_off((uint32_t)(g * V + u[2]), (uint32_t)c4, 2)) + bias.z;
-                  z.w = *(const float*)(sSt + stage_off((uint32_t)(g * V + u[3]), (uint32_t)c4, 3)) + bias.w;
+                if (g < ng) {   // staging row r = g*V + u: 256-byte pitch, 16-byte chunk XOR-ed with (r & 15)
+                  float z = lds32(sb + (((c4 ^ (uint32_t)(u + g * V)) & 15u) << 4) + (uint32_t)(g * V * 256)) + bias;
                   if (EPI == EPI_ROT_RAW) {
-                    constexpr int dummy = 0;
-                    (void)dummy;
-                    const int a = nc * C::kEpiRounds + rd;
-                    s1[a][0] += z.x, s1[a][1] += z.y, s1[a][2] += z.z, s1[a][3] += z.w;
-                    s2[a][0] = fmaf(z.x, z.x, s2[a][0]), s2[a][1] = fmaf(z.y, z.y, s2[a][1]);
-                    s2[a][2] = fmaf(z.z, z.z, s2[a][2]), s2[a][3] = fmaf(z.w, z.w, s2[a][3]);
+                    s1[nc * C::kJ + k] += z;
+                    s2[nc * C::kJ + k] = fmaf(z, z, s2[nc * C::kJ + k]);
                   } else {
-                    z.x = fmaf(z.x, sc.x, sh.x) + rsel * rv[g].x;
-                    z.y = fmaf(z.y, sc.y, sh.y) + rsel * rv[g].y;
-                    z.z = fmaf(z.z, sc.z, sh.z) + rsel * rv[g].z;
-                    z.w = fmaf(z.w, sc.w, sh.w) + rsel * rv[g].w;
-                    if (p.relu) z.x = fmaxf(z.x, 0.f), z.y = fmaxf(z.y, 0.f), z.z = fmaxf(z.z, 0.f), z.w = fmaxf(z.w, 0.f);
+                    z = fmaf(z, sc, sh) + rsel * rv[g];
+                    if (p.relu) z = fmaxf(z, 0.f);
                   }
-                  *(float4*)(p.out + o + (size_t)g * V * N) = z;
+                  optr[g * V * N] = z;
                 }
             }
           }
         }
         epi_sync();                                                // staging is reused by the next chunk / tile
       }
+      }
     }
     if (EPI == EPI_ROT_RAW) {   // flush the per-(v,d) batch statistics
 #pragma unroll
       for (int nc = 0; nc < NCH; ++nc)
 #pragma unroll
-        for (int rd = 0; rd < C::kEpiRounds; ++rd) {
-          const int slot = et + rd * kEpiThreads;
-          if (slot < C::kSlots) {
-            const int v = slot >> 4, d = nc * 64 + (slot & 15) * 4;
-            const int a = nc * C::kEpiRounds + rd;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              atomicAdd(p.stats + 2 * ((size_t)v * N + d + j), (double)s1[a][j]);
-              atomicAdd(p.stats + 2 * ((size_t)v * N + d + j) + 1, (double)s2[a][j]);
-            }
+        for (int k = 0; k < C::kJ; ++k) {
+          const int pi = k * kEpiWarps + warp;
+          if (pi < C::kPairs) {
+            const size_t f = (size_t)(pi >> 1) * N + nc * 64 + (pi & 1) * 32 + lane;
+            atomicAdd(p.stats + 2 * f, (double)s1[nc * C::kJ + k]);
+            atomicAdd(p.stats + 2 * f + 1, (double)s2[nc * C::kJ + k]);
           }
         }
     }

@@ -112,6 +112,16 @@ __global__ void mask_prepare_kernel(const float* __restrict__ mask, float* __res
   if (i < n) mm[i] = tanhf(mask[i]) + 1.f;
 }
 
+__global__ void mask_prepare_rot_kernel(const float* __restrict__ mask, float* __restrict__ mm, float* __restrict__ mm_rot,
+                                        int V, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V * C) return;
+  const int u = i / C, c = i - u * C;
+  const float m = tanhf(mask[i]) + 1.f;
+  mm[i] = m;
+  mm_rot[((u + c) % V) * C + c] = m;                       // source joint (u + c) mod V feeds operand row u
+}
+
 __global__ void mask_grad_finalize_kernel(double* __restrict__ raw, const float* __restrict__ mask,
                                           float* __restrict__ dmask, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,6 +202,13 @@ extern "C" int sgcn_mask_prepare(const float* mask, float* maskmul, int n, void*
   if (!mask || !maskmul) return set_error("sgcn_mask_prepare: null pointer");
   mask_prepare_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mask, maskmul, n);
   return check_launch("mask_prepare_kernel");
+}
+
+extern "C" int sgcn_mask_prepare_rot(const float* mask, float* maskmul, float* maskmul_rot, int V, int C, void* stream) {
+  if (!mask || !maskmul || !maskmul_rot) return set_error("sgcn_mask_prepare_rot: null pointer");
+  if (V < 1 || C < 1) return set_error("sgcn_mask_prepare_rot: bad shape");
+  mask_prepare_rot_kernel<<<(V * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mask, maskmul, maskmul_rot, V, C);
+  return check_launch("mask_prepare_rot_kernel");
 }
 
 extern "C" int sgcn_mask_grad_finalize(double* raw, const float* mask, float* dmask, int n, void* stream) {

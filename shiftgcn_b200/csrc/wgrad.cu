@@ -225,20 +225,27 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
         }
         cp_async_wait_all();
       } else {
+        // Scatter on write: a thread loads SOURCE joint sv = w + 8*slot of channel `lane` (every global load of a warp
+        // is one contiguous 128-byte row segment, and the per-(joint, channel) tables are indexed naturally) and
+        // writes the operand row the joint shift sends it to.  Consecutive channels land in consecutive rows, which
+        // the BASE32B swizzle spreads over all 32 banks.
         // ---- A = xm[(g,u), c] = x[g, (u+c) % V, c] * maskmul[u, c]          (model/shift_gcn.py:127-129)
+        //      loaded as x[g, sv, c] -> row u = (sv - c) mod V;  a_tab0[sv, c] = maskmul[(sv - c) mod V, c]
         for (uint32_t blk = 0; blk < ablocks; ++blk) {
           const int c = (int)blk * 32 + lane;
           const int cm = c % V;
           const float* src = p.a_src + (size_t)g0 * V * CA + c;
           const int gstride = V * CA;
-          uint8_t* dst = sA + (size_t)blk * BLK + toff;
+          uint8_t* dst = sA + (size_t)blk * BLK + (((uint32_t)lane & 7u) << 2);
           float val[KV][G], mm[KV];
+          uint32_t off[KV];
 #pragma unroll
           for (int sl = 0; sl < KV; ++sl) {
-            const int u = min(w + 8 * sl, V - 1);
-            int sv = u + cm;
-            if (sv >= V) sv -= V;
-            mm[sl] = __ldg(p.a_tab0 + u * CA + c);
+            const int sv = min(w + 8 * sl, V - 1);
+            int u = sv - cm;
+            if (u < 0) u += V;
+            off[sl] = (uint32_t)u * 128u + ((((uint32_t)lane >> 3) ^ ((uint32_t)u & 3u)) << 5);
+            mm[sl] = __ldg(p.a_tab0 + sv * CA + c);
 #pragma unroll
             for (int g = 0; g < G; ++g) val[sl][g] = __ldg(src + min(g, ng - 1) * gstride + sv * CA);
           }
@@ -247,27 +254,30 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
             if (w + 8 * sl < V) {
 #pragma unroll
               for (int g = 0; g < G; ++g)
-                if (g < ng) sts_tf32(dst + (g * VP + 8 * sl) * 128, val[sl][g] * mm[sl]);
+                if (g < ng) sts_tf32(dst + off[sl] + g * VP * 128, val[sl][g] * mm[sl]);
             }
         }
         // ---- B = dy[(g,u), d] = dz[g, (u+d) % V, d],  dz = alpha*gh + beta*z + gamma   (BN1d backward folded
         //      into three per-(v,d) tables; inverse of the shift_out gather, model/shift_gcn.py:135-137)
+        //      loaded as (gh, z)[g, sv, d] -> row u = (sv - d) mod V
         for (uint32_t blk = 0; blk < bblocks; ++blk) {
           const int d = (int)blk * 32 + lane;
           const int dm = d % V;
           const size_t o = (size_t)g0 * V * CB + d;
           const int gstride = V * CB;
-          uint8_t* dst = sB + (size_t)blk * BLK + toff;
+          uint8_t* dst = sB + (size_t)blk * BLK + (((uint32_t)lane & 7u) << 2);
           constexpr int KH = (KV + 1) / 2;                   // two half passes keep the batch at <= 2*G*KH loads
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float gv[KH][G], zv[KH][G], al[KH], be[KH], ga[KH];
+            uint32_t off[KH];
 #pragma unroll
             for (int i = 0; i < KH; ++i) {
               const int sl = half * KH + i;
-              const int u = min(w + 8 * sl, V - 1);
-              int sv = u + dm;
-              if (sv >= V) sv -= V;
+              const int sv = min(w + 8 * sl, V - 1);
+              int u = sv - dm;
+              if (u < 0) u += V;
+              off[i] = (uint32_t)u * 128u + ((((uint32_t)lane >> 3) ^ ((uint32_t)u & 3u)) << 5);
               al[i] = __ldg(p.b_tab0 + sv * CB + d);
               be[i] = __ldg(p.b_tab1 + sv * CB + d);
               ga[i] = __ldg(p.b_tab2 + sv * CB + d);
@@ -284,7 +294,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
               if (sl < KV && w + 8 * sl < V) {
 #pragma unroll
                 for (int g = 0; g < G; ++g)
-                  if (g < ng) sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(al[i], gv[i][g], fmaf(be[i], zv[i][g], ga[i])));
+                  if (g < ng) sts_tf32(dst + off[i] + g * VP * 128, fmaf(al[i], gv[i][g], fmaf(be[i], zv[i][g], ga[i])));
               }
             }
           }

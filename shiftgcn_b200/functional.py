@@ -62,7 +62,7 @@ def spatial_forward(x, res, W, bias, mask, bn, training, ws, fuse_eval, h_stats=
     D = W.shape[1]
     R = n * T
     dev = x.device
-    mm = ops.mask_prepare(mask.reshape(V, C))
+    mm, mm_rot = ops.mask_prepare(mask.reshape(V, C))
     wimg = ops.weight_image(W, 1, D, D, C)                         # B[n=d][k=c] = W[c][d]
     gamma, beta, rmean, rvar, nbt, mom = _bn_args(bn)
     resid = x if res is None else res
@@ -82,7 +82,7 @@ def spatial_forward(x, res, W, bias, mask, bn, training, ws, fuse_eval, h_stats=
         stats.zero_()
     h = torch.empty((n, T, V, D), device=dev, dtype=torch.float32)
     ops.bn_res_relu_fwd(z, resid, h, scale, shift, h_stats, R * V, V, D, relu=1)
-    saved = dict(x=x, z=z, h=h, mm=mm, mean=mean, invstd=invstd, training=training)
+    saved = dict(x=x, z=z, h=h, mm=mm, mm_rot=mm_rot, mean=mean, invstd=invstd, training=training)
     return h, saved
 
 
@@ -113,7 +113,7 @@ def spatial_backward(saved, gh, W, mask, gamma, vd_sums_ready, ws, unit_res=None
                 res2=unit_res[0] if unit_res is not None else None,
                 res2m=unit_res[1] if unit_res is not None else None, xin=x, red0=dmask_raw)
     dW = torch.zeros((C, D), device=dev, dtype=torch.float32)
-    ops.wgrad(ops.WG_SPATIAL, a_src=x, a_tab0=mm, b_src=gh, b_src2=z, b_tab0=fin["alpha"], b_tab1=fin["beta"],
+    ops.wgrad(ops.WG_SPATIAL, a_src=x, a_tab0=saved["mm_rot"], b_src=gh, b_src2=z, b_tab0=fin["alpha"], b_tab1=fin["beta"],
               b_tab2=fin["gamma"], dw=dW, groups=R, V=V, CA=C, CB=D)
     dmask = ops.mask_grad_finalize(dmask_raw, mask.reshape(V, C))
     return dict(gx=gx, gres=None if identity else gh, dW=dW, dbias=fin["dbias"].reshape(1, 1, D),

@@ -151,11 +151,14 @@ def weight_image(src, ld_n, ld_k, N, K):
 
 
 def mask_prepare(mask):
+    """(V, C) Feature_Mask -> (tanh(mask)+1, the same table indexed by the SOURCE joint of the shift_in gather)"""
     _count()
     lib = _lib.load()
-    mm = torch.empty_like(mask)
-    _lib.check(lib.sgcn_mask_prepare(_p(mask, name="Feature_Mask"), _p(mm), mask.numel(), _stream()), "mask prepare")
-    return mm
+    V, C = mask.shape
+    out = torch.empty(2, V, C, device=mask.device, dtype=torch.float32)
+    _lib.check(lib.sgcn_mask_prepare_rot(_p(mask, name="Feature_Mask"), _p(out[0]), _p(out[1]), V, C, _stream()),
+               "mask prepare")
+    return out[0], out[1]
 
 
 def mask_grad_finalize(raw, mask):
