@@ -55,6 +55,10 @@ __device__ __forceinline__ float to_tf32(float x) {  // round-to-nearest (ties a
   return __uint_as_float(r);
 }
 
+// Same rounding for values the TENSOR CORE will read: kind::tf32 ignores the low 13 mantissa bits, so adding half a
+// TF32 ulp to the magnitude is round-to-nearest (ties away) in ONE integer instruction (cvt.rna.tf32 expands to four).
+__device__ __forceinline__ float tf32_half_ulp(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
 // ------------------------------------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -31,6 +31,7 @@
 #include "capi_internal.h"
 #include "common.cuh"
 #include "rowgemm.h"
+#include <type_traits>
 
 namespace sgcn {
 namespace fg {
@@ -308,24 +309,34 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         const uint32_t raw = sRaw + (uint32_t)(q % RS) * C::kRawBytes + (uint32_t)lane * 4u;
         const uint32_t ob = opb + (uint32_t)os * kChunkBytes;
 
+        // Operand row r = g*V + v (128-byte pitch, 16-byte chunk XOR-ed with (r & 7)), 32-channel half, channel lane:
+        //   address = ob + half*16K + r*128 + (((lane >> 2) ^ r) & 7) * 16 + (lane & 3) * 4
+        // with everything but the swizzle term folded into a per-pair base and a compile-time offset.  Rows of groups
+        // beyond a partial last tile are written too (their operand rows and outputs are never used).
+        const uint32_t lqs = lq << 4;
+        auto put = [&](uint32_t base, uint32_t v16, int g, float val) {
+          sts32(base + ((lqs ^ (v16 + (uint32_t)(g * V * 16))) & 0x70u) + (uint32_t)(g * V * 128), tf32_half_ulp(val));
+        };
         if constexpr (PRO == PRO_SPATIAL) {
           // xm[(g,u), c] = x[g, (u+c) % V, c] * maskmul[u, c]
+          const int half = bw & 1;                                 // pairs k*12 + bw keep the parity of bw
+          const int c = kc * 64 + half * 32 + lane, cm = c % V;
+          const float* mrow = p.pro_a + c;
+          const uint32_t rbh = raw + (uint32_t)(half * 128), obh = ob + (uint32_t)(half * kBlockBytes);
 #pragma unroll
           for (int k = 0; k < C::kJ; ++k) {
-            const int pi = k * kBldWarps + bw;
-            if (pi < C::kPairs) {
-              const int u = pi >> 1, half = pi & 1, c = kc * 64 + half * 32 + lane;
-              int sv = u + c % V;
+            const int u = (k * kBldWarps + bw) >> 1;
+            if (u < V) {
+              int sv = u + cm;
               if (sv >= V) sv -= V;
-              const float mm = __ldg(p.pro_a + u * K + c);
-              const uint32_t rb = raw + (uint32_t)(sv * 256 + half * 128);
-              const uint32_t b = ob + (uint32_t)(half * kBlockBytes + u * 128);
+              const float mm = __ldg(mrow + u * K);
+              const uint32_t rb = rbh + (uint32_t)sv * 256u;
               float s[G];
 #pragma unroll
               for (int g = 0; g < G; ++g) s[g] = lds32(rb + (uint32_t)(g * V * 256));
+              const uint32_t b = obh + (uint32_t)u * 128u, u16 = (uint32_t)u << 4;
 #pragma unroll
-              for (int g = 0; g < G; ++g)   // row r = g*V + u: 128-byte pitch, 16-byte chunk XOR-ed with (r & 7)
-                if (g < ng) sts32(b + (((lq ^ (uint32_t)(u + g * V)) & 7u) << 4) + (uint32_t)(g * V * 128), to_tf32(s[g] * mm));
+              for (int g = 0; g < G; ++g) put(b, u16, g, s[g] * mm);
             }
           }
         } else {
@@ -333,50 +344,45 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
           const int T = p.T;
           const int t0 = p.groups < (1ll << 31) ? (int)((unsigned)g0 % (unsigned)T) : (int)(g0 % T);
           const bool interior = ng == G && t0 + lerp_lo >= 0 && t0 + G - 1 + lerp_lo + C::kWin < T && t0 + G <= T;
-          {
-            const int half = bw & 1;                               // pairs k*12 + bw keep the parity of bw
-            const int c = kc * 64 + half * 32 + lane;
-            const float ypos = __ldg(p.pro_c + c), sa = __ldg(p.pro_a + c), sb = __ldg(p.pro_b + c);
-            const float fl = floorf(ypos);
-            const int y1 = (int)fl, idx = y1 - lerp_lo;
-            const float f = ypos - fl, a1 = sa * f, a0 = sa - a1;
-            const bool inwin = idx >= 0 && idx < C::kWin;
+          const int half = bw & 1;                                 // pairs k*12 + bw keep the parity of bw
+          const int c = kc * 64 + half * 32 + lane;
+          const float ypos = __ldg(p.pro_c + c), sa = __ldg(p.pro_a + c), sb = __ldg(p.pro_b + c);
+          const float fl = floorf(ypos);
+          const int y1 = (int)fl, idx = y1 - lerp_lo;
+          const float f = ypos - fl, a1 = sa * f, a0 = sa - a1;
+          const bool inwin = idx >= 0 && idx < C::kWin;
+          const uint32_t rbh = raw + (uint32_t)(half * 128 + (inwin ? idx : 0) * (V * 256)), obh = ob + (uint32_t)(half * kBlockBytes);
 #pragma unroll
-            for (int k = 0; k < C::kJ; ++k) {
-              const int pi = k * kBldWarps + bw;
-              if (pi < C::kPairs) {
-                const int v = pi >> 1;
-                const uint32_t b = ob + (uint32_t)(half * kBlockBytes + v * 128);
-                float s[G + 1];
-                if (inwin) {
-                  const uint32_t rb = raw + (uint32_t)((idx * V + v) * 256 + half * 128);
+          for (int k = 0; k < C::kJ; ++k) {
+            const int v = (k * kBldWarps + bw) >> 1;
+            if (v < V) {
+              const uint32_t b = obh + (uint32_t)v * 128u, v16 = (uint32_t)v << 4;
+              float s[G + 1];
+              if (inwin) {
+                const uint32_t rb = rbh + (uint32_t)v * 256u;
 #pragma unroll
-                  for (int g = 0; g <= G; ++g) s[g] = lds32(rb + (uint32_t)(g * V * 256));
-                } else {                                           // shift position outside the staged window: global taps
-                  const long long last = p.groups - 1;
+                for (int g = 0; g <= G; ++g) s[g] = lds32(rb + (uint32_t)(g * V * 256));
+              } else {                                             // shift position outside the staged window: global taps
+                const long long last = p.groups - 1;
 #pragma unroll
-                  for (int g = 0; g <= G; ++g) {
-                    long long gi = g0 + g + y1;
-                    gi = gi < 0 ? 0 : (gi > last ? last : gi);
-                    s[g] = __ldg(p.in0 + ((size_t)gi * V + v) * K + c);
-                  }
+                for (int g = 0; g <= G; ++g) {
+                  long long gi = g0 + g + y1;
+                  gi = gi < 0 ? 0 : (gi > last ? last : gi);
+                  s[g] = __ldg(p.in0 + ((size_t)gi * V + v) * K + c);
                 }
-                if (interior && inwin) {                           // every tap inside the sample: affine commutes with the lerp
+              }
+              if (interior && inwin) {                             // every tap inside the sample: the affine commutes with the lerp
 #pragma unroll
-                  for (int g = 0; g < G; ++g)
-                    sts32(b + (((lq ^ (uint32_t)(v + g * V)) & 7u) << 4) + (uint32_t)(g * V * 128),
-                          to_tf32(fmaf(a0, s[g], fmaf(a1, s[g + 1], sb))));
-                } else {
-                  const float b1 = sb * f, b0 = sb - b1;
+                for (int g = 0; g < G; ++g) put(b, v16, g, fmaf(a0, s[g], fmaf(a1, s[g + 1], sb)));
+              } else {
+                const float b1 = sb * f, b0 = sb - b1;
 #pragma unroll
-                  for (int g = 0; g < G; ++g)
-                    if (g < ng) {
-                      int t = t0 + g;                              // frame of this group (tiles may straddle samples)
-                      if (t >= T) t -= T;
-                      const float u0 = ((unsigned)(t + y1) < (unsigned)T) ? fmaf(a0, s[g], b0) : 0.f;
-                      const float u1 = ((unsigned)(t + y1 + 1) < (unsigned)T) ? fmaf(a1, s[g + 1], b1) : 0.f;
-                      sts32(b + (((lq ^ (uint32_t)(v + g * V)) & 7u) << 4) + (uint32_t)(g * V * 128), to_tf32(u0 + u1));
-                    }
+                for (int g = 0; g < G; ++g) {
+                  int t = t0 + g;                                  // frame of this group (tiles may straddle samples)
+                  if (t >= T) t -= T;
+                  const float u0 = ((unsigned)(t + y1) < (unsigned)T) ? fmaf(a0, s[g], b0) : 0.f;
+                  const float u1 = ((unsigned)(t + y1 + 1) < (unsigned)T) ? fmaf(a1, s[g + 1], b1) : 0.f;
+                  put(b, v16, g, u0 + u1);
                 }
               }
             }
@@ -469,44 +475,51 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         }
         epi_sync();
         {
-          // z[(g,v), d] = y[(g, (v-d) % V), d] + bias: lane <-> channel d, the warp owns (joint v, half) pairs
+          // z[(g,v), d] = y[(g, (v-d) % V), d] + bias: lane <-> channel d, the warp owns (joint v, half) pairs.
+          // Staging row r = g*V + u (256-byte pitch, 16-byte chunk XOR-ed with (r & 15)):
+          //   address = stb + r*256 + ((chunk ^ r) & 15) * 16,   chunk = half*8 + (lane >> 2)
+          const int half = wv & 1;                                 // pairs k*12 + warp keep the parity of the warp
+          const int d = nc * 64 + half * 32 + lane, dm = d % V;
+          const float bias = p.bias ? __ldg(p.bias + d) : 0.f;
+          const uint32_t c4s = (uint32_t)(half * 8 + (lane >> 2)) << 4;
+          float* obase = p.out + row0 * N + d;
+          auto tile_pass = [&](auto full_tag) {
+            constexpr bool kFull = decltype(full_tag)::value;
 #pragma unroll
-          for (int k = 0; k < C::kJ; ++k) {
-            const int pi = k * kEpiWarps + wv;
-            if (pi < C::kPairs) {
-              const int v = pi >> 1, half = pi & 1;
-              const int d = nc * 64 + half * 32 + lane;
-              int u = v - d % V;
-              if (u < 0) u += V;
-              const float bias = p.bias ? __ldg(p.bias + d) : 0.f;
-              const size_t o = (row0 + v) * N + d;
-              float* optr = p.out + o;
-              const uint32_t sb = stb + (uint32_t)u * 256u;
-              const uint32_t c4 = (uint32_t)(half * 8 + (lane >> 2));
-              float sc = 0.f, sh = 0.f, rv[G];
-              if (EPI == EPI_ROT_FUSED) {
-                sc = __ldg(p.epi_a + v * N + d);
-                sh = __ldg(p.epi_b + v * N + d);
-                const float* rptr = res + o;
+            for (int k = 0; k < C::kJ; ++k) {
+              const int v = (k * kEpiWarps + wv) >> 1;
+              if (v < V) {
+                int u = v - dm;
+                if (u < 0) u += V;
+                float* optr = obase + v * N;
+                const uint32_t sb = stb + (uint32_t)u * 256u, u16 = (uint32_t)u << 4;
+                float sc = 0.f, sh = 0.f, rv[G];
+                if (EPI == EPI_ROT_FUSED) {
+                  sc = __ldg(p.epi_a + v * N + d);
+                  sh = __ldg(p.epi_b + v * N + d);
+                  const float* rptr = res + row0 * N + d + v * N;
+#pragma unroll
+                  for (int g = 0; g < G; ++g)
+                    if (kFull || g < ng) rv[g] = __ldg(rptr + g * V * N);
+                }
 #pragma unroll
                 for (int g = 0; g < G; ++g)
-                  if (g < ng) rv[g] = __ldg(rptr + g * V * N);
-              }
-#pragma unroll
-              for (int g = 0; g < G; ++g)
-                if (g < ng) {   // staging row r = g*V + u: 256-byte pitch, 16-byte chunk XOR-ed with (r & 15)
-                  float z = lds32(sb + (((c4 ^ (uint32_t)(u + g * V)) & 15u) << 4) + (uint32_t)(g * V * 256)) + bias;
-                  if (EPI == EPI_ROT_RAW) {
-                    s1[nc * C::kJ + k] += z;
-                    s2[nc * C::kJ + k] = fmaf(z, z, s2[nc * C::kJ + k]);
-                  } else {
-                    z = fmaf(z, sc, sh) + rsel * rv[g];
-                    if (p.relu) z = fmaxf(z, 0.f);
+                  if (kFull || g < ng) {
+                    float z = lds32(sb + ((c4s ^ (u16 + (uint32_t)(g * V * 16))) & 0xF0u) + (uint32_t)(g * V * 256)) + bias;
+                    if (EPI == EPI_ROT_RAW) {
+                      s1[nc * C::kJ + k] += z;
+                      s2[nc * C::kJ + k] = fmaf(z, z, s2[nc * C::kJ + k]);
+                    } else {
+                      z = fmaf(z, sc, sh) + rsel * rv[g];
+                      if (p.relu) z = fmaxf(z, 0.f);
+                    }
+                    optr[g * V * N] = z;
                   }
-                  optr[g * V * N] = z;
-                }
+              }
             }
-          }
+          };
+          if (ng == G) tile_pass(std::true_type{});
+          else tile_pass(std::false_type{});
         }
         epi_sync();                                                // staging is reused by the next chunk / tile
       }
