@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
                   if (u < 0) u += V;
                   const uint32_t row = (uint32_t)(g * V + u);
                   *(float*)(op + blk_off + (row >> 3) * 1024u + (row & 7u) * 128u + ((cc ^ (row & 7u)) << 4) + j * 4) =
-                      to_tf32(dz[j]);
+                      tf32_half_ulp(dz[j]);
                 }
               }
           }

@@ -65,7 +65,7 @@ __host__ __device__ inline WgGeom wg_geom(int CA, int CB, int V) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void sts_tf32(uint8_t* p, float v) { *(float*)p = to_tf32(v); }
+__device__ __forceinline__ void sts_tf32(uint8_t* p, float v) { *(float*)p = tf32_half_ulp(v); }
 
 // Tile row order: row(g, v) = g * VP + v.  The contraction runs over rows, so any order works as long as A and B
 // agree; this one makes the swizzle phase (row & 3) of every row a builder thread writes equal to (warp & 3),
@@ -174,53 +174,63 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
         const int rel_lo = (int)(-g0 < -(1 << 20) ? -(1 << 20) : -g0);                     // clamp window of the
         const long long room = p.groups - 1 - g0;                                          // tap frame groups,
         const int rel_hi = (int)(room > (1 << 20) ? (1 << 20) : room);                     // relative to g0
-        for (uint32_t blk = 0; blk < bblocks; ++blk) {
-          const int c = (int)blk * 32 + lane;
-          const float ypos = __ldg(p.b_tab2 + c), sa = __ldg(p.b_tab0 + c), sb = __ldg(p.b_tab1 + c);
-          const float fl = floorf(ypos);
-          const int y1 = (int)fl;
-          const float f = ypos - fl, f0 = 1.f - f;
-          const float* src = p.b_src + ((size_t)g0 * V + w) * CB + c;     // (group g0, joint w, channel c)
-          const int gstride = V * CB;
-          uint8_t* dst = sB + (size_t)blk * BLK + toff;
-          float L[KV][G + 1];
+        constexpr int NBT = G >= 3 ? 1 : 2;                  // 32-channel blocks per batch (loads in flight)
+        for (uint32_t blk0 = 0; blk0 < bblocks; blk0 += NBT) {
+          float L[NBT][KV][G + 1], sa[NBT], sb[NBT], f[NBT];
+          int y1[NBT];
 #pragma unroll
-          for (int sl = 0; sl < KV; ++sl) {
-            const int v = min(w + 8 * sl, V - 1);
+          for (int b = 0; b < NBT; ++b) {
+            const int c = (int)(blk0 + b) * 32 + lane;
+            const float ypos = __ldg(p.b_tab2 + c);
+            sa[b] = __ldg(p.b_tab0 + c), sb[b] = __ldg(p.b_tab1 + c);
+            const float fl = floorf(ypos);
+            y1[b] = (int)fl;
+            f[b] = ypos - fl;
+            const float* src = p.b_src + ((size_t)g0 * V + w) * CB + c;     // (group g0, joint w, channel c)
+            const int gstride = V * CB;
 #pragma unroll
-            for (int k = 0; k <= G; ++k) {
-              const int rel = min(max(y1 + k, rel_lo), rel_hi);
-              L[sl][k] = __ldg(src + (long long)rel * gstride + (v - w) * CB);
+            for (int sl = 0; sl < KV; ++sl) {
+              const int v = min(w + 8 * sl, V - 1);
+#pragma unroll
+              for (int k = 0; k <= G; ++k) {
+                const int rel = min(max(y1[b] + k, rel_lo), rel_hi);
+                L[b][sl][k] = __ldg(src + (long long)rel * gstride + (v - w) * CB);
+              }
             }
           }
-          if (!straddle) {
-            bool ok[G + 1];
 #pragma unroll
-            for (int k = 0; k <= G; ++k) ok[k] = (unsigned)(t0 + y1 + k) < (unsigned)T;
+          for (int b = 0; b < NBT; ++b) {
+            uint8_t* dst = sB + (size_t)(blk0 + b) * BLK + toff;
+            const float f0 = 1.f - f[b];
+            if (!straddle) {
+              bool ok[G + 1];
 #pragma unroll
-            for (int sl = 0; sl < KV; ++sl)
-              if (w + 8 * sl < V) {
-                float U[G + 1];
+              for (int k = 0; k <= G; ++k) ok[k] = (unsigned)(t0 + y1[b] + k) < (unsigned)T;
 #pragma unroll
-                for (int k = 0; k <= G; ++k) U[k] = ok[k] ? fmaf(sa, L[sl][k], sb) : 0.f;
+              for (int sl = 0; sl < KV; ++sl)
+                if (w + 8 * sl < V) {
+                  float U[G + 1];
 #pragma unroll
-                for (int g = 0; g < G; ++g)
-                  if (g < ng) sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(f, U[g + 1], f0 * U[g]));
-              }
-          } else {
+                  for (int k = 0; k <= G; ++k) U[k] = ok[k] ? fmaf(sa[b], L[b][sl][k], sb[b]) : 0.f;
 #pragma unroll
-            for (int sl = 0; sl < KV; ++sl)
-              if (w + 8 * sl < V) {
+                  for (int g = 0; g < G; ++g)
+                    if (g < ng) sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(f[b], U[g + 1], f0 * U[g]));
+                }
+            } else {
 #pragma unroll
-                for (int g = 0; g < G; ++g)
-                  if (g < ng) {
-                    int t = t0 + g;
-                    if (t >= T) t -= T;
-                    const float u0 = ((unsigned)(t + y1) < (unsigned)T) ? fmaf(sa, L[sl][g], sb) : 0.f;
-                    const float u1 = ((unsigned)(t + y1 + 1) < (unsigned)T) ? fmaf(sa, L[sl][g + 1], sb) : 0.f;
-                    sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(f, u1, f0 * u0));
-                  }
-              }
+              for (int sl = 0; sl < KV; ++sl)
+                if (w + 8 * sl < V) {
+#pragma unroll
+                  for (int g = 0; g < G; ++g)
+                    if (g < ng) {
+                      int t = t0 + g;
+                      if (t >= T) t -= T;
+                      const float u0 = ((unsigned)(t + y1[b]) < (unsigned)T) ? fmaf(sa[b], L[b][sl][g], sb[b]) : 0.f;
+                      const float u1 = ((unsigned)(t + y1[b] + 1) < (unsigned)T) ? fmaf(sa[b], L[b][sl][g + 1], sb[b]) : 0.f;
+                      sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(f[b], u1, f0 * u0));
+                    }
+                }
+            }
           }
         }
         cp_async_wait_all();
@@ -231,70 +241,85 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
         // the BASE32B swizzle spreads over all 32 banks.
         // ---- A = xm[(g,u), c] = x[g, (u+c) % V, c] * maskmul[u, c]          (model/shift_gcn.py:127-129)
         //      loaded as x[g, sv, c] -> row u = (sv - c) mod V;  a_tab0[sv, c] = maskmul[(sv - c) mod V, c]
-        for (uint32_t blk = 0; blk < ablocks; ++blk) {
-          const int c = (int)blk * 32 + lane;
-          const int cm = c % V;
-          const float* src = p.a_src + (size_t)g0 * V * CA + c;
-          const int gstride = V * CA;
-          uint8_t* dst = sA + (size_t)blk * BLK + (((uint32_t)lane & 7u) << 2);
-          float val[KV][G], mm[KV];
-          uint32_t off[KV];
+        constexpr int NB = G >= 4 ? 1 : (G >= 2 ? 2 : 4);   // 32-channel blocks per batch: ~16 independent loads in flight
+        constexpr int NBB = G >= 4 ? 1 : 2;
+        for (uint32_t blk0 = 0; blk0 < ablocks; blk0 += NB) {
+          float val[NB][KV][G], mm[NB][KV];
+          uint32_t off[NB][KV];
 #pragma unroll
-          for (int sl = 0; sl < KV; ++sl) {
-            const int sv = min(w + 8 * sl, V - 1);
-            int u = sv - cm;
-            if (u < 0) u += V;
-            off[sl] = (uint32_t)u * 128u + ((((uint32_t)lane >> 3) ^ ((uint32_t)u & 3u)) << 5);
-            mm[sl] = __ldg(p.a_tab0 + sv * CA + c);
+          for (int b = 0; b < NB; ++b) {
+            const int c = (int)(blk0 + b) * 32 + lane;
+            const int cm = c % V;
+            const float* src = p.a_src + (size_t)g0 * V * CA + c;
+            const int gstride = V * CA;
 #pragma unroll
-            for (int g = 0; g < G; ++g) val[sl][g] = __ldg(src + min(g, ng - 1) * gstride + sv * CA);
+            for (int sl = 0; sl < KV; ++sl) {
+              const int sv = min(w + 8 * sl, V - 1);
+              int u = sv - cm;
+              if (u < 0) u += V;
+              off[b][sl] = (uint32_t)u * 128u + ((((uint32_t)lane >> 3) ^ ((uint32_t)u & 3u)) << 5);
+              mm[b][sl] = __ldg(p.a_tab0 + sv * CA + c);
+#pragma unroll
+              for (int g = 0; g < G; ++g) val[b][sl][g] = __ldg(src + min(g, ng - 1) * gstride + sv * CA);
+            }
           }
 #pragma unroll
-          for (int sl = 0; sl < KV; ++sl)
-            if (w + 8 * sl < V) {
+          for (int b = 0; b < NB; ++b) {
+            uint8_t* dst = sA + (size_t)(blk0 + b) * BLK + (((uint32_t)lane & 7u) << 2);
 #pragma unroll
-              for (int g = 0; g < G; ++g)
-                if (g < ng) sts_tf32(dst + off[sl] + g * VP * 128, val[sl][g] * mm[sl]);
-            }
+            for (int sl = 0; sl < KV; ++sl)
+              if (w + 8 * sl < V) {
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+                  if (g < ng) sts_tf32(dst + off[b][sl] + g * VP * 128, val[b][sl][g] * mm[b][sl]);
+              }
+          }
         }
         // ---- B = dy[(g,u), d] = dz[g, (u+d) % V, d],  dz = alpha*gh + beta*z + gamma   (BN1d backward folded
         //      into three per-(v,d) tables; inverse of the shift_out gather, model/shift_gcn.py:135-137)
         //      loaded as (gh, z)[g, sv, d] -> row u = (sv - d) mod V
-        for (uint32_t blk = 0; blk < bblocks; ++blk) {
-          const int d = (int)blk * 32 + lane;
-          const int dm = d % V;
-          const size_t o = (size_t)g0 * V * CB + d;
-          const int gstride = V * CB;
-          uint8_t* dst = sB + (size_t)blk * BLK + (((uint32_t)lane & 7u) << 2);
-          constexpr int KH = (KV + 1) / 2;                   // two half passes keep the batch at <= 2*G*KH loads
+        for (uint32_t blk0 = 0; blk0 < bblocks; blk0 += NBB) {
+          constexpr int KH = (KV + 1) / 2;                   // two half passes keep the batch at <= 2*NB*G*KH loads
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            float gv[KH][G], zv[KH][G], al[KH], be[KH], ga[KH];
-            uint32_t off[KH];
+            float gv[NBB][KH][G], zv[NBB][KH][G], al[NBB][KH], be[NBB][KH], ga[NBB][KH];
+            uint32_t off[NBB][KH];
 #pragma unroll
-            for (int i = 0; i < KH; ++i) {
-              const int sl = half * KH + i;
-              const int sv = min(w + 8 * sl, V - 1);
-              int u = sv - dm;
-              if (u < 0) u += V;
-              off[i] = (uint32_t)u * 128u + ((((uint32_t)lane >> 3) ^ ((uint32_t)u & 3u)) << 5);
-              al[i] = __ldg(p.b_tab0 + sv * CB + d);
-              be[i] = __ldg(p.b_tab1 + sv * CB + d);
-              ga[i] = __ldg(p.b_tab2 + sv * CB + d);
+            for (int b = 0; b < NBB; ++b) {
+              const int d = (int)(blk0 + b) * 32 + lane;
+              const int dm = d % V;
+              const size_t o = (size_t)g0 * V * CB + d;
+              const int gstride = V * CB;
 #pragma unroll
-              for (int g = 0; g < G; ++g) {
-                const size_t og = o + (size_t)(min(g, ng - 1) * gstride + sv * CB);
-                gv[i][g] = __ldg(p.b_src + og);
-                zv[i][g] = __ldg(p.b_src2 + og);
+              for (int i = 0; i < KH; ++i) {
+                const int sl = half * KH + i;
+                const int sv = min(w + 8 * sl, V - 1);
+                int u = sv - dm;
+                if (u < 0) u += V;
+                off[b][i] = (uint32_t)u * 128u + ((((uint32_t)lane >> 3) ^ ((uint32_t)u & 3u)) << 5);
+                al[b][i] = __ldg(p.b_tab0 + sv * CB + d);
+                be[b][i] = __ldg(p.b_tab1 + sv * CB + d);
+                ga[b][i] = __ldg(p.b_tab2 + sv * CB + d);
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                  const size_t og = o + (size_t)(min(g, ng - 1) * gstride + sv * CB);
+                  gv[b][i][g] = __ldg(p.b_src + og);
+                  zv[b][i][g] = __ldg(p.b_src2 + og);
+                }
               }
             }
 #pragma unroll
-            for (int i = 0; i < KH; ++i) {
-              const int sl = half * KH + i;
-              if (sl < KV && w + 8 * sl < V) {
+            for (int b = 0; b < NBB; ++b) {
+              uint8_t* dst = sB + (size_t)(blk0 + b) * BLK + (((uint32_t)lane & 7u) << 2);
 #pragma unroll
-                for (int g = 0; g < G; ++g)
-                  if (g < ng) sts_tf32(dst + off[i] + g * VP * 128, fmaf(al[i], gv[i][g], fmaf(be[i], zv[i][g], ga[i])));
+              for (int i = 0; i < KH; ++i) {
+                const int sl = half * KH + i;
+                if (sl < KV && w + 8 * sl < V) {
+#pragma unroll
+                  for (int g = 0; g < G; ++g)
+                    if (g < ng)
+                      sts_tf32(dst + off[b][i] + g * VP * 128, fmaf(al[b][i], gv[b][i][g], fmaf(be[b][i], zv[b][i][g], ga[b][i])));
+                }
               }
             }
           }
