@@ -151,6 +151,13 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"                    # NCCL prints its version banner on stdout otherwise
+
+    def note(msg):
+        if args.verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ops.device_check()
@@ -168,6 +175,7 @@ def run_b200(args):
     host_y = torch.randint(0, num_class, (batch,)).pin_memory()
     dev_x, dev_y = host_x.to(dev), host_y.to(dev)
     trainer = FlatSGDTrainer(model, lr=0.1, momentum=0.9, nesterov=True) if train else None
+    note("model and trainer ready")
 
     graphed = False
     launches_per_step = None
@@ -206,6 +214,8 @@ def run_b200(args):
 
     for _ in range(max(args.warmup, 3)):
         step(dev_x, dev_y)
+    barrier()
+    note("eager warm-up done")
     if train and not args.no_graph:
         # the whole step (fwd, loss, bwd, all-reduce, K5, SGD) as ONE CUDA graph: removes ~1000 host launches
         l0 = ops.LAUNCHES
@@ -214,6 +224,8 @@ def run_b200(args):
         graphed = True
         for _ in range(2):
             step(dev_x, dev_y)
+        barrier()
+        note("graph captured and replayed")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -227,18 +239,19 @@ def run_b200(args):
     # ---- profiling pass (rank 0): per-call CUDA events -> dominant kernel of the step
     roofline = None
     peak, peak_src = _peaks()
+    # every rank runs the profiled step (it contains the gradient all-reduce); rank 0 keeps the events
+    torch.cuda.synchronize()
+    ops.PROFILE = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    if train:
+        trainer.train_step(dev_x, dev_y)                     # eager (not the graph): per-call events need real launches
+    else:
+        step(dev_x, dev_y)
+    e1.record()
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
     if rank == 0:
-        torch.cuda.synchronize()
-        ops.PROFILE = []
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        if train:
-            trainer.train_step(dev_x, dev_y)                 # eager (not the graph): per-call events need real launches
-        else:
-            step(dev_x, dev_y)
-        e1.record()
-        torch.cuda.synchronize()
-        prof, ops.PROFILE = ops.PROFILE, None
         agg = {}
         for name, a, b, nbytes in prof:
             t, cnt, by = agg.get(name, (0.0, 0, 0))
@@ -253,6 +266,7 @@ def run_b200(args):
                     "algorithmic_bytes_per_launch": by / cnt,
                     "breakdown_ms": {k: round(v[0], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
                     "profiled_step_ms": e0.elapsed_time(e1)}
+    note("profiling pass done")
     if world > 1:
         dist.barrier()
 
@@ -300,6 +314,7 @@ def main():
     ap.add_argument("--workload", default="ntu60-train", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-batch", type=int, default=4, help="bounded CPU sample (samples per CPU step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true", help="progress notes on stderr")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

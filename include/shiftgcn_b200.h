@@ -51,6 +51,51 @@ int sgcn_shift_bwd_nchw_f64(const double* grad_out, const double* in, const doub
                             double* grad_in, double* grad_xpos, double* grad_ypos, double* raw_pos, double* scratch,
                             long long n, int c, int h, int w, int stride, void* stream);
 
+/* ---------------------------------------------------------------- first spatial unit (3 input channels) -- */
+/* l1.gcn1 = Shift_gcn(3, 64) (model/shift_gcn.py:178, 121-142) including its `down` branch (1x1 conv + BatchNorm2d,
+ * :82-86).  z and the conv output are recomputed from x wherever needed; only h, g cross HBM at full size.
+ * x: rows [groups*V, 3]; h, g: rows [groups*V, 64].  Statistics buffers are zeroed fp64 scratch in the layouts the
+ * finalize kernels below consume (pairs {sum, sum of squares} / {sum g, sum g*xhat}). */
+typedef struct SgcnStem {
+  const float* x;        /* [groups*V, 3]                                                                    */
+  const float* maskmul;  /* tanh(Feature_Mask)+1 [V, 3]                                                       */
+  const float* W;        /* Linear_weight [3, 64]                                                             */
+  const float* bias;     /* Linear_bias [64] or NULL                                                          */
+  const float* Wd;       /* down conv weight [64, 3]                                                          */
+  const float* bd;       /* down conv bias [64] or NULL                                                       */
+  /* forward, mode 0 (batch statistics) */
+  double* stats_vd;      /* [V*64][2]  sums of z                                                              */
+  double* stats_r;       /* [64][2]    sums of the conv output                                                */
+  /* forward, mode 1 (apply) */
+  const float* sc1;      /* BatchNorm1d scale / shift [V*64]                                                  */
+  const float* sh1;
+  const float* sc2;      /* BatchNorm2d (down) scale / shift [64]                                             */
+  const float* sh2;
+  float* h;              /* out: relu(BN1d(z) + BN2d(conv))                                                   */
+  double* stats_h;       /* optional [64][2]: sums of h for the temporal unit's first BatchNorm               */
+  /* backward (h above is an input here) */
+  const float* g;        /* gradient wrt h (ReLU mask not applied)                                            */
+  const float* mean1;    /* mode 0: batch mean / invstd of z [V*64] and of the conv output [64]               */
+  const float* invstd1;
+  const float* mean2;
+  const float* invstd2;
+  double* vd_sums;       /* mode 0 out: [V*64][2] {sum gm, sum gm*zhat}                                       */
+  double* r_sums;        /* mode 0 out: [64][2]   {sum gm, sum gm*rhat}                                       */
+  const float* al;       /* mode 1: dz = al*gm + be*z + ga [V*64]  (sgcn_bn1d_bwd_finalize)                   */
+  const float* be;
+  const float* ga;
+  const float* a2;       /* mode 1: dr = a2*gm + b2*r + c2 [64]    (sgcn_bn1d_bwd_finalize with V = 1)        */
+  const float* b2;
+  const float* c2;
+  double* dw_raw;        /* mode 1 out: [64][8] {dW[0..2][d], dWd[d][0..2], dbd[d], 0}                         */
+  double* dmask_raw;     /* mode 1 out: [V*3] raw Feature_Mask gradient (sgcn_mask_grad_finalize)             */
+  float* dx;             /* mode 1 out: [groups*V, 3]                                                         */
+  long long groups;
+  int V, D;
+} SgcnStem;
+int sgcn_stem_fwd(const SgcnStem* p, int mode, void* stream);
+int sgcn_stem_bwd(const SgcnStem* p, int mode, void* stream);
+
 /* ---------------------------------------------------------------- fused tensor-core contractions ---------- */
 typedef struct SgcnRowGemm {
   const float* in0;    /* SPATIAL: x   | LERP: h      | PLAIN: rows       | DY: grad wrt gcn output (after ReLU mask) */

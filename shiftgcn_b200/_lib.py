@@ -40,6 +40,13 @@ class SgcnTShiftInBwd(ctypes.Structure):
                [("n_samples", _ll), ("T", _i), ("V", _i), ("C", _i), ("relu_h", _i)]
 
 
+class SgcnStem(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("x", "maskmul", "W", "bias", "Wd", "bd", "stats_vd", "stats_r", "sc1", "sh1", "sc2",
+                                   "sh2", "h", "stats_h", "g", "mean1", "invstd1", "mean2", "invstd2", "vd_sums",
+                                   "r_sums", "al", "be", "ga", "a2", "b2", "c2", "dw_raw", "dmask_raw", "dx")] + \
+               [("groups", _ll), ("V", _i), ("D", _i)]
+
+
 # name -> argtypes (restype is always int unless noted); must list every symbol of include/shiftgcn_b200.h
 SIGNATURES = {
     "sgcn_abi_version": [],
@@ -50,6 +57,8 @@ SIGNATURES = {
     "sgcn_shift_fwd_nchw_f64": [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
     "sgcn_shift_bwd_nchw_f32": [_vp] * 9 + [_ll, _i, _i, _i, _i, _vp],
     "sgcn_shift_bwd_nchw_f64": [_vp] * 9 + [_ll, _i, _i, _i, _i, _vp],
+    "sgcn_stem_fwd": [ctypes.POINTER(SgcnStem), _i, _vp],
+    "sgcn_stem_bwd": [ctypes.POINTER(SgcnStem), _i, _vp],
     "sgcn_rowgemm": [ctypes.POINTER(SgcnRowGemm), _i, _i, _vp],
     "sgcn_wgrad": [ctypes.POINTER(SgcnWgrad), _i, _vp],
     "sgcn_bn_res_relu_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp],

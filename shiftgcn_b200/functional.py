@@ -120,6 +120,54 @@ def spatial_backward(saved, gh, W, mask, gamma, vd_sums_ready, ws, unit_res=None
                 dmask=dmask.reshape(1, V, C), dgamma=fin["dgamma"], dbeta=fin["dbeta"])
 
 
+# ================================================================================================ first spatial unit
+def stem_forward(x, W, bias, mask, bn, Wd, bd, bn2, training, ws):
+    """l1.gcn1 = Shift_gcn(3, 64) with its conv + BN `down` branch (model/shift_gcn.py:82-86,121-142); x: (n,T,V,3)."""
+    n, T, V, C = x.shape
+    D = W.shape[1]
+    R = n * T
+    dev = x.device
+    mm, _ = ops.mask_prepare(mask.reshape(V, C))
+    Wd2 = Wd.reshape(D, C)
+    common = dict(groups=R, V=V, D=D, x=x, maskmul=mm, W=W, bias=bias.reshape(D), Wd=Wd2, bd=bd)
+    g1, b1, rm1, rv1, nbt1, mom1 = _bn_args(bn)
+    g2, b2, rm2, rv2, nbt2, mom2 = _bn_args(bn2)
+    s_vd = s_r = None
+    if training:
+        s_vd, s_r = ws.get("stem_vd", 2 * V * D, dev), ws.get("stem_r", 2 * D, dev)
+        ops.stem_fwd(0, stats_vd=s_vd, stats_r=s_r, **common)
+    mean1, invstd1, sc1, sh1 = ops.bn_fwd_finalize(s_vd, g1, b1, rm1, rv1, nbt1, V * D, R, mom1, bn.eps, training)
+    mean2, invstd2, sc2, sh2 = ops.bn_fwd_finalize(s_r, g2, b2, rm2, rv2, nbt2, D, R * V, mom2, bn2.eps, training)
+    h = torch.empty((n, T, V, D), device=dev, dtype=torch.float32)
+    ops.stem_fwd(1, sc1=sc1, sh1=sh1, sc2=sc2, sh2=sh2, h=h, **common)
+    saved = dict(x=x, h=h, mm=mm, mean1=mean1, invstd1=invstd1, mean2=mean2, invstd2=invstd2, training=training)
+    return h, saved
+
+
+def stem_backward(saved, g, W, bias, mask, gamma1, Wd, bd, gamma2, ws):
+    x, h, mm = saved["x"], saved["h"], saved["mm"]
+    n, T, V, C = x.shape
+    D = W.shape[1]
+    R = n * T
+    dev = x.device
+    training = saved["training"]
+    common = dict(groups=R, V=V, D=D, x=x, maskmul=mm, W=W, bias=bias.reshape(D), Wd=Wd.reshape(D, C), bd=bd, g=g, h=h)
+    vd, rs = ws.get("stem_vd_bwd", 2 * V * D, dev), ws.get("stem_r_bwd", 2 * D, dev)
+    ops.stem_bwd(0, mean1=saved["mean1"], invstd1=saved["invstd1"], mean2=saved["mean2"], invstd2=saved["invstd2"],
+                 vd_sums=vd, r_sums=rs, **common)
+    f1 = ops.bn1d_bwd_finalize(vd, gamma1, saved["mean1"], saved["invstd1"], V, D, R, training)
+    f2 = ops.bn1d_bwd_finalize(rs, gamma2, saved["mean2"], saved["invstd2"], 1, D, R * V, training)
+    dw_raw, dm_raw = ws.get("stem_dw", 8 * D, dev), ws.get("stem_dmask", V * C, dev)
+    dx = torch.empty_like(x)
+    ops.stem_bwd(1, al=f1["alpha"], be=f1["beta"], ga=f1["gamma"], a2=f2["alpha"], b2=f2["beta"], c2=f2["gamma"],
+                 dw_raw=dw_raw, dmask_raw=dm_raw, dx=dx, **common)
+    dw = ops.reduce_export(dw_raw).reshape(D, 8)
+    dmask = ops.mask_grad_finalize(dm_raw, mask.reshape(V, C))
+    return dict(dx=dx, dW=dw[:, 0:3].t().contiguous(), dbias=f1["dbias"].reshape(1, 1, D), dmask=dmask.reshape(1, V, C),
+                dgamma1=f1["dgamma"], dbeta1=f1["dbeta"], dWd=dw[:, 3:6].reshape(D, C, 1, 1).contiguous(),
+                dbd=dw[:, 6].contiguous(), dgamma2=f2["dgamma"], dbeta2=f2["dbeta"])
+
+
 # ================================================================================================ temporal unit
 def temporal_forward(h, res, relu, bn, ypos_in, Wt, bt, ypos_out, bn2, stride, training, ws, h_stats_ready):
     """h: (n,T,V,C) rows -> y: (n,T/stride,V,C) rows = [relu](bn2(Shift_s(relu(conv(Shift_1(bn(h)))))) + res)"""
@@ -256,6 +304,26 @@ class SpatialFn(torch.autograd.Function):
         p = st["p"]
         r = spatial_backward(st["s"], g.contiguous(), p["W"], p["mask"], p["gamma"], False, ctx.module._ws)
         return r["gx"], r["gres"], r["dW"], r["dbias"], r["dmask"], r["dgamma"], r["dbeta"], None
+
+
+class StemSpatialFn(torch.autograd.Function):
+    """Shift_gcn(3, 64).forward including its conv + BN `down` branch (model/shift_gcn.py:82-86,121-142) on rows."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, mask, g1, b1, Wd, bd, g2, b2, module):
+        h, saved = stem_forward(x, W, bias, mask, module.bn, Wd, bd, module.down[1], module.training, module._ws)
+        ctx.module = module
+        _stash(ctx, s=saved, p=dict(W=W, bias=bias, mask=mask, g1=g1, Wd=Wd, bd=bd, g2=g2))
+        return h
+
+    @staticmethod
+    def backward(ctx, g):
+        st = _unstash(ctx)
+        p = st["p"]
+        r = stem_backward(st["s"], g.contiguous(), p["W"], p["bias"], p["mask"], p["g1"], p["Wd"], p["bd"], p["g2"],
+                          ctx.module._ws)
+        return (r["dx"], r["dW"], r["dbias"], r["dmask"], r["dgamma1"], r["dbeta1"], r["dWd"], r["dbd"], r["dgamma2"],
+                r["dbeta2"], None)
 
 
 class TemporalFn(torch.autograd.Function):

@@ -172,6 +172,16 @@ class Shift_gcn(nn.Module):
         self.shift_out = nn.Parameter(torch.from_numpy(tab_out), requires_grad=False)
         self._ws = FN.Workspace()
 
+    def stem_supported(self, x0):
+        """the 3-channel first layer (reference :178) has its own kernels (csrc/stem.cu)"""
+        return (self.in_channels == 3 and self.out_channels == 64 and x0.shape[1] == 3 and x0.shape[3] == self.num_point
+                and self.num_point <= 39 and isinstance(self.down, nn.Sequential))
+
+    def forward_stem_rows(self, x_rows):
+        conv, bn2 = self.down[0], self.down[1]
+        return FN.StemSpatialFn.apply(x_rows, self.Linear_weight, self.Linear_bias, self.Feature_Mask, self.bn.weight,
+                                      self.bn.bias, conv.weight, conv.bias, bn2.weight, bn2.bias, self)
+
     def fused_supported(self, x0):
         return (self.in_channels in FUSED_CHANNELS and self.out_channels in FUSED_CHANNELS
                 and x0.shape[1] == self.in_channels and x0.shape[3] == self.num_point and self.num_point in (25, 33))
@@ -198,6 +208,8 @@ class Shift_gcn(nn.Module):
 
     def forward(self, x0):
         _require_cuda(x0, "Shift_gcn")
+        if self.stem_supported(x0):
+            return from_rows(self.forward_stem_rows(to_rows(x0)))
         if not self.fused_supported(x0):
             return self._forward_general(x0)
         return from_rows(self.forward_rows(to_rows(x0), x0))

@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import SgcnRowGemm, SgcnTShift, SgcnTShiftBwd, SgcnTShiftInBwd, SgcnWgrad
+from ._lib import SgcnRowGemm, SgcnStem, SgcnTShift, SgcnTShiftBwd, SgcnTShiftInBwd, SgcnWgrad
 
 PRO_SPATIAL, PRO_LERP, PRO_PLAIN, PRO_DY = 0, 1, 2, 3
 EPI_ROT_RAW, EPI_ROT_FUSED, EPI_LINEAR, EPI_SPATIAL_BWD = 0, 1, 2, 3
@@ -234,6 +234,34 @@ def wgrad(mode, *, a_src, b_src, dw, groups, V, CA, CB, T=1, a_tab0=None, b_src2
                   T=int(T), CA=CA, CB=CB)
     _launch("wgrad[%s]" % ("spatial", "temporal")[mode], 1, _nbytes(a_src, b_src, b_src2), lib.sgcn_wgrad,
             ctypes.byref(p), mode, _stream())
+
+
+# ------------------------------------------------------------------------------------------------ first spatial unit
+_STEM_F32 = ("x", "maskmul", "W", "bias", "Wd", "bd", "sc1", "sh1", "sc2", "sh2", "h", "g", "mean1", "invstd1", "mean2",
+             "invstd2", "al", "be", "ga", "a2", "b2", "c2", "dx")
+_STEM_F64 = ("stats_vd", "stats_r", "stats_h", "vd_sums", "r_sums", "dw_raw", "dmask_raw")
+
+
+def _stem_params(groups, V, D, **t):
+    kw = {k: _p(t.get(k), name=k) for k in _STEM_F32}
+    kw.update({k: _d(t.get(k), name=k) for k in _STEM_F64})
+    return SgcnStem(groups=int(groups), V=V, D=D, **kw)
+
+
+def stem_fwd(mode, *, groups, V, D, **t):
+    """l1.gcn1 forward: mode 0 batch statistics of z / of the down conv, mode 1 h = relu(BN1d(z) + BN2d(conv(x)))"""
+    lib = _lib.load()
+    p = _stem_params(groups, V, D, **t)
+    _launch("stem_fwd[%s]" % ("stats", "apply")[mode], 1, _nbytes(t.get("x"), t.get("h") if mode == 1 else None),
+            lib.sgcn_stem_fwd, ctypes.byref(p), mode, _stream())
+
+
+def stem_bwd(mode, *, groups, V, D, **t):
+    """l1.gcn1 backward: mode 0 BatchNorm backward sums, mode 1 parameter gradients + dx"""
+    lib = _lib.load()
+    p = _stem_params(groups, V, D, **t)
+    _launch("stem_bwd[%s]" % ("stats", "apply")[mode], 1, _nbytes(t.get("x"), t.get("g"), t.get("h"), t.get("dx")),
+            lib.sgcn_stem_bwd, ctypes.byref(p), mode, _stream())
 
 
 # ------------------------------------------------------------------------------------------------ SIMT kernels

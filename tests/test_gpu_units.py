@@ -93,7 +93,7 @@ def _inputs(shape, seed):
 
 @pytest.mark.parametrize("train", [True, False])
 @pytest.mark.parametrize("C,D,V,n,T", [(64, 64, 25, 2, 12), (64, 128, 25, 2, 7), (128, 128, 33, 1, 9), (128, 256, 25, 1, 6),
-                                       (256, 256, 25, 1, 6), (3, 64, 25, 2, 8)])
+                                       (256, 256, 25, 1, 6), (3, 64, 25, 2, 8), (3, 64, 33, 1, 37), (3, 64, 25, 3, 50)])
 def test_shift_gcn(cuda_device, C, D, V, n, T, train):
     from shiftgcn_b200.modules import Shift_gcn
     torch.manual_seed(1)
