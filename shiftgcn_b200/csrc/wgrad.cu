@@ -26,6 +26,7 @@
 #include "capi_internal.h"
 #include "common.cuh"
 #include "wgrad.h"
+#include <type_traits>
 
 namespace sgcn {
 
@@ -65,23 +66,35 @@ __host__ __device__ inline WgGeom wg_geom(int CA, int CB, int V) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void sts_tf32(uint8_t* p, float v) { *(float*)p = tf32_half_ulp(v); }
+__device__ __forceinline__ void sts_tf32(uint32_t saddr, float v) { sts32(saddr, tf32_half_ulp(v)); }
 
 // Tile row order: row(g, v) = g * VP + v.  The contraction runs over rows, so any order works as long as A and B
 // agree; this one makes the swizzle phase (row & 3) of every row a builder thread writes equal to (warp & 3),
 // i.e. all shared-memory offsets are "per-thread constant + compile-time immediate".
-template <int MODE, int V, int G>
+__host__ __device__ constexpr int wg_pick_g(int CA, int CB, int V) {   // same rule as wg_geom, usable as a template argument
+  for (int i = 0; i < 4; ++i) {
+    const int G = 4 - i;
+    const int KR = G * wg_vp(V);
+    const int stage = ((CA + CB) / 32) * KR * 128;
+    int ns = kWgSmemBudget / stage;
+    if (ns > kWgMaxGroups) ns = kWgMaxGroups;
+    if (KR <= 128 && ns >= (G == 1 ? 1 : 3)) return G;
+  }
+  return 1;
+}
+
+template <int MODE, int V, int CA, int CB>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p, const WgGeom geo) {
+  constexpr int G = wg_pick_g(CA, CB, V);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int CA = p.CA, CB = p.CB;
   constexpr int KV = (V + 7) / 8;                           // joint slots per builder warp
   constexpr int VP = KV * 8;
   constexpr int KR = G * VP;
   constexpr int BLK = KR * 128;
-  const uint32_t ablocks = CA / 32, bblocks = CB / 32;
-  const int mblocks = (CA + 127) / 128;
+  constexpr uint32_t ablocks = CA / 32, bblocks = CB / 32;
+  constexpr int mblocks = (CA + 127) / 128;
   const int NG = geo.nstages;
   const uint32_t stage_bytes = (ablocks + bblocks) * BLK;
 
@@ -97,8 +110,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
     mbar_init(&bar_done, 1);
     fence_mbar_init();
   }
-  const int need_cols = mblocks * CB;
-  const uint32_t tmem_cols = need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u));
+  constexpr int need_cols = mblocks * CB;
+  constexpr uint32_t tmem_cols = need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u));
   if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
   {  // padding rows (joints V..VP-1) must be finite zeros; they are never written afterwards
     const int n16 = NG * (int)stage_bytes / 16;
@@ -140,7 +153,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
     const int grp = (tid - 32) / kWgGroupThreads;          // builder group == operand stage
     const int w = gt >> 5;                                  // warp inside the group, 0..7
     uint8_t* sA = smem + (size_t)grp * stage_bytes;
-    uint8_t* sB = sA + (size_t)ablocks * BLK;
+    const uint32_t sA32 = smem_u32(sA), sB32 = sA32 + ablocks * (uint32_t)BLK;    // 32-bit shared-window addresses
     // offset of (row = g*VP + 8*slot + w, channel = lane) inside a block: thread constant + (g*VP + 8*slot)*128
     const uint32_t toff = (uint32_t)w * 128u + ((((uint32_t)lane >> 3) ^ ((uint32_t)w & 3u)) << 5) + (((uint32_t)lane & 7u) << 2);
     const int T = p.T;
@@ -200,7 +213,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
           }
 #pragma unroll
           for (int b = 0; b < NBT; ++b) {
-            uint8_t* dst = sB + (size_t)(blk0 + b) * BLK + toff;
+            const uint32_t dst = sB32 + (blk0 + b) * (uint32_t)BLK + toff;
             const float f0 = 1.f - f[b];
             if (!straddle) {
               bool ok[G + 1];
@@ -235,6 +248,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
         }
         cp_async_wait_all();
       } else {
+        auto build_spatial = [&](auto full_tag) {
+          constexpr bool kFull = decltype(full_tag)::value;   // full tile: compile-time offsets, no predicates
         // Scatter on write: a thread loads SOURCE joint sv = w + 8*slot of channel `lane` (every global load of a warp
         // is one contiguous 128-byte row segment, and the per-(joint, channel) tables are indexed naturally) and
         // writes the operand row the joint shift sends it to.  Consecutive channels land in consecutive rows, which
@@ -260,18 +275,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
               off[b][sl] = (uint32_t)u * 128u + ((((uint32_t)lane >> 3) ^ ((uint32_t)u & 3u)) << 5);
               mm[b][sl] = __ldg(p.a_tab0 + sv * CA + c);
 #pragma unroll
-              for (int g = 0; g < G; ++g) val[b][sl][g] = __ldg(src + min(g, ng - 1) * gstride + sv * CA);
+              for (int g = 0; g < G; ++g) val[b][sl][g] = __ldg(src + (kFull ? g : min(g, ng - 1)) * gstride + sv * CA);
             }
           }
 #pragma unroll
           for (int b = 0; b < NB; ++b) {
-            uint8_t* dst = sA + (size_t)(blk0 + b) * BLK + (((uint32_t)lane & 7u) << 2);
+            const uint32_t dst = sA32 + (blk0 + b) * (uint32_t)BLK + (((uint32_t)lane & 7u) << 2);
 #pragma unroll
             for (int sl = 0; sl < KV; ++sl)
               if (w + 8 * sl < V) {
 #pragma unroll
                 for (int g = 0; g < G; ++g)
-                  if (g < ng) sts_tf32(dst + off[b][sl] + g * VP * 128, val[b][sl][g] * mm[b][sl]);
+                  if (kFull || g < ng) sts_tf32(dst + off[b][sl] + g * VP * 128, val[b][sl][g] * mm[b][sl]);
               }
           }
         }
@@ -302,7 +317,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
                 ga[b][i] = __ldg(p.b_tab2 + sv * CB + d);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                  const size_t og = o + (size_t)(min(g, ng - 1) * gstride + sv * CB);
+                  const size_t og = o + (size_t)((kFull ? g : min(g, ng - 1)) * gstride + sv * CB);
                   gv[b][i][g] = __ldg(p.b_src + og);
                   zv[b][i][g] = __ldg(p.b_src2 + og);
                 }
@@ -310,20 +325,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
             }
 #pragma unroll
             for (int b = 0; b < NBB; ++b) {
-              uint8_t* dst = sB + (size_t)(blk0 + b) * BLK + (((uint32_t)lane & 7u) << 2);
+              const uint32_t dst = sB32 + (blk0 + b) * (uint32_t)BLK + (((uint32_t)lane & 7u) << 2);
 #pragma unroll
               for (int i = 0; i < KH; ++i) {
                 const int sl = half * KH + i;
                 if (sl < KV && w + 8 * sl < V) {
 #pragma unroll
                   for (int g = 0; g < G; ++g)
-                    if (g < ng)
+                    if (kFull || g < ng)
                       sts_tf32(dst + off[b][i] + g * VP * 128, fmaf(al[b][i], gv[b][i][g], fmaf(be[b][i], zv[b][i][g], ga[b][i])));
                 }
               }
             }
           }
         }
+              };
+        if (ng == G) build_spatial(std::true_type{});
+        else build_spatial(std::false_type{});
       }
       if (ng < G) {   // partial last tile: rows of missing groups may hold an earlier tile
         const int nblk = (int)(ablocks + bblocks);
@@ -362,10 +380,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-template <int MODE, int V, int G>
-static int launch_wgrad_vg(const SgcnWgrad& p, const WgGeom& geo, cudaStream_t s) {
+template <int MODE, int V, int CA, int CB>
+static int launch_wgrad_cc(const SgcnWgrad& p, cudaStream_t s) {
+  const WgGeom geo = wg_geom(CA, CB, V);
+  constexpr int G = wg_pick_g(CA, CB, V);
+  if (geo.nstages < 1 || geo.G != G) return set_error("sgcn_wgrad: operand stage does not fit in shared memory");
   const size_t smem = 1024 + (size_t)geo.nstages * geo.stage + 64;
-  auto kern = wgrad_kernel<MODE, V, G>;
+  auto kern = wgrad_kernel<MODE, V, CA, CB>;
   static thread_local size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -382,13 +403,13 @@ static int launch_wgrad_vg(const SgcnWgrad& p, const WgGeom& geo, cudaStream_t s
 
 template <int MODE, int V>
 static int launch_wgrad_v(const SgcnWgrad& p, cudaStream_t s) {
-  const WgGeom geo = wg_geom(p.CA, p.CB, V);
-  if (geo.nstages < 1) return set_error("sgcn_wgrad: operand stage does not fit in shared memory");
-  switch (geo.G) {
-    case 4: return launch_wgrad_vg<MODE, V, 4>(p, geo, s);
-    case 3: return launch_wgrad_vg<MODE, V, 3>(p, geo, s);
-    case 2: return launch_wgrad_vg<MODE, V, 2>(p, geo, s);
-    default: return launch_wgrad_vg<MODE, V, 1>(p, geo, s);
+  switch (p.CA * 1000 + p.CB) {
+    case 64064: return launch_wgrad_cc<MODE, V, 64, 64>(p, s);
+    case 64128: return launch_wgrad_cc<MODE, V, 64, 128>(p, s);
+    case 128128: return launch_wgrad_cc<MODE, V, 128, 128>(p, s);
+    case 128256: return launch_wgrad_cc<MODE, V, 128, 256>(p, s);
+    case 256256: return launch_wgrad_cc<MODE, V, 256, 256>(p, s);
+    default: return set_error("sgcn_wgrad: unsupported (CA, CB) channel pair");
   }
 }
 
