@@ -188,6 +188,61 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
         const long long room = p.groups - 1 - g0;                                          // tap frame groups,
         const int rel_hi = (int)(room > (1 << 20) ? (1 << 20) : room);                     // relative to g0
         constexpr int NBT = G >= 3 ? 1 : 2;                  // 32-channel blocks per batch (loads in flight)
+        constexpr int kDeep = 8;                             // |floor(ypos)| < kDeep and >= kDeep frames from both sample ends
+        const bool deep = ng == G && t0 >= kDeep && t0 + G + kDeep <= T;   // (warp uniform) no clamps, no zero padding
+        if (deep) {
+          // interior tile: the BN affine commutes with the interpolation,  p = (sa*(1-f)) h[t+y1] + (sa*f) h[t+y1+1] + sb
+          for (uint32_t blk0 = 0; blk0 < bblocks; blk0 += NBT) {
+            float L[NBT][KV][G + 1], a0[NBT], a1[NBT], sb[NBT];
+            bool far[NBT];
+#pragma unroll
+            for (int b = 0; b < NBT; ++b) {
+              const int c = (int)(blk0 + b) * 32 + lane;
+              const float ypos = __ldg(p.b_tab2 + c), sa = __ldg(p.b_tab0 + c);
+              sb[b] = __ldg(p.b_tab1 + c);
+              const float fl = floorf(ypos);
+              int y1 = (int)fl;
+              far[b] = y1 < -kDeep || y1 + 1 > kDeep;        // taps may leave the sample: handled below
+              y1 = min(max(y1, -kDeep), kDeep - 1);
+              a1[b] = sa * (ypos - fl);
+              a0[b] = sa - a1[b];
+              const float* src = p.b_src + ((size_t)(g0 + y1) * V + w) * CB + c;
+#pragma unroll
+              for (int sl = 0; sl < KV; ++sl) {
+                const int dv = (min(w + 8 * sl, V - 1) - w) * CB;
+#pragma unroll
+                for (int k = 0; k <= G; ++k) L[b][sl][k] = __ldg(src + k * (V * CB) + dv);
+              }
+            }
+#pragma unroll
+            for (int b = 0; b < NBT; ++b) {
+              const uint32_t dst = sB32 + (blk0 + b) * (uint32_t)BLK + toff;
+              if (far[b]) {                                  // |ypos| beyond the fast window (rare): exact taps with padding
+                const int c = (int)(blk0 + b) * 32 + lane;
+                const float ypos = __ldg(p.b_tab2 + c), sa = __ldg(p.b_tab0 + c);
+                const float fl = floorf(ypos), f = ypos - fl;
+                const int y1 = (int)fl;
+                for (int sl = 0; sl < KV; ++sl)
+                  if (w + 8 * sl < V)
+                    for (int g = 0; g < G; ++g) {
+                      const int ta = t0 + g + y1, tb = ta + 1;
+                      const float* row = p.b_src + ((size_t)(g0 - t0) * V + (w + 8 * sl)) * CB + c;   // frame 0 of the sample
+                      const float u0 = (unsigned)ta < (unsigned)T ? fmaf(sa, __ldg(row + (size_t)ta * V * CB), sb[b]) : 0.f;
+                      const float u1 = (unsigned)tb < (unsigned)T ? fmaf(sa, __ldg(row + (size_t)tb * V * CB), sb[b]) : 0.f;
+                      sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(f, u1, (1.f - f) * u0));
+                    }
+                continue;
+              }
+#pragma unroll
+              for (int sl = 0; sl < KV; ++sl)
+                if (w + 8 * sl < V) {
+#pragma unroll
+                  for (int g = 0; g < G; ++g)
+                    sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(a0[b], L[b][sl][g], fmaf(a1[b], L[b][sl][g + 1], sb[b])));
+                }
+            }
+          }
+        } else
         for (uint32_t blk0 = 0; blk0 < bblocks; blk0 += NBT) {
           float L[NBT][KV][G + 1], sa[NBT], sb[NBT], f[NBT];
           int y1[NBT];

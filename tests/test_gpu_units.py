@@ -107,7 +107,8 @@ def test_shift_gcn(cuda_device, C, D, V, n, T, train):
 
 
 @pytest.mark.parametrize("train", [True, False])
-@pytest.mark.parametrize("C,V,n,T,stride", [(64, 25, 2, 12, 1), (64, 25, 2, 13, 2), (128, 33, 1, 10, 2), (256, 25, 1, 8, 1)])
+@pytest.mark.parametrize("C,V,n,T,stride", [(64, 25, 2, 12, 1), (64, 25, 2, 13, 2), (128, 33, 1, 10, 2), (256, 25, 1, 8, 1),
+                                            (64, 25, 2, 47, 1), (128, 25, 1, 44, 2), (256, 33, 1, 41, 1)])   # long enough for the interior-tile fast paths
 def test_shift_tcn(cuda_device, C, V, n, T, stride, train):
     from shiftgcn_b200.modules import Shift_tcn
     torch.manual_seed(1)
@@ -127,6 +128,7 @@ def test_shift_tcn(cuda_device, C, V, n, T, stride, train):
     (256, 256, 25, 1, 6, 1, True),
     (64, 128, 25, 2, 12, 2, True),       # strided unit, conv residual
     (3, 64, 25, 2, 10, 1, False),        # first layer
+    (64, 64, 25, 2, 45, 1, True),        # identity unit, long sequence (interior-tile fast paths)
 ])
 def test_tcn_gcn_unit(cuda_device, C, D, V, n, T, stride, residual, train):
     from shiftgcn_b200.modules import TCN_GCN_unit
