@@ -121,6 +121,11 @@ typedef struct SgcnRowGemm {
   int K;               /* contraction width = input channels (64/128/256)                                  */
   int N;               /* output channels (64/128/256)                                                     */
   int relu;            /* ROT_FUSED / LINEAR: apply ReLU                                                   */
+  /* PLAIN x LINEAR only (conv + BatchNorm side branches, model/shift_gcn.py:82-86, 31-45); all 0 = plain dense GEMM   */
+  int k0;              /* > 0: the first k0 input channels come from in0 [rows, k0], the other K-k0 from in1      */
+  int in0_gs, in1_gs;  /* frame stride of the input rows: group g reads group g*gs (strided 1x1 convolution)       */
+  int out_gs;          /* frame stride of the output rows (transposed strided convolution)                         */
+  int accum;           /* out += result instead of out = result                                                    */
 } SgcnRowGemm;
 
 enum { SGCN_PRO_SPATIAL = 0, SGCN_PRO_LERP = 1, SGCN_PRO_PLAIN = 2, SGCN_PRO_DY = 3 };
@@ -140,9 +145,12 @@ typedef struct SgcnWgrad {
   long long groups;
   int V, G, T;
   int CA, CB;
+  int a_gs;             /* PLAIN: row group g of A is group g*a_gs of a_src (strided 1x1 convolution), 0 or 1 = dense  */
 } SgcnWgrad;
 
-enum { SGCN_WG_SPATIAL = 0, SGCN_WG_TEMPORAL = 1 };
+/* PLAIN: dW[a, b] = sum_rows a_src[row, a] * b_src[row, b] with both operands copied as they are (Gram matrices and
+ * input-gradient correlations of the conv + BatchNorm side branches, model/shift_gcn.py:82-86, 31-45) */
+enum { SGCN_WG_SPATIAL = 0, SGCN_WG_TEMPORAL = 1, SGCN_WG_PLAIN = 2 };
 
 int sgcn_wgrad(const SgcnWgrad* params, int mode, void* stream);
 

@@ -35,6 +35,13 @@ def tf32_round(t):
     return rounded.to(t.dtype)
 
 
+def tf32_trunc(t):
+    """what kind::tf32 does to an fp32 operand that was copied to shared memory as it is: the low 13 mantissa bits
+    are ignored (truncation toward zero) -- the product's cp.async operand paths (fused_gemm.cuh PRO_PLAIN, wgrad PLAIN)"""
+    f = t.detach().to(torch.float32).contiguous()
+    return (f.view(torch.int32) & ~0x1FFF).view(torch.float32).to(t.dtype)
+
+
 class _Tf32Matmul(torch.autograd.Function):
     """y = a @ w with TF32-rounded operands in all three contractions (fwd, dgrad, wgrad)."""
 
@@ -60,6 +67,75 @@ def contract(a, w):
     if TF32_EMULATION and a.shape[-1] >= TF32_MIN_K:
         return _Tf32Matmul.apply(a, w)
     return torch.matmul(a, w)
+
+
+class _SideBranchEmu(torch.autograd.Function):
+    """BatchNorm2d(Conv2d 1x1 (x)) with the rounding points of the product's tensor-core formulation (checker only):
+    the BN is folded into the conv weights before the forward GEMM, and the backward is ONE GEMM over [g | x] plus the
+    correlation P = x^T g, weights TF32-rounded, activations truncated (they are copied
+    into the operand tiles as they are) (shiftgcn_b200/functional.py: side_forward / side_backward).
+    Mathematically identical to autograd through nn.Conv2d + nn.BatchNorm2d (model/shift_gcn.py:82-86, 31-45)."""
+
+    @staticmethod
+    def forward(ctx, x, Wd, bd, gamma, beta, bn):            # x: (rows, C); Wd: (D, C)
+        rows = x.shape[0]
+        xr = tf32_trunc(x)
+        training = bn.training
+        if training:
+            mu = x.mean(0)
+            cov = (xr.t() @ xr) / rows - torch.outer(mu, mu)
+            mean_r = Wd @ mu + bd
+            var_r = ((Wd @ cov) * Wd).sum(1).clamp_min(0)
+            with torch.no_grad():
+                m = 0.1 if bn.momentum is None else bn.momentum
+                bn.running_mean.mul_(1 - m).add_(m * mean_r.to(bn.running_mean.dtype))
+                bn.running_var.mul_(1 - m).add_(m * (var_r * rows / max(rows - 1, 1)).to(bn.running_var.dtype))
+                bn.num_batches_tracked += 1
+        else:
+            mean_r, var_r = bn.running_mean.to(x.dtype), bn.running_var.to(x.dtype)
+        invstd = torch.rsqrt(var_r + bn.eps)
+        sc = gamma * invstd
+        Wf = tf32_round((Wd * sc[:, None]).float()).to(x.dtype)
+        bf = (beta + sc * (bd - mean_r)).float().to(x.dtype)
+        ctx.save_for_backward(x, Wd, bd, gamma, mean_r, invstd)
+        ctx.training = training
+        return xr @ Wf.t() + bf
+
+    @staticmethod
+    def backward(ctx, G):
+        x, Wd, bd, gamma, mean_r, invstd = ctx.saved_tensors
+        rows = x.shape[0]
+        xr, Gr = tf32_trunc(x), tf32_trunc(G)
+        Pt = (xr.t() @ Gr).float().to(x.dtype).t()            # (D, C), fp32 accumulator image
+        sg = G.sum(0)
+        dgamma = invstd * ((Wd * Pt).sum(1) + (bd - mean_r) * sg)
+        k = gamma * invstd
+        if ctx.training:
+            m1, m2 = sg / rows, dgamma / rows
+            sx, XX = x.sum(0), (xr.t() @ xr).float().to(x.dtype)
+        else:
+            m1 = m2 = torch.zeros_like(sg)
+            sx, XX = torch.zeros_like(x[0]), torch.zeros(x.shape[1], x.shape[1], dtype=x.dtype)
+        al, be = k, -k * m2 * invstd
+        ga = -k * m1 + k * m2 * invstd * mean_r
+        dWd = al[:, None] * Pt + be[:, None] * (Wd @ XX + torch.outer(bd, sx)) + torch.outer(ga, sx)
+        dbd = al * sg + be * (Wd @ sx + rows * bd) + rows * ga
+        Wcat = tf32_round(torch.cat([al[:, None] * Wd, Wd.t() @ (be[:, None] * Wd)], 0).float()).to(x.dtype)
+        kvec = (Wd.t() @ (be * bd + ga)).float().to(x.dtype)
+        dx = torch.cat([Gr, xr], 1) @ Wcat + kvec
+        return dx, dWd, dbd, dgamma, sg, None
+
+
+def side_branch(conv, bn, x):
+    """conv (1x1, optional frame stride) + BN on NCHW x; emulated form for the channel pairs the product serves"""
+    c, d = conv.in_channels, conv.out_channels
+    if not (TF32_EMULATION and (c, d) in ((64, 128), (128, 256)) and conv.kernel_size == (1, 1)):
+        return bn(conv(x))
+    xs = x[:, :, ::conv.stride[0]]
+    n, _, t, v = xs.shape
+    rows = xs.permute(0, 2, 3, 1).reshape(n * t * v, c)
+    out = _SideBranchEmu.apply(rows, conv.weight.reshape(d, c), conv.bias, bn.weight, bn.bias, bn)
+    return out.view(n, t, v, d).permute(0, 3, 1, 2)
 
 
 # --------------------------------------------------------------------------- index tables
@@ -174,7 +250,7 @@ class RefShiftGcn(nn.Module):
         z = y.reshape(n * t, -1).index_select(1, self.shift_out)               # :135-136
         z = self.bn(z)                                                         # :137
         z = z.view(n, t, v, self.out_channels).permute(0, 3, 1, 2)             # :138
-        res = x0 if self.down is None else self.down(x0)                       # :140
+        res = x0 if self.down is None else side_branch(self.down[0], self.down[1], x0)   # :140
         return F.relu(z + res)                                                 # :141
 
 
@@ -196,7 +272,7 @@ class RefUnit(nn.Module):
         if self.residual_mode == "identity":
             y = y + x
         elif self.residual_mode == "conv":
-            y = y + self.residual(x)
+            y = y + side_branch(self.residual.conv, self.residual.bn, x)
         return F.relu(y)
 
 

@@ -15,12 +15,13 @@ _i, _ll, _d, _vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_vo
 class SgcnRowGemm(ctypes.Structure):
     _fields_ = [(n, _vp) for n in ("in0", "in1", "out", "wimg", "pro_a", "pro_b", "pro_c", "bias", "epi_a", "epi_b",
                                    "res", "res2", "res2m", "xin", "stats", "red0")] + \
-               [("groups", _ll), ("V", _i), ("G", _i), ("T", _i), ("K", _i), ("N", _i), ("relu", _i)]
+               [("groups", _ll), ("V", _i), ("G", _i), ("T", _i), ("K", _i), ("N", _i), ("relu", _i), ("k0", _i),
+                ("in0_gs", _i), ("in1_gs", _i), ("out_gs", _i), ("accum", _i)]
 
 
 class SgcnWgrad(ctypes.Structure):
     _fields_ = [(n, _vp) for n in ("a_src", "a_tab0", "b_src", "b_src2", "b_tab0", "b_tab1", "b_tab2", "dw")] + \
-               [("groups", _ll), ("V", _i), ("G", _i), ("T", _i), ("CA", _i), ("CB", _i)]
+               [("groups", _ll), ("V", _i), ("G", _i), ("T", _i), ("CA", _i), ("CB", _i), ("a_gs", _i)]
 
 
 class SgcnTShift(ctypes.Structure):

@@ -222,15 +222,34 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
     if constexpr (PRO == PRO_PLAIN) {
       // cp.async straight into the swizzled operand stage (the tensor core reads the fp32 bit patterns as TF32)
       const uint32_t dst0 = (uint32_t)(pc4 >> 3) * kBlockBytes + (uint32_t)prow * 128u + ((((uint32_t)pc4 ^ (uint32_t)prow) & 7u) << 4);
+      // The K channels may come from two row tensors side by side (p.k0 from in0, the rest from in1: the input-gradient
+      // GEMM of a conv + BN side branch contracts [g | x] in one pass), each with its own frame stride (1x1 conv, stride 2).
+      const int k0 = p.k0 > 0 ? p.k0 : K;
+      const bool simple = k0 == K && p.in0_gs <= 1;
       auto issue = [&](int q) {                                    // row & 7 is invariant under +24, so is the swizzle
         const int ti = q / KC, kc = q - ti * KC;
         const long long g0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * G;
         const int nrow = (int)((p.groups - g0) < G ? (p.groups - g0) : G) * V;
-        const float* src = p.in0 + ((size_t)g0 * V + prow) * K + kc * 64 + pc4 * 4;
         const uint32_t dst = sOp + (uint32_t)(q % OS) * kChunkBytes + dst0;
+        if (simple) {
+          const float* src = p.in0 + ((size_t)g0 * V + prow) * K + kc * 64 + pc4 * 4;
 #pragma unroll
-        for (int i = 0; i < kPieces; ++i)
-          if (prow + 24 * i < nrow) cp16(dst + (uint32_t)i * 3072u, src + (size_t)i * 24 * K);
+          for (int i = 0; i < kPieces; ++i)
+            if (prow + 24 * i < nrow) cp16(dst + (uint32_t)i * 3072u, src + (size_t)i * 24 * K);
+        } else {
+          const bool second = kc * 64 >= k0;
+          const float* base = second ? p.in1 : p.in0;
+          const int pitch = second ? K - k0 : k0, ch = (second ? kc * 64 - k0 : kc * 64) + pc4 * 4;
+          const long long gs = second ? (p.in1_gs > 0 ? p.in1_gs : 1) : (p.in0_gs > 0 ? p.in0_gs : 1);
+#pragma unroll
+          for (int i = 0; i < kPieces; ++i) {
+            const int row = prow + 24 * i;
+            if (row < nrow) {
+              const int gr = row / V;
+              cp16(dst + (uint32_t)i * 3072u, base + ((size_t)((g0 + gr) * gs) * V + (row - gr * V)) * pitch + ch);
+            }
+          }
+        }
       };
       for (int j = 0; j < OS - 1; ++j) {
         if (j < total_chunks) issue(j);
@@ -441,16 +460,36 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
           epi_sync();
           const int d = st * 32 + lc * 4;
           const float4 bias = p.bias ? ldg4(p.bias + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float* optr = p.out + (row0 + lrow) * N + d;
           const uint32_t sb = sSt + (uint32_t)lrow * 128u + ((((uint32_t)lc) ^ ((uint32_t)lrow & 7u)) << 4);
+          if (p.out_gs <= 1 && !p.accum) {
+            float* optr = p.out + (row0 + lrow) * N + d;
 #pragma unroll
-          for (int i = 0; i < (C::kTileRows + 47) / 48; ++i)
-            if (lrow + 48 * i < nrow) {                            // (row & 7) is invariant under +48
-              float4 y = lds128(sb + (uint32_t)(i * 48 * 128));
-              y.x += bias.x, y.y += bias.y, y.z += bias.z, y.w += bias.w;
-              if (p.relu) y.x = fmaxf(y.x, 0.f), y.y = fmaxf(y.y, 0.f), y.z = fmaxf(y.z, 0.f), y.w = fmaxf(y.w, 0.f);
-              *(float4*)(optr + (size_t)i * 48 * N) = y;
+            for (int i = 0; i < (C::kTileRows + 47) / 48; ++i)
+              if (lrow + 48 * i < nrow) {                          // (row & 7) is invariant under +48
+                float4 y = lds128(sb + (uint32_t)(i * 48 * 128));
+                y.x += bias.x, y.y += bias.y, y.z += bias.z, y.w += bias.w;
+                if (p.relu) y.x = fmaxf(y.x, 0.f), y.y = fmaxf(y.y, 0.f), y.z = fmaxf(y.z, 0.f), y.w = fmaxf(y.w, 0.f);
+                *(float4*)(optr + (size_t)i * 48 * N) = y;
+              }
+          } else {   // output frames strided (transposed stride-2 conv) and / or accumulated into an existing gradient
+            const long long ogs = p.out_gs > 0 ? p.out_gs : 1;
+#pragma unroll
+            for (int i = 0; i < (C::kTileRows + 47) / 48; ++i) {
+              const int row = lrow + 48 * i;
+              if (row < nrow) {
+                const int gr = row / V;
+                float4* optr = (float4*)(p.out + ((size_t)((g0 + gr) * ogs) * V + (row - gr * V)) * N + d);
+                float4 y = lds128(sb + (uint32_t)(i * 48 * 128));
+                y.x += bias.x, y.y += bias.y, y.z += bias.z, y.w += bias.w;
+                if (p.relu) y.x = fmaxf(y.x, 0.f), y.y = fmaxf(y.y, 0.f), y.z = fmaxf(y.z, 0.f), y.w = fmaxf(y.w, 0.f);
+                if (p.accum) {
+                  const float4 o = *optr;
+                  y.x += o.x, y.y += o.y, y.z += o.z, y.w += o.w;
+                }
+                *optr = y;
+              }
             }
+          }
           epi_sync();                                              // staging is reused by the next step / tile
         }
       } else {

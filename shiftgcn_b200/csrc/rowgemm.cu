@@ -515,7 +515,8 @@ extern "C" int sgcn_rowgemm(const SgcnRowGemm* pp, int pro, int epi, void* strea
   const SgcnRowGemm& p = *pp;
   if (p.V < 25 || p.V > 8 * kUI) return set_error("sgcn_rowgemm: num_point must be in [25, 40]");
   if (p.G < 1 || p.G > kGMax || p.G * p.V > kTileRows) return set_error("sgcn_rowgemm: need G <= 5 and G*V <= 128");
-  if (p.K != 64 && p.K != 128 && p.K != 256) return set_error("sgcn_rowgemm: K must be 64, 128 or 256");
+  const bool concat = pro == PRO_PLAIN && p.k0 > 0 && (p.K == 192 || p.K == 384);   // [g | x] input-gradient GEMM
+  if (p.K != 64 && p.K != 128 && p.K != 256 && !concat) return set_error("sgcn_rowgemm: K must be 64, 128 or 256");
   if (p.N != 64 && p.N != 128 && p.N != 256) return set_error("sgcn_rowgemm: N must be 64, 128 or 256");
   if (p.groups < 0) return set_error("sgcn_rowgemm: negative group count");
   if (!p.in0 || !p.out || !p.wimg) return set_error("sgcn_rowgemm: null tensor");
@@ -539,7 +540,9 @@ extern "C" int sgcn_rowgemm(const SgcnRowGemm* pp, int pro, int epi, void* strea
     return launch_nch<PRO_LERP, EPI_LINEAR>(p, s);
   }
   if (pro == PRO_PLAIN && epi == EPI_LINEAR) {
-    if (fast && p.K == p.N) return temporal_gemm_launch(p, 0, s);
+    if (p.k0 > 0 && (!p.in1 || p.k0 % 64 != 0 || p.k0 >= p.K)) return set_error("plain GEMM: bad two-source split");
+    if (fast) return temporal_gemm_launch(p, 0, s);
+    if (p.k0 > 0 || p.in0_gs > 1 || p.out_gs > 1 || p.accum) return set_error("plain GEMM: strided / two-source form needs num_point 25 or 33");
     return launch_nch<PRO_PLAIN, EPI_LINEAR>(p, s);
   }
   if (pro == PRO_DY && epi == EPI_SPATIAL_BWD) {

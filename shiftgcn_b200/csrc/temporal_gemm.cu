@@ -8,13 +8,22 @@ namespace sgcn {
 template <int PRO, int V>
 static int temporal_gemm_v(const SgcnRowGemm& p, cudaStream_t s) {
   using namespace fg;
-  if (p.K != p.N) return set_error("temporal 1x1 convolution: in and out channels must match");
-  switch (p.K) {
-    case 64: return launch<PRO, EPI_LINEAR, V, 64, 64>(p, s);
-    case 128: return launch<PRO, EPI_LINEAR, V, 128, 128>(p, s);
-    case 256: return launch<PRO, EPI_LINEAR, V, 256, 256>(p, s);
-    default: return set_error("temporal 1x1 convolution: channels must be 64, 128 or 256");
+  switch (p.K * 1000 + p.N) {
+    case 64064: return launch<PRO, EPI_LINEAR, V, 64, 64>(p, s);
+    case 128128: return launch<PRO, EPI_LINEAR, V, 128, 128>(p, s);
+    case 256256: return launch<PRO, EPI_LINEAR, V, 256, 256>(p, s);
+    default: break;
   }
+  if constexpr (PRO == PRO_PLAIN) {   // 1x1 conv side branches: forward (C -> D) and input gradient ([g | x]: D + C -> C)
+    switch (p.K * 1000 + p.N) {
+      case 64128: return launch<PRO, EPI_LINEAR, V, 64, 128>(p, s);
+      case 128256: return launch<PRO, EPI_LINEAR, V, 128, 256>(p, s);
+      case 192064: return launch<PRO, EPI_LINEAR, V, 192, 64>(p, s);
+      case 384128: return launch<PRO, EPI_LINEAR, V, 384, 128>(p, s);
+      default: break;
+    }
+  }
+  return set_error("row GEMM: unsupported (in, out) channel pair");
 }
 
 int temporal_gemm_launch(const SgcnRowGemm& p, int lerp, cudaStream_t s) {

@@ -30,7 +30,7 @@
 
 namespace sgcn {
 
-enum { WG_SPATIAL = 0, WG_TEMPORAL = 1 };
+enum { WG_SPATIAL = 0, WG_TEMPORAL = 1, WG_PLAIN = 2 };
 
 constexpr int kWgMaxGroups = 3;
 constexpr int kWgGroupThreads = 256;
@@ -165,22 +165,42 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
       const long long use = j / NG;
       if (use > 0) mbar_wait(&bar_free[grp], (uint32_t)((use - 1) & 1));   // the MMAs of the previous use are done
 
-      if (MODE == WG_TEMPORAL) {
-        // ---- A = dpre rows as they are: 16-byte cp.async pieces straight into the swizzled blocks
+      if (MODE == WG_TEMPORAL || MODE == WG_PLAIN) {
+        // ---- A = rows as they are: 16-byte cp.async pieces straight into the swizzled blocks (the tensor core reads
+        //      fp32 bit patterns as TF32).  PLAIN: row group g of the tile comes from group (g0+g)*a_gs (strided 1x1 conv)
         {
-          const int ppr = CA >> 2;                           // 16-byte pieces per row (16, 32 or 64)
+          constexpr int ppr = CA >> 2;                       // 16-byte pieces per row (16, 32 or 64)
           const int k = gt & (ppr - 1);                      // this thread's piece inside a row
           const uint32_t kk = (uint32_t)k & 7u;
           const uint32_t poff = ((uint32_t)k >> 3) * BLK + ((kk & 1u) << 4);
-          const float* src = p.a_src + (size_t)g0 * V * CA + (size_t)k * 4;
-          const int rstep = kWgGroupThreads / ppr;
+          const long long ags = MODE == WG_PLAIN ? (p.a_gs > 0 ? p.a_gs : 1) : 1;
+          const float* src = p.a_src + (size_t)g0 * ags * V * CA + (size_t)k * 4;
+          constexpr int rstep = kWgGroupThreads / ppr;
           for (int q = gt / ppr; q < ng * V; q += rstep) {   // q = g*V + v
             const int g = q / V, v = q - g * V;
             const uint32_t r = (uint32_t)(g * VP + v);
-            cp_async16(sA + poff + r * 128u + ((((kk >> 1) ^ (r & 3u))) << 5), src + (size_t)q * CA);
+            cp_async16(sA + poff + r * 128u + ((((kk >> 1) ^ (r & 3u))) << 5), src + ((size_t)g * ags * V + v) * CA);
           }
           cp_async_commit();
         }
+      }
+      if (MODE == WG_PLAIN) {
+        // ---- B = rows as they are
+        constexpr int ppr = CB >> 2;
+        const int k = gt & (ppr - 1);
+        const uint32_t kk = (uint32_t)k & 7u;
+        const uint32_t poff = ((uint32_t)k >> 3) * BLK + ((kk & 1u) << 4);
+        const float* src = p.b_src + (size_t)g0 * V * CB + (size_t)k * 4;
+        constexpr int rstep = kWgGroupThreads / ppr;
+        uint8_t* sBp = sA + (size_t)ablocks * BLK;
+        for (int q = gt / ppr; q < ng * V; q += rstep) {
+          const int g = q / V, v = q - g * V;
+          const uint32_t r = (uint32_t)(g * VP + v);
+          cp_async16(sBp + poff + r * 128u + ((((kk >> 1) ^ (r & 3u))) << 5), src + (size_t)q * CB);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+      } else if (MODE == WG_TEMPORAL) {
         // ---- B = p[(g,v), c] = (1-f) U(t+y1) + f U(t+y1+1),  U = sa*h + sb inside the sample, 0 outside
         const int t0 = (int)(g0 % T);                        // frame of the tile's first group
         const bool straddle = t0 + ng > T;                   // the tile crosses into the next sample (warp uniform)
@@ -493,5 +513,6 @@ extern "C" int sgcn_wgrad(const SgcnWgrad* pp, int mode, void* stream) {
     if (!p.b_tab0 || !p.b_tab1 || !p.b_tab2 || p.T < 1) return set_error("sgcn_wgrad(temporal): null table / bad T");
     return launch_wgrad<WG_TEMPORAL>(p, (cudaStream_t)stream);
   }
+  if (mode == WG_PLAIN) return launch_wgrad<WG_PLAIN>(p, (cudaStream_t)stream);
   return set_error("sgcn_wgrad: unknown mode");
 }

@@ -168,6 +168,103 @@ def stem_backward(saved, g, W, bias, mask, gamma1, Wd, bd, gamma2, ws):
                 dbd=dw[:, 6].contiguous(), dgamma2=f2["dgamma"], dbeta2=f2["dbeta"])
 
 
+# ================================================================================================ conv + BN side branches
+def side_forward(x, Wd, bd, bn, training, ws):
+    """BatchNorm2d(Conv2d_1x1(x)) on rows (`down` of Shift_gcn, model/shift_gcn.py:82-86; `tcn` residual, :31-45).
+
+    x: (rows, C) with rows a multiple of V*... (any row count that is a multiple of the tile group size is fine: the
+    branch has no joint structure).  The batch statistics of the conv output follow from the first two moments of x:
+        mean_r = Wd mu + bd,   var_r[d] = Wd[d] Cov(x) Wd[d]^T
+    so they cost one Gram-matrix contraction of x on the tensor cores (rounding errors of ~1e6 products average out)
+    plus one channel-sum pass, and the normalisation is FOLDED into the conv weights before the only full-size GEMM:
+    r' = x (sc*Wd)^T + (beta - sc*(Wd mu)).  The raw conv output is never stored.
+    """
+    n, T, V, C = x.shape
+    rows = n * T * V
+    D = Wd.shape[0]
+    dev = x.device
+    gamma, beta, rmean, rvar, nbt, mom = _bn_args(bn)
+    Wd64 = Wd.detach().reshape(D, C).double()
+    saved = dict(x=x, training=training)
+    if training:
+        st = ws.get("side_sx", 2 * C, dev)
+        ops.channel_stats(x, st, rows, C)
+        sx = ops.reduce_export(st).reshape(C, 2)[:, 0].double()
+        XX = torch.zeros((C, C), device=dev, dtype=torch.float32)
+        ops.wgrad(ops.WG_PLAIN, a_src=x, b_src=x, dw=XX, groups=n * T, V=V, CA=C, CB=C)
+        mu = sx / rows
+        cov = XX.double() / rows - torch.outer(mu, mu)
+        wmu = Wd64 @ mu
+        mean_r = wmu + (bd.detach().double() if bd is not None else 0.0)
+        var_r = ((Wd64 @ cov) * Wd64).sum(1).clamp_min(0.0)
+        with torch.no_grad():
+            if bn.track_running_stats and rmean is not None:
+                unbiased = var_r * (rows / max(rows - 1, 1))
+                rmean.mul_(1 - mom).add_((mom * mean_r).float())
+                rvar.mul_(1 - mom).add_((mom * unbiased).float())
+                nbt.add_(1)
+        saved.update(sx=sx, XX=XX)
+    else:
+        mean_r = rmean.double()
+        var_r = rvar.double()
+        wmu = None
+    invstd = torch.rsqrt(var_r + bn.eps)
+    sc = gamma.detach().double() * invstd
+    Wf = (Wd64 * sc[:, None]).float().contiguous()
+    bias_r = bd.detach().double() if bd is not None else torch.zeros(D, device=dev, dtype=torch.float64)
+    bf = (beta.detach().double() + sc * (bias_r - mean_r)).float().contiguous()
+    wimg = ops.weight_image(Wf, C, 1, D, C)                        # B[n=d][k=c] = Wf[d][c]
+    out = torch.empty((n, T, V, D), device=dev, dtype=torch.float32)
+    ops.rowgemm(ops.PRO_PLAIN, ops.EPI_LINEAR, in0=x, out=out, wimg=wimg, groups=n * T, V=V, K=C, N=D, bias=bf, relu=0)
+    saved.update(mean_r=mean_r, invstd=invstd)
+    return out, saved
+
+
+def side_backward(saved, G, sg, Wd, bd, gamma, ws):
+    """Gradients of the conv + BN branch without touching the conv output: with P = x^T G (one plain contraction),
+    XX = x^T x and sx from the forward, everything else is C x C x D arithmetic on the device (fp64):
+        dgamma = invstd * (rowsum(Wd * P^T) + (bd - mean_r) * sg),  dbeta = sg,
+        dr = al*G + be*r + ga  (BatchNorm backward as an affine map),   dWd = al*P^T + be*(Wd XX + bd sx^T) + ga sx^T,
+        dx = G (al*Wd) + x (Wd^T be Wd) + Wd^T (be*bd + ga)           -- ONE GEMM over the concatenation [G | x].
+    """
+    x = saved["x"]
+    n, T, V, C = x.shape
+    rows = n * T * V
+    D = Wd.shape[0]
+    dev = x.device
+    training = saved["training"]
+    Wd64 = Wd.detach().reshape(D, C).double()
+    bd64 = bd.detach().double() if bd is not None else torch.zeros(D, device=dev, dtype=torch.float64)
+    P = torch.zeros((C, D), device=dev, dtype=torch.float32)
+    ops.wgrad(ops.WG_PLAIN, a_src=x, b_src=G, dw=P, groups=n * T, V=V, CA=C, CB=D)
+    Pt = P.double().t()                                             # (D, C)
+    sg = sg.double()
+    invstd, mean_r = saved["invstd"], saved["mean_r"]
+    dgamma = invstd * ((Wd64 * Pt).sum(1) + (bd64 - mean_r) * sg)
+    dbeta = sg
+    k = gamma.detach().double() * invstd
+    if training:
+        m1, m2 = sg / rows, dgamma / rows
+        sx, XX = saved["sx"], saved["XX"].double()
+    else:
+        m1 = m2 = torch.zeros_like(sg)
+        sx = torch.zeros(C, device=dev, dtype=torch.float64)
+        XX = torch.zeros((C, C), device=dev, dtype=torch.float64)
+    al, be = k, -k * m2 * invstd
+    ga = -k * m1 + k * m2 * invstd * mean_r
+    dWd = al[:, None] * Pt + be[:, None] * (Wd64 @ XX + torch.outer(bd64, sx)) + torch.outer(ga, sx)
+    dbd = al * sg + be * (Wd64 @ sx + rows * bd64) + rows * ga
+    A1 = al[:, None] * Wd64                                         # (D, C)
+    M = Wd64.t() @ (be[:, None] * Wd64)                             # (C, C)
+    kvec = Wd64.t() @ (be * bd64 + ga)
+    Wcat = torch.cat([A1, M], 0).float().contiguous()              # (D + C, C): out[c] = sum_k in[k] Wcat[k][c]
+    wimg = ops.weight_image(Wcat, 1, C, C, D + C)                  # B[n=c][k] = Wcat[k][c]
+    dx = torch.empty((n, T, V, C), device=dev, dtype=torch.float32)
+    ops.rowgemm(ops.PRO_PLAIN, ops.EPI_LINEAR, in0=G, in1=x, out=dx, wimg=wimg, groups=n * T, V=V, K=D + C, N=C, k0=D,
+                bias=kvec.float().contiguous(), relu=0)
+    return dict(dx=dx, dWd=dWd.float().reshape(Wd.shape), dbd=dbd.float(), dgamma=dgamma.float(), dbeta=dbeta.float())
+
+
 # ================================================================================================ temporal unit
 def temporal_forward(h, res, relu, bn, ypos_in, Wt, bt, ypos_out, bn2, stride, training, ws, h_stats_ready):
     """h: (n,T,V,C) rows -> y: (n,T/stride,V,C) rows = [relu](bn2(Shift_s(relu(conv(Shift_1(bn(h)))))) + res)"""
@@ -303,6 +400,9 @@ class SpatialFn(torch.autograd.Function):
         st = _unstash(ctx)
         p = st["p"]
         r = spatial_backward(st["s"], g.contiguous(), p["W"], p["mask"], p["gamma"], False, ctx.module._ws)
+        if r["gres"] is not None:        # column sums of the gradient handed to the `down` branch (SideBranchFn)
+            V, D = st["s"]["x"].shape[2], p["W"].shape[1]
+            ctx.module._down_sg = r["dbeta"].reshape(V, D).sum(0)
         return r["gx"], r["gres"], r["dW"], r["dbias"], r["dmask"], r["dgamma"], r["dbeta"], None
 
 
@@ -324,6 +424,33 @@ class StemSpatialFn(torch.autograd.Function):
                           ctx.module._ws)
         return (r["dx"], r["dW"], r["dbias"], r["dmask"], r["dgamma1"], r["dbeta1"], r["dWd"], r["dbd"], r["dgamma2"],
                 r["dbeta2"], None)
+
+
+class SideBranchFn(torch.autograd.Function):
+    """BatchNorm2d(Conv2d 1x1 (x)) on rows: the `down` branch of Shift_gcn (model/shift_gcn.py:82-86) and the conv
+    residual of the strided units (:31-45, 157-158; the caller gathers the strided frames)."""
+
+    @staticmethod
+    def forward(ctx, x, Wd, bd, gamma, beta, bn, owner, hint_attr):
+        out, saved = side_forward(x, Wd, bd, bn, bn.training, owner._ws)
+        ctx.owner, ctx.hint_attr = owner, hint_attr
+        _stash(ctx, s=saved, p=dict(Wd=Wd, bd=bd, gamma=gamma))
+        return out
+
+    @staticmethod
+    def backward(ctx, G):
+        st = _unstash(ctx)
+        p = st["p"]
+        G = G.contiguous()
+        hint = getattr(ctx.owner, ctx.hint_attr, None)             # column sums of G left by the kernel that produced it
+        setattr(ctx.owner, ctx.hint_attr, None)
+        if hint is None:
+            D = G.shape[-1]
+            acc = ctx.owner._ws.get("side_sg", 2 * D, G.device)
+            ops.channel_stats(G, acc, G.numel() // D, D)
+            hint = ops.reduce_export(acc).reshape(D, 2)[:, 0]
+        r = side_backward(st["s"], G, hint, p["Wd"], p["bd"], p["gamma"], ctx.owner._ws)
+        return r["dx"], r["dWd"], r["dbd"], r["dgamma"], r["dbeta"], None, None, None
 
 
 class TemporalFn(torch.autograd.Function):
@@ -353,6 +480,7 @@ class TemporalFn(torch.autograd.Function):
         gres = None
         if ctx.has_res:
             gres = ops.relu_mask_grad(gy, saved["y"]) if saved["relu"] else gy
+            ctx.module._res_sg = r["dbeta_b"] if saved["relu"] else None   # column sums of gres (conv residual branch)
         return (r["gh"], gres, r["dgamma_a"], r["dbeta_a"], r["gx_in"], r["gy_in"], r["dWt"], r["dbt"], r["gx_out"],
                 r["gy_out"], r["dgamma_b"], r["dbeta_b"], None, None)
 

@@ -60,6 +60,12 @@ def from_rows(r):
     return r.permute(0, 3, 1, 2)
 
 
+def side_supported(conv, num_point):
+    """1x1 conv + BatchNorm side branches served by the tensor-core path (FN.side_forward)"""
+    return (isinstance(conv, nn.Conv2d) and conv.kernel_size == (1, 1) and conv.padding == (0, 0)
+            and (conv.in_channels, conv.out_channels) in ((64, 128), (128, 256)) and num_point in (25, 33))
+
+
 def shift_tables(num_point, in_channels, out_channels):
     """int64 gather tables of the spatial shift (model/shift_gcn.py:108-118), vectorised:
     shift_in[v*C + c] = (v*C + c + c*C) mod (V*C),  shift_out[v*D + d] = (v*D + d - d*D) mod (V*D)."""
@@ -190,7 +196,13 @@ class Shift_gcn(nn.Module):
         return (self.Linear_weight, self.Linear_bias, self.Feature_Mask, self.bn.weight, self.bn.bias)
 
     def forward_rows(self, x_rows, x0):
-        res = None if self.in_channels == self.out_channels else to_rows(self.down(x0))
+        if self.in_channels == self.out_channels:
+            res = None
+        elif side_supported(self.down[0], self.num_point):
+            conv, bn = self.down[0], self.down[1]
+            res = FN.SideBranchFn.apply(x_rows, conv.weight, conv.bias, bn.weight, bn.bias, bn, self, "_down_sg")
+        else:
+            res = to_rows(self.down(x0))
         return FN.SpatialFn.apply(x_rows, res, *self._args(), self)
 
     def _forward_general(self, x0):
@@ -241,7 +253,17 @@ class TCN_GCN_unit(nn.Module):
             return from_rows(y)
         h = gcn(x)
         if tcn1.fused_supported(h):
-            res = to_rows(self.residual(x)) if self._res_mode != "none" else None
+            if self._res_mode == "none":
+                res = None
+            elif self._res_mode == "conv" and side_supported(self.residual.conv, x.shape[3]) \
+                    and x.shape[2] % self.residual.conv.stride[0] == 0:
+                conv, bn = self.residual.conv, self.residual.bn
+                xs = to_rows(x)
+                if conv.stride[0] != 1:
+                    xs = xs[:, ::conv.stride[0]].contiguous()           # frames the strided 1x1 conv reads
+                res = FN.SideBranchFn.apply(xs, conv.weight, conv.bias, bn.weight, bn.bias, bn, tcn1, "_res_sg")
+            else:
+                res = to_rows(self.residual(x))
             return from_rows(tcn1.forward_rows(to_rows(h), res, 1))
         return self.relu(tcn1(h) + self.residual(x))
 

@@ -13,7 +13,7 @@ from ._lib import SgcnRowGemm, SgcnStem, SgcnTShift, SgcnTShiftBwd, SgcnTShiftIn
 
 PRO_SPATIAL, PRO_LERP, PRO_PLAIN, PRO_DY = 0, 1, 2, 3
 EPI_ROT_RAW, EPI_ROT_FUSED, EPI_LINEAR, EPI_SPATIAL_BWD = 0, 1, 2, 3
-WG_SPATIAL, WG_TEMPORAL = 0, 1
+WG_SPATIAL, WG_TEMPORAL, WG_PLAIN = 0, 1, 2
 
 
 LAUNCHES = 0          # kernels of this library enqueued so far (bench.py reports the per-step count)
@@ -216,23 +216,27 @@ def bn1d_bwd_finalize(vd_sums, gamma, mean, invstd, V, D, count, training):
 
 # ------------------------------------------------------------------------------------------------ tensor-core kernels
 def rowgemm(pro, epi, *, in0, out, wimg, groups, V, K, N, T=1, in1=None, pro_a=None, pro_b=None, pro_c=None, bias=None,
-            epi_a=None, epi_b=None, res=None, res2=None, res2m=None, xin=None, stats=None, red0=None, relu=0):
+            epi_a=None, epi_b=None, res=None, res2=None, res2m=None, xin=None, stats=None, red0=None, relu=0, k0=0,
+            in0_gs=0, in1_gs=0, out_gs=0, accum=0):
     lib = _lib.load()
     p = SgcnRowGemm(in0=_p(in0, name="in0"), in1=_p(in1), out=_p(out, name="out"), wimg=_p(wimg), pro_a=_p(pro_a),
                     pro_b=_p(pro_b), pro_c=_p(pro_c), bias=_p(bias), epi_a=_p(epi_a), epi_b=_p(epi_b), res=_p(res),
                     res2=_p(res2), res2m=_p(res2m), xin=_p(xin), stats=_d(stats), red0=_d(red0), groups=int(groups),
-                    V=V, G=groups_per_tile(V), T=int(T), K=K, N=N, relu=int(relu))
+                    V=V, G=groups_per_tile(V), T=int(T), K=K, N=N, relu=int(relu), k0=int(k0), in0_gs=int(in0_gs),
+                    in1_gs=int(in1_gs), out_gs=int(out_gs), accum=int(accum))
     name = "rowgemm[%s/%s]" % (("spatial", "lerp", "plain", "dy")[pro], ("rot_raw", "rot_fused", "linear", "spatial_bwd")[epi])
-    _launch(name, 1, _nbytes(in0, in1, out, res, res2, res2m, xin), lib.sgcn_rowgemm, ctypes.byref(p), pro, epi, _stream())
+    nbytes = int(groups) * V * 4 * (K + N * (2 if accum else 1)) if pro == PRO_PLAIN else _nbytes(in0, in1, out, res, res2, res2m, xin)
+    _launch(name, 1, nbytes, lib.sgcn_rowgemm, ctypes.byref(p), pro, epi, _stream())
 
 
 def wgrad(mode, *, a_src, b_src, dw, groups, V, CA, CB, T=1, a_tab0=None, b_src2=None, b_tab0=None, b_tab1=None,
-          b_tab2=None):
+          b_tab2=None, a_gs=1):
     lib = _lib.load()
     p = SgcnWgrad(a_src=_p(a_src), a_tab0=_p(a_tab0), b_src=_p(b_src), b_src2=_p(b_src2), b_tab0=_p(b_tab0),
                   b_tab1=_p(b_tab1), b_tab2=_p(b_tab2), dw=_p(dw), groups=int(groups), V=V, G=groups_per_tile(V),
-                  T=int(T), CA=CA, CB=CB)
-    _launch("wgrad[%s]" % ("spatial", "temporal")[mode], 1, _nbytes(a_src, b_src, b_src2), lib.sgcn_wgrad,
+                  T=int(T), CA=CA, CB=CB, a_gs=int(a_gs))
+    nbytes = int(groups) * V * 4 * (CA + CB) if mode == WG_PLAIN else _nbytes(a_src, b_src, b_src2)
+    _launch("wgrad[%s]" % ("spatial", "temporal", "plain")[mode], 1, nbytes, lib.sgcn_wgrad,
             ctypes.byref(p), mode, _stream())
 
 
