@@ -86,9 +86,10 @@ def spatial_forward(x, res, W, bias, mask, bn, training, ws, fuse_eval, h_stats=
     return h, saved
 
 
-def spatial_backward(saved, gh, W, mask, gamma, vd_sums_ready, ws, unit_res=None):
+def spatial_backward(saved, gh, W, mask, gamma, vd_sums_ready, ws, unit_res=None, side_fn=None):
     """gh: grad wrt the gcn output with the ReLU mask already applied when ``vd_sums_ready`` (fused unit),
     otherwise the raw incoming gradient.  unit_res = (g_y, y) adds the block's identity-residual gradient.
+    side_fn(gh, column sums of gh) -> input gradient of the conv side branches, added inside the kernel.
 
     Returns dict(gx, gres, dW, dbias, dmask, dgamma, dbeta).
     """
@@ -107,16 +108,17 @@ def spatial_backward(saved, gh, W, mask, gamma, vd_sums_ready, ws, unit_res=None
     gx = torch.empty_like(x)
     dmask_raw = ws.get("dmask", V * C, dev)
     identity = C == D and saved.get("identity_res", True)
+    side_dx = side_fn(gh, fin["dbeta"].reshape(V, D).sum(0)) if side_fn is not None else None
     ops.rowgemm(ops.PRO_DY, ops.EPI_SPATIAL_BWD, in0=gh, in1=z, out=gx, wimg=wimg_t, groups=R, V=V, K=D, N=C,
                 pro_a=fin["alpha"], pro_b=fin["beta"], pro_c=fin["gamma"], epi_a=mm,
-                res=gh if identity else None,
+                res=gh if identity else side_dx,
                 res2=unit_res[0] if unit_res is not None else None,
                 res2m=unit_res[1] if unit_res is not None else None, xin=x, red0=dmask_raw)
     dW = torch.zeros((C, D), device=dev, dtype=torch.float32)
     ops.wgrad(ops.WG_SPATIAL, a_src=x, a_tab0=saved["mm_rot"], b_src=gh, b_src2=z, b_tab0=fin["alpha"], b_tab1=fin["beta"],
               b_tab2=fin["gamma"], dw=dW, groups=R, V=V, CA=C, CB=D)
     dmask = ops.mask_grad_finalize(dmask_raw, mask.reshape(V, C))
-    return dict(gx=gx, gres=None if identity else gh, dW=dW, dbias=fin["dbias"].reshape(1, 1, D),
+    return dict(gx=gx, gres=None if (identity or side_fn is not None) else gh, dW=dW, dbias=fin["dbias"].reshape(1, 1, D),
                 dmask=dmask.reshape(1, V, C), dgamma=fin["dgamma"], dbeta=fin["dbeta"])
 
 
@@ -522,3 +524,64 @@ class UnitFn(torch.autograd.Function):
                              unit_res=(gy, t_saved["y"]))
         return (s["gx"], s["dW"], s["dbias"], s["dmask"], s["dgamma"], s["dbeta"], t["dgamma_a"], t["dbeta_a"],
                 t["gx_in"], t["gy_in"], t["dWt"], t["dbt"], t["gx_out"], t["gy_out"], t["dgamma_b"], t["dbeta_b"], None)
+
+
+class ConvUnitFn(torch.autograd.Function):
+    """A whole TCN_GCN_unit whose side branches are 1x1 conv + BatchNorm (l5, l8: in != out channels, frame stride 2;
+    model/shift_gcn.py:82-86, 152-162): relu(tcn1(gcn1(x)) + residual(x)), sequenced so that every gradient that flows
+    into x is added inside the spatial backward kernel instead of by separate full-tensor additions."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, mask, g1, b1, Wd, bd, gd, bdn, ga, ba, xpos_in, ypos_in, Wt, bt, xpos_out, ypos_out, gb,
+                bb, Wr, br, gr, brn, unit):
+        gcn, tcn = unit.gcn1, unit.tcn1
+        training = unit.training
+        stride = tcn.shift_out.stride
+        D = W.shape[1]
+        need_grad = any(ctx.needs_input_grad)
+        res_d, sd_saved = side_forward(x, Wd, bd, gcn.down[1], training, gcn._ws)
+        h_stats = tcn._ws.get("bn_a", 2 * D, x.device) if training else None
+        h, s_saved = spatial_forward(x, res_d, W, bias, mask, gcn.bn, training, gcn._ws,
+                                     fuse_eval=(not training and not need_grad), h_stats=h_stats)
+        xs = x if stride == 1 else x[:, ::stride].contiguous()          # frames the strided 1x1 conv reads
+        res_r, sr_saved = side_forward(xs, Wr, br, unit.residual.bn, training, tcn._ws)
+        y, t_saved = temporal_forward(h, res_r, 1, tcn.bn, ypos_in, Wt.reshape(D, D), bt, ypos_out, tcn.bn2, stride,
+                                      training, tcn._ws, h_stats_ready=training)
+        ctx.unit = unit
+        if s_saved is not None:
+            s_saved["identity_res"] = False
+        _stash(ctx, s=s_saved, t=t_saved, sd=sd_saved, sr=sr_saved,
+               p=dict(W=W, mask=mask, g1=g1, Wd=Wd, bd=bd, gd=gd, ga=ga, Wt=Wt, gb=gb, Wr=Wr, br=br, gr=gr))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        st = _unstash(ctx)
+        s_saved, t_saved, sd_saved, sr_saved, p = st["s"], st["t"], st["sd"], st["sr"], st["p"]
+        unit = ctx.unit
+        gcn, tcn = unit.gcn1, unit.tcn1
+        gy = gy.contiguous()
+        D = p["W"].shape[1]
+        stride = t_saved["stride"]
+        want_raw = getattr(tcn.shift_in, "_export_raw", False)
+        t = temporal_backward(t_saved, gy, p["ga"], p["Wt"].reshape(D, D), p["gb"], tcn._ws, spatial_saved=s_saved,
+                              spatial_ws=gcn._ws, want_raw=want_raw)
+        if want_raw:
+            tcn.shift_in._raw_ypos_grad, tcn.shift_out._raw_ypos_grad = t["raw_in"], t["raw_out"]
+        gres = ops.relu_mask_grad(gy, t_saved["y"])                      # gradient into the conv residual branch
+        rr = side_backward(sr_saved, gres, t["dbeta_b"], p["Wr"], p["br"], p["gr"], tcn._ws)
+        rd = {}
+
+        def side_fn(gh, sg):
+            rd.update(side_backward(sd_saved, gh, sg, p["Wd"], p["bd"], p["gd"], gcn._ws))
+            dx = rd["dx"]
+            if stride == 1:
+                dx.add_(rr["dx"])
+            else:
+                dx[:, ::stride].add_(rr["dx"])                           # transposed frame stride of the 1x1 conv
+            return dx
+
+        s = spatial_backward(s_saved, t["gh"], p["W"], p["mask"], p["g1"], True, gcn._ws, side_fn=side_fn)
+        return (s["gx"], s["dW"], s["dbias"], s["dmask"], s["dgamma"], s["dbeta"], rd["dWd"], rd["dbd"], rd["dgamma"],
+                rd["dbeta"], t["dgamma_a"], t["dbeta_a"], t["gx_in"], t["gy_in"], t["dWt"], t["dbt"], t["gx_out"],
+                t["gy_out"], t["dgamma_b"], t["dbeta_b"], rr["dWd"], rr["dbd"], rr["dgamma"], rr["dbeta"], None)

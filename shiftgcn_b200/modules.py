@@ -245,11 +245,23 @@ class TCN_GCN_unit(nn.Module):
             self.residual = tcn(in_channels, out_channels, kernel_size=1, stride=stride)
             self._res_mode = "conv"
 
+    def _tcn_fused_for(self, x):
+        """would tcn1 take the fused path for the gcn output of this input?"""
+        probe = torch.empty((x.shape[0], self.gcn1.out_channels, x.shape[2], x.shape[3]), device="meta")
+        return self.tcn1.fused_supported(probe)
+
     def forward(self, x):
         _require_cuda(x, "TCN_GCN_unit")
         gcn, tcn1 = self.gcn1, self.tcn1
         if self._res_mode == "identity" and gcn.fused_supported(x) and tcn1.fused_supported(x):
             y = FN.UnitFn.apply(to_rows(x), *gcn._args(), *tcn1._args(), self)
+            return from_rows(y)
+        if (self._res_mode == "conv" and isinstance(gcn.down, nn.Sequential) and gcn.fused_supported(x)
+                and side_supported(gcn.down[0], x.shape[3]) and side_supported(self.residual.conv, x.shape[3])
+                and x.shape[2] % self.residual.conv.stride[0] == 0 and self._tcn_fused_for(x)):
+            d, r = gcn.down, self.residual
+            y = FN.ConvUnitFn.apply(to_rows(x), *gcn._args(), d[0].weight, d[0].bias, d[1].weight, d[1].bias,
+                                    *tcn1._args(), r.conv.weight, r.conv.bias, r.bn.weight, r.bn.bias, self)
             return from_rows(y)
         h = gcn(x)
         if tcn1.fused_supported(h):
