@@ -137,7 +137,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args):
@@ -151,7 +151,6 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner must not land on stdout next to the JSON line
 
     def note(msg):
         if args.verbose:
@@ -299,7 +298,7 @@ def run_b200(args):
                               "algorithmic_mb_per_sample": algo_mb, "peak_source": peak_src},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # the captured step holds NCCL work: drop it before the communicator, and do not wait on teardown
         trainer = None
@@ -309,7 +308,26 @@ def run_b200(args):
         os._exit(0)
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, cuDNN notes) write to fd 1: point it at stderr for the whole run and keep the
+    real stdout for the ONE JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
