@@ -37,6 +37,23 @@ WORKLOADS = {
 }
 
 
+def _ncu_traffic(kernel, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture
+    of the same step (profiles/r*_traffic_*.json); None when no capture exists for this kernel / workload."""
+    if workload not in ("ntu60-train", "ntu120-train"):
+        return None, None
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic_*.json")), reverse=True):
+        try:
+            with open(path) as f:
+                rec = json.load(f)
+        except (OSError, ValueError):
+            continue
+        if rec.get("kernel") == kernel:
+            return float(rec["dram_bytes_per_launch"]), os.path.relpath(path, ROOT)
+    return None, None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -258,8 +275,10 @@ def run_b200(args):
         top = max(agg.items(), key=lambda kv: kv[1][0])
         name, (t_ms, cnt, by) = top
         achieved = by / cnt / (t_ms / cnt * 1e-3) / 1e9
+        traffic, traffic_src = _ncu_traffic(name, args.workload)
         roofline = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "launches_per_step": cnt,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src, "launches_per_step": cnt,
                     "ms_per_launch": t_ms / cnt, "share_of_step_kernel_time": t_ms / max(total_kernel_ms, 1e-9),
                     "algorithmic_bytes_per_launch": by / cnt,
                     "breakdown_ms": {k: round(v[0], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},

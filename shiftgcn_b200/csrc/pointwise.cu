@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_fwd_kernel(const Sgc
   const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
   const float sc = MODE == 1 ? __ldg(p.scale + k.c) : 0.f, sh = MODE == 1 ? __ldg(p.shift + k.c) : 0.f;
   const int to0 = k.chunk * tper, to1 = min(To, to0 + tper);
-  constexpr int U = MODE == 0 ? kUnrollWide : kUnroll;
+  constexpr int U = MODE == 0 ? kUnrollMax : kUnroll;   // the statistics pass has one load per frame: 16 in flight
   float acc[2] = {0.f, 0.f};
   for (int v = k.warp; v < V; v += k.nw) {
     const float* qb = p.q + ((size_t)k.n * Ti * V + v) * C + k.c;

@@ -25,6 +25,9 @@ import torch
 from . import ops
 
 BN_EPS = 1e-5
+# Function.forward always runs with grad mode off, and needs_input_grad ignores torch.no_grad(): the modules record the
+# caller's grad mode here right before .apply so that inference takes the fully fused (nothing saved) kernels
+GRAD_MODE = True
 
 
 def _bn_args(bn):
@@ -388,7 +391,7 @@ class SpatialFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, res, W, bias, mask, gamma, beta, module):
         training = module.training
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = GRAD_MODE and any(ctx.needs_input_grad)
         h, saved = spatial_forward(x, res, W, bias, mask, module.bn, training, module._ws,
                                    fuse_eval=(not training and not need_grad))
         ctx.module = module
@@ -496,7 +499,7 @@ class UnitFn(torch.autograd.Function):
         gcn, tcn = unit.gcn1, unit.tcn1
         training = unit.training
         n, T, V, C = x.shape
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = GRAD_MODE and any(ctx.needs_input_grad)
         h_stats = tcn._ws.get("bn_a", 2 * C, x.device) if training else None
         h, s_saved = spatial_forward(x, None, W, bias, mask, gcn.bn, training, gcn._ws,
                                      fuse_eval=(not training and not need_grad), h_stats=h_stats)
@@ -538,7 +541,7 @@ class ConvUnitFn(torch.autograd.Function):
         training = unit.training
         stride = tcn.shift_out.stride
         D = W.shape[1]
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = GRAD_MODE and any(ctx.needs_input_grad)
         res_d, sd_saved = side_forward(x, Wd, bd, gcn.down[1], training, gcn._ws)
         h_stats = tcn._ws.get("bn_a", 2 * D, x.device) if training else None
         h, s_saved = spatial_forward(x, res_d, W, bias, mask, gcn.bn, training, gcn._ws,

@@ -203,6 +203,7 @@ class Shift_gcn(nn.Module):
             res = FN.SideBranchFn.apply(x_rows, conv.weight, conv.bias, bn.weight, bn.bias, bn, self, "_down_sg")
         else:
             res = to_rows(self.down(x0))
+        FN.GRAD_MODE = torch.is_grad_enabled()
         return FN.SpatialFn.apply(x_rows, res, *self._args(), self)
 
     def _forward_general(self, x0):
@@ -254,12 +255,14 @@ class TCN_GCN_unit(nn.Module):
         _require_cuda(x, "TCN_GCN_unit")
         gcn, tcn1 = self.gcn1, self.tcn1
         if self._res_mode == "identity" and gcn.fused_supported(x) and tcn1.fused_supported(x):
+            FN.GRAD_MODE = torch.is_grad_enabled()
             y = FN.UnitFn.apply(to_rows(x), *gcn._args(), *tcn1._args(), self)
             return from_rows(y)
         if (self._res_mode == "conv" and isinstance(gcn.down, nn.Sequential) and gcn.fused_supported(x)
                 and side_supported(gcn.down[0], x.shape[3]) and side_supported(self.residual.conv, x.shape[3])
                 and x.shape[2] % self.residual.conv.stride[0] == 0 and self._tcn_fused_for(x)):
             d, r = gcn.down, self.residual
+            FN.GRAD_MODE = torch.is_grad_enabled()
             y = FN.ConvUnitFn.apply(to_rows(x), *gcn._args(), d[0].weight, d[0].bias, d[1].weight, d[1].bias,
                                     *tcn1._args(), r.conv.weight, r.conv.bias, r.bn.weight, r.bn.bias, self)
             return from_rows(y)
