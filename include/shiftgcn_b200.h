@@ -27,6 +27,11 @@ int sgcn_abi_version(void);
 const char* sgcn_last_error(void);
 /* 0 when the current CUDA device is compute capability 10.x, error otherwise (there is no fallback path) */
 int sgcn_device_check(void);
+/* Traversal order of the full-tensor kernels (process-wide setting).  snake != 0: every kernel walks its
+ * tiles in the opposite order of the kernel launched before it, so that it starts on the part of its inputs the
+ * previous kernel touched last (still resident in the 126 MB L2); 0 (default): always ascending.  Results do not
+ * depend on the order.  Returns the previous setting. */
+int sgcn_set_traversal(int snake);
 /* tcgen05 descriptor self test (tests only): mode 0: D[128,N] = A[128,K] * B[N,K]^T; mode 1: D[128,N] = A[128,M]^T * B[128,N] */
 int sgcn_selftest_umma(const float* a, const float* b, float* d, int mode, int K, int N, int M, void* stream);
 /* descriptor probe (tests only): D[128,N] = A*B, each operand K-major or MN-major with explicit swizzle / layout / LBO / SBO */
@@ -188,8 +193,9 @@ typedef struct SgcnTShiftBwd {
 } SgcnTShiftBwd;
 
 /* backward of  p = Shift_1(BN(h)):  du = Shift^T(dp)
- * mode 0: sums[c][3] += { du, du*hhat, dp*dU };
- * mode 1: gh = [h>0] * k1*(du - m1 - hhat*m2);  vd_sums[v,c][2] += { gh, gh*zhat } when z != NULL */
+ * mode 0: sums[c][3] += { du, du*hhat, dp*dU }   (skipped when gate != NULL and *gate == 0, see sgcn_tshift_in_bwd_sums);
+ * mode 1: gh = [h>0] * k1*(du - m1 - hhat*m2);  vd_sums[v,c][2] += { gh, gh*zhat } when z != NULL;
+ *         pos_sums[c] += dp*dU (the position-gradient sum of mode 0; needs scale / shift) */
 typedef struct SgcnTShiftInBwd {
   const float* dp;        /* grad wrt p [n, T, V, C]                            */
   const float* h;         /* tcn input (gcn output)                             */
@@ -207,9 +213,41 @@ typedef struct SgcnTShiftInBwd {
   double* sums;           /* [C][3] (mode 0)                                    */
   double* vd_sums;        /* [V, C][2] (mode 1)                                 */
   float* gh;              /* [n, T, V, C] (mode 1)                              */
+  double* pos_sums;       /* [C] (mode 1)                                       */
+  const int* gate;        /* device flag or NULL (mode 0)                       */
   long long n_samples;
   int T, V, C, relu_h;
 } SgcnTShiftInBwd;
+
+/* The two BatchNorm backward sums of sgcn_tshift_in_bwd mode 0 WITHOUT a pass over dp and h.  With p = Shift_1(U),
+ * U = scale*h + shift, dp = dpre * W_t and dW_t = dpre^T p (model/shift_gcn.py:66-70):
+ *     sum du        = sum_d W_t[d,c] * dbt[d]  -  sum over the few frames r next to the sequence ends of dp(r)*(1 - e_c(r))
+ *     sum du * U    = sum_d W_t[d,c] * dW_t[d,c]
+ *     sum du * hhat = invstd * ((sum du*U - shift*sum du) / scale - mean * sum du)
+ * (dbt = column sums of dpre = the conv-bias gradient, e_c(r) = total weight of the shift taps of frame r that fall
+ * inside the sequence).  Only the boundary frames of dp are read.  sums[c][0..1] receive the two sums.  gate[0] is
+ * set to 1 -- and nothing is written to sums -- when some |gamma[c]| = |scale/invstd| < 1e-3 makes the division
+ * ill-conditioned: sgcn_tshift_in_bwd mode 0 launched with the same gate then computes the sums the long way. */
+typedef struct SgcnTShiftInSums {
+  const float* dp;        /* [n, T, V, C]                                       */
+  const float* ypos_eff;  /* [C]                                                */
+  const float* Wt;        /* [C out][C in] temporal_linear.weight               */
+  const float* dWt;       /* its gradient                                       */
+  const float* dbt;       /* [C] conv-bias gradient                             */
+  const float* mean;      /* [C] BN(h) tables                                   */
+  const float* invstd;
+  const float* scale;
+  const float* shift;
+  double* sums;           /* [C][3]                                             */
+  int* gate;              /* device flag                                        */
+  long long n_samples;
+  int T, V, C;
+} SgcnTShiftInSums;
+int sgcn_tshift_in_bwd_sums(const SgcnTShiftInSums* p, void* stream);
+/* K5 (shift_cuda_kernel.cu:371-395) on pos_sums[c] / n_batch: grad_xpos = 0, grad_ypos = sign * 0.01 (1e-4 at 0);
+ * raw_out (optional) receives the means; pos_sums is handed back zeroed. */
+int sgcn_shift_pos_finalize(double* pos_sums, float* grad_xpos, float* grad_ypos, float* raw_out, int C, double n_batch,
+                            void* stream);
 
 int sgcn_bn_res_relu_fwd(const float* z, const float* res, float* h, const float* scale, const float* shift,
                          double* stats_out, long long rows, int V, int D, int relu, void* stream);

@@ -37,8 +37,14 @@ class SgcnTShiftBwd(ctypes.Structure):
 
 class SgcnTShiftInBwd(ctypes.Structure):
     _fields_ = [(n, _vp) for n in ("dp", "h", "z", "ypos_eff", "mean", "invstd", "scale", "shift", "k1", "m1", "m2",
-                                   "zmean", "zinvstd", "sums", "vd_sums", "gh")] + \
+                                   "zmean", "zinvstd", "sums", "vd_sums", "gh", "pos_sums", "gate")] + \
                [("n_samples", _ll), ("T", _i), ("V", _i), ("C", _i), ("relu_h", _i)]
+
+
+class SgcnTShiftInSums(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("dp", "ypos_eff", "Wt", "dWt", "dbt", "mean", "invstd", "scale", "shift", "sums",
+                                   "gate")] + \
+               [("n_samples", _ll), ("T", _i), ("V", _i), ("C", _i)]
 
 
 class SgcnStem(ctypes.Structure):
@@ -52,6 +58,7 @@ class SgcnStem(ctypes.Structure):
 SIGNATURES = {
     "sgcn_abi_version": [],
     "sgcn_device_check": [],
+    "sgcn_set_traversal": [_i],
     "sgcn_selftest_umma": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "sgcn_selftest_probe": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "sgcn_shift_fwd_nchw_f32": [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
@@ -66,6 +73,8 @@ SIGNATURES = {
     "sgcn_tshift_fwd": [ctypes.POINTER(SgcnTShift), _i, _vp],
     "sgcn_tshift_bwd": [ctypes.POINTER(SgcnTShiftBwd), _i, _vp],
     "sgcn_tshift_in_bwd": [ctypes.POINTER(SgcnTShiftInBwd), _i, _vp],
+    "sgcn_tshift_in_bwd_sums": [ctypes.POINTER(SgcnTShiftInSums), _vp],
+    "sgcn_shift_pos_finalize": [_vp, _vp, _vp, _vp, _i, _d, _vp],
     "sgcn_relu_bn1d_bwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "sgcn_channel_stats": [_vp, _vp, _ll, _i, _vp],
     "sgcn_relu_mask_grad": [_vp, _vp, _vp, _ll, _vp],
@@ -84,7 +93,8 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB_PATH
+    # SGCN_LIB: developer override for A/B runs of two builds of the same ABI
+    return os.environ.get("SGCN_LIB") or _build.LIB_PATH
 
 
 def load():
@@ -104,6 +114,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError here == header / library drift
         fn.restype = ctypes.c_int
         fn.argtypes = argtypes
+    # snake traversal of the full-tensor kernels (on unless SGCN_SNAKE=0), see include/shiftgcn_b200.h
+    lib.sgcn_set_traversal(0 if os.environ.get("SGCN_SNAKE", "1") == "0" else 1)
     _lib = lib
     return lib
 

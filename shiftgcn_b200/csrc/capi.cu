@@ -2,6 +2,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "capi_internal.h"
 
 namespace sgcn {
@@ -37,7 +39,23 @@ int num_sms() {
   return cached;
 }
 
+// process-wide (autograd runs the backward kernels from its own host thread); a race between two launching threads
+// can only pick a less favourable order, never a wrong result
+static std::atomic<int> g_snake{0}, g_last_rev{0};
+
+int next_direction() {
+  if (!g_snake.load(std::memory_order_relaxed)) return 0;
+  return g_last_rev.fetch_xor(1, std::memory_order_relaxed) ^ 1;
+}
+
+void mark_forward() { g_last_rev.store(0, std::memory_order_relaxed); }
+
 }  // namespace sgcn
+
+extern "C" int sgcn_set_traversal(int snake) {
+  sgcn::g_last_rev.store(0);
+  return sgcn::g_snake.exchange(snake ? 1 : 0);
+}
 
 extern "C" const char* sgcn_last_error(void) { return sgcn::g_err; }
 

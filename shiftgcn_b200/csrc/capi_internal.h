@@ -10,4 +10,8 @@ int set_error(const char* msg);                              // returns -1
 int set_cuda_error(const char* where, cudaError_t e);        // returns -2
 int check_launch(const char* kernel_name);                   // cudaGetLastError() -> 0 / -2
 int num_sms();                                               // SM count of the current device (cached)
+// "Snake" traversal (sgcn_set_traversal): every full-tensor kernel walks its tiles in the opposite order of the kernel
+// launched before it on this host thread, so it starts on the ~100 MB that are still resident in the 126 MB L2.
+int next_direction();                                        // 0 = ascending, 1 = descending; flips when enabled
+void mark_forward();                                         // a kernel without a reversed order was launched
 }  // namespace sgcn

@@ -110,7 +110,7 @@ struct Cfg {
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int PRO, int EPI, int V, int K, int N>
-__global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGemm p) {
+__global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGemm p, const int rev) {
   using C = Cfg<PRO, EPI, V, K, N>;
   constexpr int G = C::G, KC = C::KC, NCH = C::NCH, OS = C::kOpStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -155,6 +155,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
   const long long ntiles = (p.groups + G - 1) / G;
   const int my_tiles = (long long)blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   const int total_chunks = my_tiles * KC;
+  // snake traversal (capi_internal.h): rev walks the tiles from the last one down
+  auto tile_of = [&](int ti) -> long long {
+    const long long t = (long long)blockIdx.x + (long long)ti * gridDim.x;
+    return rev ? ntiles - 1 - t : t;
+  };
 
   if (warp >= kMmaWarp && warp < kBld0) {
     reg_dec<kRegsMma>();
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
       const bool simple = k0 == K && p.in0_gs <= 1;
       auto issue = [&](int q) {                                    // row & 7 is invariant under +24, so is the swizzle
         const int ti = q / KC, kc = q - ti * KC;
-        const long long g0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * G;
+        const long long g0 = tile_of(ti) * G;
         const int nrow = (int)((p.groups - g0) < G ? (p.groups - g0) : G) * V;
         const uint32_t dst = sOp + (uint32_t)(q % OS) * kChunkBytes + dst0;
         if (simple) {
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
       }
       auto issue = [&](int q) {
         const int ti = q / KC, kc = q - ti * KC;
-        const long long g0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * G;
+        const long long g0 = tile_of(ti) * G;
         const uint32_t dst = sRaw + (uint32_t)(q % RS) * C::kRawBytes + (uint32_t)prow * 256u + (uint32_t)pc4 * 16u;
         const long long gfirst = g0 + lerp_lo;                     // first group of the raw tile
         if (PRO == PRO_SPATIAL || (gfirst >= 0 && gfirst + G + C::kWin <= p.groups)) {
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
       }
       for (int q = 0; q < total_chunks; ++q) {
         const int ti = q / KC, kc = q - ti * KC;
-        const long long g0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * G;
+        const long long g0 = tile_of(ti) * G;
         const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
         cp_wait<RS - 1>();
         bld_sync();                                                // every thread's pieces of chunk q have landed
@@ -427,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
     const uint32_t stb = sSt + (uint32_t)(lane & 3) * 4u;
 
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const long long g0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * G;
+      const long long g0 = tile_of(ti) * G;
       const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
       const size_t row0 = (size_t)g0 * V;
       const int buf = ti & 1;
@@ -597,7 +602,7 @@ static int launch(const SgcnRowGemm& p, cudaStream_t s) {
   if (ntiles == 0) return 0;
   long long grid = num_sms();
   if (grid > ntiles) grid = ntiles;
-  kern<<<(unsigned)grid, kThreads, C::kSmem, s>>>(p);
+  kern<<<(unsigned)grid, kThreads, C::kSmem, s>>>(p, next_direction());
   return check_launch("fused_gemm_kernel");
 }
 

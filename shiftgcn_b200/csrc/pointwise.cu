@@ -27,6 +27,9 @@
 namespace sgcn {
 
 constexpr int kMaxWarps = 20;     // ceil(V/2) warps, V <= 40
+#ifndef SGCN_WALKER_MINBLOCKS
+#define SGCN_WALKER_MINBLOCKS 2   // register cap of the walkers: 65536 / (640 * MINBLOCKS)
+#endif
 constexpr int kUnroll = 4;        // frames in flight per thread (kernels with >= 3 loads per frame)
 constexpr int kUnrollWide = 8;    // ... with 2 loads per frame
 constexpr int kUnrollMax = 16;    // ... with a single load per frame (read-only statistics passes are latency bound)
@@ -39,13 +42,15 @@ struct Col {            // the walker's identity
   int chunk;            // frame chunk
 };
 
-__device__ __forceinline__ Col col_of(int C, int nchunks) {
+// rev: walk the grid from its last block to its first ("snake" traversal, capi_internal.h:next_direction) so that
+// the kernel starts on the part of its inputs that the previous kernel touched last and that is still in L2
+__device__ __forceinline__ Col col_of(int C, int nchunks, int rev) {
   Col k;
   k.lane = threadIdx.x & 31;
   k.warp = threadIdx.x >> 5;
   k.nw = blockDim.x >> 5;
   const int cblocks = C >> 5;
-  unsigned b = blockIdx.x;
+  unsigned b = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const unsigned cb = b % cblocks;
   b /= cblocks;
   k.chunk = (int)(b % (unsigned)nchunks);
@@ -57,7 +62,7 @@ __device__ __forceinline__ Col col_of(int C, int nchunks) {
 // combine per-thread partials over the block's warps, then one double atomic per (channel, value)
 template <int NV>
 __device__ __forceinline__ void block_reduce_channels(const float (&v)[NV], double* __restrict__ dst, int c,
-                                                      float* scratch /* [kMaxWarps * 32 * NV] */) {
+                                                      float* scratch /* [kMaxWarps * 32 * NV] */, int stride = NV) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
   for (int k = 0; k < NV; ++k) scratch[(warp * NV + k) * 32 + lane] = v[k];
@@ -65,7 +70,7 @@ __device__ __forceinline__ void block_reduce_channels(const float (&v)[NV], doub
   for (int k = warp; k < NV; k += nw) {
     double s = 0.0;
     for (int w = 0; w < nw; ++w) s += (double)scratch[(w * NV + k) * 32 + lane];
-    atomicAdd(dst + (size_t)c * NV + k, s);
+    atomicAdd(dst + (size_t)c * stride + k, s);
   }
 }
 
@@ -98,16 +103,16 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 // ------------------------------------------------------------------------------------------------
 // h = relu(z * sc[v,d] + sh[v,d] + res)          stats_out[d] += {sum h, sum h^2}
 // walks row GROUPS (frames of any sample): groups [g0, g1) of the chunk
-__global__ void __launch_bounds__(kMaxWarps * 32, 2) bn_res_relu_fwd_kernel(const float* __restrict__ z,
+__global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) bn_res_relu_fwd_kernel(const float* __restrict__ z,
                                                                          const float* __restrict__ res,
                                                                          float* __restrict__ h,
                                                                          const float* __restrict__ sc,
                                                                          const float* __restrict__ sh,
                                                                          double* __restrict__ stats_out,
                                                                          long long groups, int gper, int nchunks, int V,
-                                                                         int D, int relu) {
+                                                                         int D, int relu, int rev) {
   __shared__ float scratch[kMaxWarps * 32 * 2];
-  const Col k = col_of(D, nchunks);
+  const Col k = col_of(D, nchunks, rev);
   const long long g0 = (long long)k.chunk * gper;
   const int ng = (int)((groups - g0) < gper ? (groups - g0) : gper);
   const int pitch = V * D;
@@ -145,9 +150,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) bn_res_relu_fwd_kernel(cons
 // s(to) = g * Q(to*stride + y1) + f * Q(to*stride + y1 + 1), Q zero padded           (K1 with xpos = 0)
 // MODE 0: stats[c] += {sum s, sum s^2};  MODE 1: out = [relu](s*sc + sh + res)
 template <int MODE, bool S1>
-__global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_fwd_kernel(const SgcnTShift p, int tper, int nchunks) {
+__global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_fwd_kernel(const SgcnTShift p, int tper, int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32 * 2];
-  const Col k = col_of(p.C, nchunks);
+  const Col k = col_of(p.C, nchunks, rev);
   const int C = p.C, V = p.V, Ti = p.T_in, To = p.T_out, st = S1 ? 1 : p.stride;
   const int pitch = V * C;
   const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
@@ -195,15 +200,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_fwd_kernel(const Sgc
 // sums5[c] += { g, g*shat, g*dq, dq, shat*dq }   with g = gy*[y>0] (if relu), s = Shift(q), shat = (s-mean)*invstd,
 // dq = Q(ta+1) - Q(ta)  (d s / d ypos, K4 with xpos = 0)
 template <bool S1>
-__global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_bwd_stats_kernel(const SgcnTShiftBwd p, int tper, int nchunks) {
+__global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_bwd_stats_kernel(const SgcnTShiftBwd p, int tper, int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32 * 5];
-  const Col k = col_of(p.C, nchunks);
+  const Col k = col_of(p.C, nchunks, rev);
   const int C = p.C, V = p.V, Ti = p.T_in, To = p.T_out, st = S1 ? 1 : p.stride;
   const int pitch = V * C;
   const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
-  const float mean = __ldg(p.mean + k.c), invstd = __ldg(p.invstd + k.c);
   const int to0 = k.chunk * tper, to1 = min(To, to0 + tper);
-  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};                       // { g, g*s, g*dq, dq, s*dq }: shat applied after the walk
   for (int v = k.warp; v < V; v += k.nw) {
     const float* qb = p.q + ((size_t)k.n * Ti * V + v) * C + k.c;
     const size_t ob = ((size_t)k.n * To * V + v) * C + k.c;
@@ -227,41 +231,51 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_bwd_stats_kernel(con
           const float s = fmaf(L.f, q1[u], L.g * a);
           const float dq = q1[u] - a;
           qa = q1[u];
-          const float shat = (s - mean) * invstd;
           const float g = (!p.relu || yv[u] > 0.f) ? gv[u] : 0.f;
           acc[0] += g;
-          acc[1] = fmaf(g, shat, acc[1]);
+          acc[1] = fmaf(g, s, acc[1]);
           acc[2] = fmaf(g, dq, acc[2]);
           acc[3] += dq;
-          acc[4] = fmaf(shat, dq, acc[4]);
+          acc[4] = fmaf(s, dq, acc[4]);
         }
     }
+  }
+  {   // sum x*shat = invstd * (sum x*s - mean * sum x)
+    const float mean = __ldg(p.mean + k.c), invstd = __ldg(p.invstd + k.c);
+    acc[1] = invstd * (acc[1] - mean * acc[0]);
+    acc[4] = invstd * (acc[4] - mean * acc[3]);
   }
   block_reduce_channels<5>(acc, p.sums, k.c, scratch);
 }
 
 struct BwdCh {
-  float mean, invstd, k1, m1, m2;
+  float k1, ka, kb;      // ds = k1*(g - m1 - shat*m2) = k1*g + ka*s + kb
 };
+__device__ __forceinline__ BwdCh bwd_of(const SgcnTShiftBwd& p, int c) {
+  const float mean = __ldg(p.mean + c), invstd = __ldg(p.invstd + c), k1 = __ldg(p.k1 + c), m1 = __ldg(p.m1 + c),
+              m2 = __ldg(p.m2 + c);
+  const float ka = -k1 * invstd * m2;
+  return {k1, ka, -k1 * m1 - ka * mean};
+}
 // ds(to) = k1*(g - m1 - shat*m2) for an output frame inside [0, T_out), else 0
 __device__ __forceinline__ float ds_eval(bool valid, float g, float y, int relu, float qa, float qb, const LerpCh& L,
                                          const BwdCh& B) {
   if (!valid) return 0.f;
   if (relu && !(y > 0.f)) g = 0.f;
   const float s = fmaf(L.f, qb, L.g * qa);
-  return B.k1 * (g - B.m1 - (s - B.mean) * B.invstd * B.m2);
+  return fmaf(B.k1, g, fmaf(B.ka, s, B.kb));
 }
 
 // stride 1:  dpre(t) = [Q(t) > 0] * ( g*ds(t-y1) + f*ds(t-y1-1) ),  ds(to) uses s(to) = g*Q(to+y1) + f*Q(to+y1+1)
 // walk over input frames t; to = t - y1; the previous ds and the tap Q(t+1) slide along in registers
-__global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_bwd_apply_s1_kernel(const SgcnTShiftBwd p, int tper,
-                                                                            int nchunks) {
+__global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_bwd_apply_s1_kernel(const SgcnTShiftBwd p, int tper,
+                                                                            int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32];
-  const Col k = col_of(p.C, nchunks);
+  const Col k = col_of(p.C, nchunks, rev);
   const int C = p.C, V = p.V, T = p.T_in;
   const int pitch = V * C;
   const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
-  const BwdCh B = {__ldg(p.mean + k.c), __ldg(p.invstd + k.c), __ldg(p.k1 + k.c), __ldg(p.m1 + k.c), __ldg(p.m2 + k.c)};
+  const BwdCh B = bwd_of(p, k.c);
   const int relu = p.relu;
   const int t0 = k.chunk * tper, t1 = min(T, t0 + tper);
   float acc[1] = {0.f};
@@ -307,14 +321,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_bwd_apply_s1_kernel(
 
 // stride 2 (K3): output frame to feeds input frames t = 2*to + y1 (weight g) and t + 1 (weight f); frames that no
 // output frame touches get 0.  Walk over output frames.
-__global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_bwd_apply_s2_kernel(const SgcnTShiftBwd p, int tper,
-                                                                            int nchunks) {
+__global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_bwd_apply_s2_kernel(const SgcnTShiftBwd p, int tper,
+                                                                            int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32];
-  const Col k = col_of(p.C, nchunks);
+  const Col k = col_of(p.C, nchunks, rev);
   const int C = p.C, V = p.V, Ti = p.T_in, To = p.T_out;
   const int pitch = V * C;
   const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
-  const BwdCh B = {__ldg(p.mean + k.c), __ldg(p.invstd + k.c), __ldg(p.k1 + k.c), __ldg(p.m1 + k.c), __ldg(p.m2 + k.c)};
+  const BwdCh B = bwd_of(p, k.c);
   const int relu = p.relu;
   const int to0 = k.chunk * tper, to1 = min(To, to0 + tper);
   float acc[1] = {0.f};
@@ -364,10 +378,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_bwd_apply_s2_kernel(
 //   sum_t du            = sum_r dp(r) * ( g*[r+y1 in range] + f*[r+y1+1 in range] )
 //   sum_t du * hhat(t)  = sum_r dp(r) * ( g*hhat(r+y1) + f*hhat(r+y1+1) )          (hhat zero padded)
 //   d/dypos             = sum_r dp(r) * ( U(r+y1+1) - U(r+y1) )
-__global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_in_bwd_stats_kernel(const SgcnTShiftInBwd p, int tper,
-                                                                            int nchunks) {
+__global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_in_bwd_stats_kernel(const SgcnTShiftInBwd p, int tper,
+                                                                            int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32 * 3];
-  const Col k = col_of(p.C, nchunks);
+  if (p.gate && *p.gate == 0) return;                          // sgcn_tshift_in_bwd_sums already produced the sums
+  const Col k = col_of(p.C, nchunks, rev);
   const int C = p.C, V = p.V, T = p.T;
   const int pitch = V * C;
   const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
@@ -407,25 +422,39 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_in_bwd_stats_kernel(
 
 // gh(t) = [h(t) > 0] * k*(du(t) - m1 - hhat(t)*m2),  du(t) = g*dp(t-y1) + f*dp(t-y1-1);
 // per-(v,c) sums for the BN1d backward of the spatial unit: { gh, gh * zhat }
-__global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_in_bwd_apply_kernel(const SgcnTShiftInBwd p, int tper,
-                                                                            int nchunks) {
-  const Col k = col_of(p.C, nchunks);
+__global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_in_bwd_apply_kernel(const SgcnTShiftInBwd p, int tper,
+                                                                            int nchunks, int rev) {
+  __shared__ float scratch[kMaxWarps * 32];
+  const Col k = col_of(p.C, nchunks, rev);
   const int C = p.C, V = p.V, T = p.T;
   const int pitch = V * C;
   const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
-  const float mean = __ldg(p.mean + k.c), invstd = __ldg(p.invstd + k.c), kk = __ldg(p.k1 + k.c),
-              m1 = __ldg(p.m1 + k.c), m2 = __ldg(p.m2 + k.c);
+  // k*(du - m1 - hhat*m2) as the affine map  kk*du + ka*h + kb  (three registers instead of five)
+  const float kk = __ldg(p.k1 + k.c);
+  float ka, kb;
+  {
+    const float mean = __ldg(p.mean + k.c), invstd = __ldg(p.invstd + k.c), m1 = __ldg(p.m1 + k.c), m2 = __ldg(p.m2 + k.c);
+    ka = -kk * invstd * m2;
+    kb = -kk * m1 - ka * mean;
+  }
   const int t0 = k.chunk * tper, t1 = min(T, t0 + tper);
   const bool has_z = p.z != nullptr;
+  // position gradient (K4): sum_r dp(r) * (U(r+y1+1) - U(r+y1)), U = sc*h + sh zero padded, re-indexed over
+  // t = r+y1+1 so that it needs only the walker's own taps:  sc * sum_t dp(t-y1-1) * (h(t) - h(t-1))  [h(-1) = h(T) = 0]
+  // + sh * (dp(-y1-1) - dp(T-y1-1)); the term of t = T is added by the chunk that ends the sequence
+  float acc[1] = {0.f};
   for (int v = k.warp; v < V; v += k.nw) {
     const size_t cb = ((size_t)k.n * T * V + v) * C + k.c;
     const float* dpb = p.dp + cb;
     const float* hb = p.h + cb;
     const float* zb = has_z ? p.z + cb : hb;
     float* gb = p.gh + cb;
-    const float zmean = has_z ? __ldg(p.zmean + v * C + k.c) : 0.f, zinv = has_z ? __ldg(p.zinvstd + v * C + k.c) : 0.f;
+    const float zinv = has_z ? __ldg(p.zinvstd + v * C + k.c) : 0.f;
+    const float zoff = has_z ? -__ldg(p.zmean + v * C + k.c) * zinv : 0.f;      // zhat = z*zinv + zoff
     float s0 = 0.f, s1 = 0.f;
     float dprev = tap(dpb, t0 - L.y1 - 1, T, pitch);
+    float hprev = t0 > 0 ? ldrow(hb, t0 - 1, T, pitch) : 0.f;
+    float ah = 0.f;
     for (int t = t0; t < t1; t += kUnroll) {
       float d0[kUnroll], hv[kUnroll], zv[kUnroll];
 #pragma unroll
@@ -439,28 +468,92 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) tshift_in_bwd_apply_kernel(
       for (int u = 0; u < kUnroll; ++u)
         if (t + u < t1) {
           const float du = fmaf(L.f, dprev, L.g * d0[u]);
+          ah = fmaf(dprev, hv[u] - hprev, ah);
+          hprev = hv[u];
           dprev = d0[u];
-          float g = kk * (du - m1 - (hv[u] - mean) * invstd * m2);
+          float g = fmaf(kk, du, fmaf(ka, hv[u], kb));
           if (p.relu_h && !(hv[u] > 0.f)) g = 0.f;
           gb[(size_t)(t + u) * pitch] = g;
           s0 += g;
-          s1 = fmaf(g, (zv[u] - zmean) * zinv, s1);
+          s1 = fmaf(g, fmaf(zv[u], zinv, zoff), s1);
         }
+    }
+    {
+      float edge = t0 == 0 ? tap(dpb, -L.y1 - 1, T, pitch) : 0.f;   // re-loaded: not worth a register across the walk
+      if (t1 == T) {                                              // t = T: h(T) = 0, dprev = dp(T-1-y1)
+        ah = fmaf(dprev, -hprev, ah);
+        edge -= dprev;
+      }
+      acc[0] += fmaf(__ldg(p.scale + k.c), ah, __ldg(p.shift + k.c) * edge);
     }
     if (has_z) {
       atomicAdd(p.vd_sums + 2 * ((size_t)v * C + k.c), (double)s0);
       atomicAdd(p.vd_sums + 2 * ((size_t)v * C + k.c) + 1, (double)s1);
     }
   }
+  block_reduce_channels<1>(acc, p.pos_sums, k.c, scratch);
+}
+
+// ------------------------------------------------------------------------------------------------ algebraic BN(h) backward sums
+// gate = 1 when a BatchNorm weight is too small for the division below (the exact pass runs instead)
+__global__ void tshift_in_gate_kernel(const float* __restrict__ scale, const float* __restrict__ invstd, int* gate, int C) {
+  const int c = threadIdx.x;
+  const int bad = (c < C) && !(fabsf(__ldg(scale + c)) >= 1e-3f * fabsf(__ldg(invstd + c)));
+  const int any = __syncthreads_or(bad);
+  if (threadIdx.x == 0) *gate = any;
+}
+
+// sums[c][0] -= sum over the frames r whose shift taps leave the sequence of dp(r) * (1 - e_c(r)),
+// e_c(r) = g*[0 <= r+y1 < T] + f*[0 <= r+y1+1 < T]:  at most |y1|+1 frames at one end of every sample
+__global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_in_boundary_kernel(const SgcnTShiftInSums p) {
+  __shared__ float scratch[kMaxWarps * 32];
+  if (*p.gate) return;
+  const Col k = col_of(p.C, 1, 0);
+  const int C = p.C, V = p.V, T = p.T;
+  const int pitch = V * C;
+  const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
+  const int r0 = L.y1 >= 0 ? max(0, T - L.y1 - 1) : 0, r1 = L.y1 >= 0 ? T : min(T, -L.y1);
+  float acc[1] = {0.f};
+  for (int v = k.warp; v < V; v += k.nw) {
+    const float* dpb = p.dp + ((size_t)k.n * T * V + v) * C + k.c;
+    for (int r = r0; r < r1; ++r) {
+      const float w = (inside(r + L.y1, T) ? 0.f : L.g) + (inside(r + L.y1 + 1, T) ? 0.f : L.f);
+      acc[0] = fmaf(__ldg(dpb + (size_t)r * pitch), -w, acc[0]);
+    }
+  }
+  block_reduce_channels<1>(acc, p.sums, k.c, scratch, 3);       // sums[c][0]
+}
+
+__global__ void __launch_bounds__(256) tshift_in_combine_kernel(const SgcnTShiftInSums p) {
+  __shared__ double part[2][4][64];
+  const int cl = threadIdx.x & 63, dg = threadIdx.x >> 6;         // 64 channels x 4 interleaved row groups
+  const int c = blockIdx.x * 64 + cl, C = p.C;
+  if (*p.gate) return;
+  double s0 = 0.0, sw = 0.0;
+  for (int d = dg; d < C; d += 4) {
+    const double w = (double)__ldg(p.Wt + (size_t)d * C + c);
+    s0 = fma(w, (double)__ldg(p.dbt + d), s0);
+    sw = fma(w, (double)__ldg(p.dWt + (size_t)d * C + c), sw);
+  }
+  part[0][dg][cl] = s0;
+  part[1][dg][cl] = sw;
+  __syncthreads();
+  if (dg != 0) return;
+  s0 = part[0][0][cl] + part[0][1][cl] + part[0][2][cl] + part[0][3][cl];
+  sw = part[1][0][cl] + part[1][1][cl] + part[1][2][cl] + part[1][3][cl];
+  s0 += p.sums[3 * (size_t)c];                                   // minus the boundary frames (tshift_in_boundary_kernel)
+  const double duh = (sw - (double)p.shift[c] * s0) / (double)p.scale[c];   // sum du * h
+  p.sums[3 * (size_t)c] = s0;
+  p.sums[3 * (size_t)c + 1] = (double)p.invstd[c] * (duh - (double)p.mean[c] * s0);
 }
 
 // ------------------------------------------------------------------------------------------------ group walkers
 // stats[c] += { sum x, sum x^2 }   (BatchNorm2d statistics of a stand-alone Shift_tcn input, model/shift_gcn.py:66)
-__global__ void __launch_bounds__(kMaxWarps * 32, 2) channel_stats_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) channel_stats_kernel(const float* __restrict__ x,
                                                                        double* __restrict__ stats, long long groups,
-                                                                       int gper, int nchunks, int V, int C) {
+                                                                       int gper, int nchunks, int V, int C, int rev) {
   __shared__ float scratch[kMaxWarps * 32 * 2];
-  const Col k = col_of(C, nchunks);
+  const Col k = col_of(C, nchunks, rev);
   const long long g0 = (long long)k.chunk * gper;
   const int ng = (int)((groups - g0) < gper ? (groups - g0) : gper);
   const int pitch = V * C;
@@ -485,7 +578,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) channel_stats_kernel(const 
 }
 
 // gh = g * [h > 0];  vd_sums[v,c] += { gh, gh * zhat }      (stand-alone Shift_gcn backward, model/shift_gcn.py:137-141)
-__global__ void __launch_bounds__(kMaxWarps * 32, 2) relu_bn1d_bwd_stats_kernel(const float* __restrict__ g,
+__global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) relu_bn1d_bwd_stats_kernel(const float* __restrict__ g,
                                                                              const float* __restrict__ h,
                                                                              const float* __restrict__ z,
                                                                              const float* __restrict__ zmean,
@@ -493,8 +586,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) relu_bn1d_bwd_stats_kernel(
                                                                              float* __restrict__ gh,
                                                                              double* __restrict__ vd_sums,
                                                                              long long groups, int gper, int nchunks,
-                                                                             int V, int C) {
-  const Col k = col_of(C, nchunks);
+                                                                             int V, int C, int rev) {
+  const Col k = col_of(C, nchunks, rev);
   const long long g0 = (long long)k.chunk * gper;
   const int ng = (int)((groups - g0) < gper ? (groups - g0) : gper);
   const int pitch = V * C;
@@ -527,8 +620,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) relu_bn1d_bwd_stats_kernel(
 
 // out = g * [y > 0]
 __global__ void __launch_bounds__(256) relu_mask_grad_kernel(const float4* __restrict__ g, const float4* __restrict__ y,
-                                                             float4* __restrict__ out, long long n4) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+                                                             float4* __restrict__ out, long long n4, int rev) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (long long)gridDim.x * blockDim.x) {
+    const long long i = rev ? n4 - 1 - j : j;
     const float4 a = g[i], b = y[i];
     out[i] = make_float4(b.x > 0.f ? a.x : 0.f, b.y > 0.f ? a.y : 0.f, b.z > 0.f ? a.z : 0.f, b.w > 0.f ? a.w : 0.f);
   }
@@ -574,7 +668,7 @@ extern "C" int sgcn_bn_res_relu_fwd(const float* z, const float* res, float* h, 
   const long long groups = rows / V;
   const Geo g = geometry(D, V, 1, groups, 8);
   bn_res_relu_fwd_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(z, res, h, scale, shift, stats_out, groups,
-                                                                        g.per, g.nchunks, V, D, relu);
+                                                                        g.per, g.nchunks, V, D, relu, next_direction());
   return check_launch("bn_res_relu_fwd_kernel");
 }
 
@@ -584,14 +678,15 @@ extern "C" int sgcn_tshift_fwd(const SgcnTShift* p, int mode, void* stream) {
   if (p->stride < 1 || p->T_out != p->T_in / p->stride) return set_error("sgcn_tshift_fwd: T_out must be T_in / stride");
   if (p->n_samples <= 0 || p->T_out <= 0) return 0;
   const Geo g = geometry(p->C, p->V, p->n_samples, p->T_out, 8);
+  const int rev = next_direction();
   if (mode == 0) {
     if (!p->stats) return set_error("sgcn_tshift_fwd(stats): null stats");
-    if (p->stride == 1) tshift_fwd_kernel<0, true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
-    else tshift_fwd_kernel<0, false><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
+    if (p->stride == 1) tshift_fwd_kernel<0, true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
+    else tshift_fwd_kernel<0, false><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
   } else {
     if (!p->out || !p->scale || !p->shift) return set_error("sgcn_tshift_fwd(apply): null pointer");
-    if (p->stride == 1) tshift_fwd_kernel<1, true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
-    else tshift_fwd_kernel<1, false><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
+    if (p->stride == 1) tshift_fwd_kernel<1, true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
+    else tshift_fwd_kernel<1, false><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
   }
   return check_launch("tshift_fwd_kernel");
 }
@@ -602,24 +697,25 @@ extern "C" int sgcn_tshift_bwd(const SgcnTShiftBwd* p, int mode, void* stream) {
   if (int rc = check_cv(p->C, p->V)) return rc;
   if (p->stride < 1 || p->T_out != p->T_in / p->stride) return set_error("sgcn_tshift_bwd: T_out must be T_in / stride");
   if (p->n_samples <= 0) return 0;
+  const int rev = next_direction();
   if (mode == 0) {
     if (!p->sums) return set_error("sgcn_tshift_bwd(stats): null sums");
     if (p->T_out <= 0) return 0;
     const Geo g = geometry(p->C, p->V, p->n_samples, p->T_out, 8);
-    if (p->stride == 1) tshift_bwd_stats_kernel<true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
-    else tshift_bwd_stats_kernel<false><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
+    if (p->stride == 1) tshift_bwd_stats_kernel<true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
+    else tshift_bwd_stats_kernel<false><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
     return check_launch("tshift_bwd_stats_kernel");
   }
   if (!p->dpre || !p->dbias || !p->k1 || !p->m1 || !p->m2) return set_error("sgcn_tshift_bwd(apply): null pointer");
   if (p->stride == 1) {
     const Geo g = geometry(p->C, p->V, p->n_samples, p->T_in, 8);
-    tshift_bwd_apply_s1_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
+    tshift_bwd_apply_s1_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
     return check_launch("tshift_bwd_apply_s1_kernel");
   }
   if (p->stride == 2) {   // the reference's backward exists for strides 1 and 2 only (shift_cuda_kernel.cu:156-256)
     if (p->T_out <= 0) return set_error("sgcn_tshift_bwd(apply): empty output");
     const Geo g = geometry(p->C, p->V, p->n_samples, p->T_out, 8);
-    tshift_bwd_apply_s2_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
+    tshift_bwd_apply_s2_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
     return check_launch("tshift_bwd_apply_s2_kernel");
   }
   return set_error("sgcn_tshift_bwd(apply): stride must be 1 or 2 (as in the reference's backward kernels)");
@@ -629,17 +725,35 @@ extern "C" int sgcn_tshift_in_bwd(const SgcnTShiftInBwd* p, int mode, void* stre
   if (!p || !p->dp || !p->h || !p->ypos_eff || !p->mean || !p->invstd) return set_error("sgcn_tshift_in_bwd: null pointer");
   if (int rc = check_cv(p->C, p->V)) return rc;
   if (p->n_samples <= 0 || p->T <= 0) return 0;
+  const int rev = next_direction();
   if (mode == 0) {
     if (!p->sums || !p->scale || !p->shift) return set_error("sgcn_tshift_in_bwd(stats): null pointer");
     const Geo g = geometry(p->C, p->V, p->n_samples, p->T, 8);
-    tshift_in_bwd_stats_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
+    tshift_in_bwd_stats_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
     return check_launch("tshift_in_bwd_stats_kernel");
   }
   if (!p->gh || !p->k1 || !p->m1 || !p->m2) return set_error("sgcn_tshift_in_bwd(apply): null pointer");
+  if (!p->pos_sums || !p->scale || !p->shift) return set_error("sgcn_tshift_in_bwd(apply): null pos_sums / scale / shift");
   if (p->z && (!p->zmean || !p->zinvstd || !p->vd_sums)) return set_error("sgcn_tshift_in_bwd(apply): null BN1d tables");
   const Geo g = geometry(p->C, p->V, p->n_samples, p->T, 16);
-  tshift_in_bwd_apply_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks);
+  tshift_in_bwd_apply_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
   return check_launch("tshift_in_bwd_apply_kernel");
+}
+
+extern "C" int sgcn_tshift_in_bwd_sums(const SgcnTShiftInSums* p, void* stream) {
+  if (!p || !p->dp || !p->ypos_eff || !p->Wt || !p->dWt || !p->dbt || !p->mean || !p->invstd || !p->scale || !p->shift ||
+      !p->sums || !p->gate)
+    return set_error("sgcn_tshift_in_bwd_sums: null pointer");
+  if (int rc = check_cv(p->C, p->V)) return rc;
+  if (p->n_samples <= 0 || p->T <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  tshift_in_gate_kernel<<<1, 256, 0, s>>>(p->scale, p->invstd, p->gate, p->C);
+  if (int rc = check_launch("tshift_in_gate_kernel")) return rc;
+  const unsigned grid = (unsigned)((p->C / 32) * p->n_samples);
+  tshift_in_boundary_kernel<<<grid, 32 * ceil_div(p->V, 2), 0, s>>>(*p);
+  if (int rc = check_launch("tshift_in_boundary_kernel")) return rc;
+  tshift_in_combine_kernel<<<p->C / 64, 256, 0, s>>>(*p);
+  return check_launch("tshift_in_combine_kernel");
 }
 
 extern "C" int sgcn_channel_stats(const float* x, double* stats, long long rows, int C, void* stream) {
@@ -651,13 +765,13 @@ extern "C" int sgcn_channel_stats(const float* x, double* stats, long long rows,
   const long long groups = rows / V;
   if (groups > 0) {
     const Geo g = geometry(C, V, 1, groups, 8);
-    channel_stats_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(x, stats, groups, g.per, g.nchunks, V, C);
+    channel_stats_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(x, stats, groups, g.per, g.nchunks, V, C, next_direction());
     if (int rc = check_launch("channel_stats_kernel")) return rc;
   }
   const int tail = (int)(rows - groups * V);
   if (tail > 0) {
     channel_stats_kernel<<<C / 32, 32 * ceil_div(tail, 2), 0, (cudaStream_t)stream>>>(x + (size_t)groups * V * C, stats,
-                                                                                     1, 1, 1, tail, C);
+                                                                                     1, 1, 1, tail, C, 0);
     return check_launch("channel_stats_kernel(tail)");
   }
   return 0;
@@ -671,7 +785,7 @@ extern "C" int sgcn_relu_bn1d_bwd_stats(const float* g, const float* h, const fl
   if (groups <= 0) return 0;
   const Geo geo = geometry(C, V, 1, groups, 16);
   relu_bn1d_bwd_stats_kernel<<<geo.grid, geo.threads, 0, (cudaStream_t)stream>>>(g, h, z, zmean, zinvstd, gh, vd_sums,
-                                                                                groups, geo.per, geo.nchunks, V, C);
+                                                                                groups, geo.per, geo.nchunks, V, C, next_direction());
   return check_launch("relu_bn1d_bwd_stats_kernel");
 }
 
@@ -683,6 +797,6 @@ extern "C" int sgcn_relu_mask_grad(const float* g, const float* y, float* out, l
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   relu_mask_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)g, (const float4*)y,
-                                                                           (float4*)out, numel / 4);
+                                                                           (float4*)out, numel / 4, next_direction());
   return check_launch("relu_mask_grad_kernel");
 }

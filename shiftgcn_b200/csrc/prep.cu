@@ -82,6 +82,16 @@ __global__ void tshift_bwd_finalize_kernel(double* __restrict__ sums, const floa
   shift_constraint((float)raw, gx + c, gy + c);
 }
 
+__global__ void shift_pos_finalize_kernel(double* __restrict__ pos, float* __restrict__ gx, float* __restrict__ gy,
+                                          float* __restrict__ raw_out, int C, double n_batch) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double raw = pos[c] / n_batch;
+  pos[c] = 0.0;
+  if (raw_out) raw_out[c] = (float)raw;
+  shift_constraint((float)raw, gx + c, gy + c);
+}
+
 __global__ void bn1d_bwd_finalize_kernel(double* __restrict__ vd, const float* __restrict__ gamma,
                                          const float* __restrict__ mean, const float* __restrict__ invstd,
                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -185,6 +195,14 @@ extern "C" int sgcn_tshift_in_bwd_finalize(double* sums, const float* gamma, con
   tshift_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       sums, gamma, invstd, dgamma, dbeta, k1, m1, m2, grad_xpos, grad_ypos, raw_out, C, count, n_batch, training, 3);
   return check_launch("tshift_in_bwd_finalize_kernel");
+}
+
+extern "C" int sgcn_shift_pos_finalize(double* pos_sums, float* grad_xpos, float* grad_ypos, float* raw_out, int C,
+                                       double n_batch, void* stream) {
+  if (!pos_sums || !grad_xpos || !grad_ypos) return set_error("sgcn_shift_pos_finalize: null pointer");
+  shift_pos_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(pos_sums, grad_xpos, grad_ypos, raw_out, C,
+                                                                              n_batch);
+  return check_launch("shift_pos_finalize_kernel");
 }
 
 extern "C" int sgcn_bn1d_bwd_finalize(double* vd_sums, const float* gamma, const float* mean, const float* invstd,

@@ -66,7 +66,7 @@ struct Cfg {
 };
 
 template <int V, int K, int N>
-__global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowGemm p) {
+__global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowGemm p, const int rev) {
   using C = Cfg<V, K, N>;
   constexpr int G = C::G, KC = C::KC, NCH = C::NCH;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
     const int bt = tid - (kMmaWarp + 1) * 32;
     long long q = 0;
     for (long long ti = 0; ti < my_tiles; ++ti) {
-      const long long tile = blockIdx.x + ti * gridDim.x;
+      const long long tile = rev ? ntiles - 1 - (blockIdx.x + ti * gridDim.x) : blockIdx.x + ti * gridDim.x;
       const long long g0 = tile * G;
       const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
       const size_t row0 = (size_t)g0 * V;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
         for (int c = 0; c < 4; ++c) dm[a][b][c] = 0.f;
 
     for (long long ti = 0; ti < my_tiles; ++ti) {
-      const long long tile = blockIdx.x + ti * gridDim.x;
+      const long long tile = rev ? ntiles - 1 - (blockIdx.x + ti * gridDim.x) : blockIdx.x + ti * gridDim.x;
       const long long g0 = tile * G;
       const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
       const size_t row0 = (size_t)g0 * V;
@@ -335,7 +335,7 @@ static int launch(const SgcnRowGemm& p, cudaStream_t s) {
   if (ntiles == 0) return 0;
   long long grid = num_sms();
   if (grid > ntiles) grid = ntiles;
-  kern<<<(unsigned)grid, kThreads, C::kSmem, s>>>(p);
+  kern<<<(unsigned)grid, kThreads, C::kSmem, s>>>(p, next_direction());
   return check_launch("spatial_bwd_kernel");
 }
 

@@ -106,13 +106,13 @@ __device__ __forceinline__ void reduce_channels(const float (&v)[NV], double* __
 
 // ------------------------------------------------------------------------------------------------ forward
 template <int MODE, int kMaxJ>
-__global__ void __launch_bounds__(832, 1) stem_fwd_kernel(const SgcnStem p, int gper) {
+__global__ void __launch_bounds__(832, 1) stem_fwd_kernel(const SgcnStem p, int gper, int rev) {
   __shared__ float sx[kGS * 40 * 3];
   __shared__ float scratch[16 * 2 * D];
   const Thread<kMaxJ> t = setup<kMaxJ>(p);
   const Lay l = layout(p.V);
   const int V = p.V;
-  const long long g0 = (long long)blockIdx.x * gper;
+  const long long g0 = (long long)(rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * gper;   // snake traversal
   const int ng = (int)((p.groups - g0) < gper ? (p.groups - g0) : gper);
   float sc1[kMaxJ], sh1[kMaxJ], sc2 = 0.f, sh2 = 0.f;
   float sz[kMaxJ], szz[kMaxJ], acc[2] = {0.f, 0.f};
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(832, 1) stem_fwd_kernel(const SgcnStem p, int 
 // One pass over the block's groups PER JOINT the thread owns (the per-joint constants and accumulators of all joints
 // at once do not fit in registers; x is tiny and is simply staged again).
 template <int MODE, int kMaxJ>
-__global__ void __launch_bounds__(832, 1) stem_bwd_kernel(const SgcnStem p, int gper) {
+__global__ void __launch_bounds__(832, 1) stem_bwd_kernel(const SgcnStem p, int gper, int rev) {
   __shared__ float sx[kGS * 40 * 3];
   __shared__ float sdx[kGS * 40 * 3];
   __shared__ float scratch[16 * 8 * D];
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(832, 1) stem_bwd_kernel(const SgcnStem p, int 
   const int V = p.V;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cb = warp / l.nwj, jw = warp - cb * l.nwj, d = cb * 32 + lane;
-  const long long g0 = (long long)blockIdx.x * gper;
+  const long long g0 = (long long)(rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * gper;   // snake traversal
   const int ng = (int)((p.groups - g0) < gper ? (p.groups - g0) : gper);
   float wc[3], wd[3];
 #pragma unroll
@@ -344,14 +344,15 @@ extern "C" int sgcn_stem_fwd(const SgcnStem* p, int mode, void* stream) {
   const stem::Lay l = stem::layout(p->V);
   const int threads = 2 * l.nwj * 32, per = stem::per_block(p->groups);
   const unsigned grid = (unsigned)((p->groups + per - 1) / per);
+  const int rev = next_direction();
   if (mode == 0) {
     if (!p->stats_vd || !p->stats_r) return set_error("sgcn_stem_fwd(stats): null statistics buffer");
-    if (l.jp <= 2) stem::stem_fwd_kernel<0, 2><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per);
-    else stem::stem_fwd_kernel<0, 3><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per);
+    if (l.jp <= 2) stem::stem_fwd_kernel<0, 2><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
+    else stem::stem_fwd_kernel<0, 3><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
   } else {
     if (!p->h || !p->sc1 || !p->sh1 || !p->sc2 || !p->sh2) return set_error("sgcn_stem_fwd(apply): null pointer");
-    if (l.jp <= 2) stem::stem_fwd_kernel<1, 2><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per);
-    else stem::stem_fwd_kernel<1, 3><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per);
+    if (l.jp <= 2) stem::stem_fwd_kernel<1, 2><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
+    else stem::stem_fwd_kernel<1, 3><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
   }
   return check_launch("stem_fwd_kernel");
 }
@@ -363,16 +364,17 @@ extern "C" int sgcn_stem_bwd(const SgcnStem* p, int mode, void* stream) {
   const stem::Lay l = stem::layout(p->V);
   const int threads = 2 * l.nwj * 32, per = stem::per_block(p->groups);
   const unsigned grid = (unsigned)((p->groups + per - 1) / per);
+  const int rev = next_direction();
   if (mode == 0) {
     if (!p->mean1 || !p->invstd1 || !p->mean2 || !p->invstd2 || !p->vd_sums || !p->r_sums)
       return set_error("sgcn_stem_bwd(stats): null pointer");
-    if (l.jp <= 2) stem::stem_bwd_kernel<0, 2><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per);
-    else stem::stem_bwd_kernel<0, 3><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per);
+    if (l.jp <= 2) stem::stem_bwd_kernel<0, 2><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
+    else stem::stem_bwd_kernel<0, 3><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
   } else {
     if (!p->al || !p->be || !p->ga || !p->a2 || !p->b2 || !p->c2 || !p->dw_raw || !p->dmask_raw || !p->dx)
       return set_error("sgcn_stem_bwd(apply): null pointer");
-    if (l.jp <= 2) stem::stem_bwd_kernel<1, 2><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per);
-    else stem::stem_bwd_kernel<1, 3><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per);
+    if (l.jp <= 2) stem::stem_bwd_kernel<1, 2><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
+    else stem::stem_bwd_kernel<1, 3><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
   }
   return check_launch("stem_bwd_kernel");
 }

@@ -84,7 +84,7 @@ __host__ __device__ constexpr int wg_pick_g(int CA, int CB, int V) {   // same r
 }
 
 template <int MODE, int V, int CA, int CB>
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p, const WgGeom geo) {
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p, const WgGeom geo, const int rev) {
   constexpr int G = wg_pick_g(CA, CB, V);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
     const int T = p.T;
 
     for (long long j = grp; j < my_tiles; j += NG) {
-      const long long tile = split + j * nsplit;
+      const long long tile = rev ? ntiles - 1 - (split + j * nsplit) : split + j * nsplit;
       const long long g0 = tile * G;
       const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
       const long long use = j / NG;
@@ -472,7 +472,7 @@ static int launch_wgrad_cc(const SgcnWgrad& p, cudaStream_t s) {
   if (ntiles == 0) return 0;
   long long grid = num_sms();
   if (grid > ntiles) grid = ntiles;
-  kern<<<(unsigned)grid, kWgThreads, smem, s>>>(p, geo);
+  kern<<<(unsigned)grid, kWgThreads, smem, s>>>(p, geo, next_direction());
   return check_launch("wgrad_kernel");
 }
 

@@ -15,8 +15,8 @@ Kernel schedule of one identity unit in training (a = one activation tensor pass
             dpre = [q>0] * Shift^T(BN-bwd)                    4a      sgcn_tshift_bwd  mode 1
             dp = dpre * W_t                                   2a      sgcn_rowgemm  PLAIN / LINEAR
             dW_t                                              2a      sgcn_wgrad  TEMPORAL
-            sums for bn / ypos_in                             2a      sgcn_tshift_in_bwd  mode 0
-            gh = [h>0] * BN-bwd(Shift^T dp), BN1d sums        4a      sgcn_tshift_in_bwd  mode 1
+            sums for bn (from dW_t, dbt: no tensor pass)      ~0      sgcn_tshift_in_bwd_sums
+            gh = [h>0] * BN-bwd(Shift^T dp), BN1d + ypos_in   4a      sgcn_tshift_in_bwd  mode 1
             g_x = spatial backward-data (+ both residuals)    6a      sgcn_rowgemm  DY / SPATIAL_BWD
             dW                                                3a      sgcn_wgrad  SPATIAL
 """
@@ -47,6 +47,14 @@ class Workspace:
         buf = self._bufs.get(key)
         if buf is None:
             buf = torch.zeros(numel, device=device, dtype=torch.float64)
+            self._bufs[key] = buf
+        return buf
+
+    def get_int(self, name, numel, device):
+        key = (name, numel, str(device), "i32")
+        buf = self._bufs.get(key)
+        if buf is None:
+            buf = torch.zeros(numel, device=device, dtype=torch.int32)
             self._bufs[key] = buf
         return buf
 
@@ -334,24 +342,33 @@ def temporal_backward(saved, gy, gamma_a, Wt, gamma_b, ws, spatial_saved=None, s
     dWt = torch.zeros((C, C), device=dev, dtype=torch.float32)
     ops.wgrad(ops.WG_TEMPORAL, a_src=dpre, b_src=h, b_tab0=saved["scale_a"], b_tab1=saved["shift_a"],
               b_tab2=saved["ypos_in_eff"], dw=dWt, groups=n * T, V=V, CA=C, CB=C, T=T)
+    # BN(h) backward sums without a pass over dp and h: sum du = W_t^T dbt - boundary frames, sum du*U = colsum(W_t * dW_t)
+    # (include/shiftgcn_b200.h:SgcnTShiftInSums); the gated statistics pass only runs for a degenerate BatchNorm weight
     sums3 = ws.get("tshift_in_bwd", 3 * C, dev)
+    gate = ws.get_int("tshift_in_gate", 1, dev)
     common_in = dict(dp=dp, h=h, ypos_eff=saved["ypos_in_eff"], mean=saved["mean_a"], invstd=saved["invstd_a"],
-                     n_samples=n, T=T, V=V, C=C)
-    ops.tshift_in_bwd(0, scale=saved["scale_a"], shift=saved["shift_a"], sums=sums3, **common_in)
-    fa = ops.tshift_bwd_finalize(sums3, gamma_a, saved["invstd_a"], C, n * T * V, n, training, input_shift=True,
-                                 want_raw=want_raw)
+                     scale=saved["scale_a"], shift=saved["shift_a"], n_samples=n, T=T, V=V, C=C)
+    ops.tshift_in_bwd_sums(dp=dp, ypos_eff=saved["ypos_in_eff"], Wt=Wt.contiguous(), dWt=dWt, dbt=dbt,
+                           mean=saved["mean_a"], invstd=saved["invstd_a"], scale=saved["scale_a"], shift=saved["shift_a"],
+                           sums=sums3, gate=gate, n_samples=n, T=T, V=V, C=C)
+    ops.tshift_in_bwd(0, sums=sums3, gate=gate, **common_in)
+    fa = ops.tshift_bwd_finalize(sums3, gamma_a, saved["invstd_a"], C, n * T * V, n, training, input_shift=True)
     gh = torch.empty((n, T, V, C), device=dev, dtype=torch.float32)
+    pos = ws.get("tshift_in_pos", C, dev)
     if spatial_saved is not None:
         vd = spatial_ws.get("bn1d_bwd", 2 * V * C, dev)
         ops.tshift_in_bwd(1, k1=fa["k1"], m1=fa["m1"], m2=fa["m2"], gh=gh, relu_h=1, z=spatial_saved["z"],
-                          zmean=spatial_saved["mean"], zinvstd=spatial_saved["invstd"], vd_sums=vd, **common_in)
+                          zmean=spatial_saved["mean"], zinvstd=spatial_saved["invstd"], vd_sums=vd, pos_sums=pos,
+                          **common_in)
     else:
-        ops.tshift_in_bwd(1, k1=fa["k1"], m1=fa["m1"], m2=fa["m2"], gh=gh, relu_h=1 if relu_h else 0, **common_in)
+        ops.tshift_in_bwd(1, k1=fa["k1"], m1=fa["m1"], m2=fa["m2"], gh=gh, relu_h=1 if relu_h else 0, pos_sums=pos,
+                          **common_in)
+    gx_in, gy_in, raw_in = ops.shift_pos_finalize(pos, C, n, want_raw=want_raw)    # K4 sums of the apply pass -> K5
     out = dict(gh=gh, dWt=dWt.reshape(C, C, 1, 1), dbt=dbt, dgamma_a=fa["dgamma"], dbeta_a=fa["dbeta"],
-               dgamma_b=fb["dgamma"], dbeta_b=fb["dbeta"], gx_in=fa["gx"], gy_in=fa["gy"], gx_out=fb["gx"],
+               dgamma_b=fb["dgamma"], dbeta_b=fb["dbeta"], gx_in=gx_in, gy_in=gy_in, gx_out=fb["gx"],
                gy_out=fb["gy"])
     if want_raw:
-        out["raw_in"], out["raw_out"] = fa["raw"], fb["raw"]
+        out["raw_in"], out["raw_out"] = raw_in, fb["raw"]
     return out
 
 

@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import SgcnRowGemm, SgcnStem, SgcnTShift, SgcnTShiftBwd, SgcnTShiftInBwd, SgcnWgrad
+from ._lib import SgcnRowGemm, SgcnStem, SgcnTShift, SgcnTShiftBwd, SgcnTShiftInBwd, SgcnTShiftInSums, SgcnWgrad
 
 PRO_SPATIAL, PRO_LERP, PRO_PLAIN, PRO_DY = 0, 1, 2, 3
 EPI_ROT_RAW, EPI_ROT_FUSED, EPI_LINEAR, EPI_SPATIAL_BWD = 0, 1, 2, 3
@@ -66,6 +66,12 @@ def _d(t, name="buffer"):
 
 def device_check():
     _lib.check(_lib.load().sgcn_device_check(), "device check")
+
+
+def set_traversal(snake):
+    """Snake traversal (include/shiftgcn_b200.h:sgcn_set_traversal): consecutive kernels walk their tiles in opposite
+    orders so that each starts on what is still in L2.  Returns the previous setting."""
+    return bool(_lib.load().sgcn_set_traversal(1 if snake else 0))
 
 
 def groups_per_tile(V):
@@ -296,14 +302,35 @@ def tshift_bwd(mode, *, q, gy, ypos_eff, mean, invstd, n_samples, T_in, T_out, V
 
 
 def tshift_in_bwd(mode, *, dp, h, ypos_eff, mean, invstd, n_samples, T, V, C, scale=None, shift=None, k1=None, m1=None,
-                  m2=None, z=None, zmean=None, zinvstd=None, sums=None, vd_sums=None, gh=None, relu_h=0):
+                  m2=None, z=None, zmean=None, zinvstd=None, sums=None, vd_sums=None, gh=None, relu_h=0, pos_sums=None,
+                  gate=None):
     lib = _lib.load()
     p = SgcnTShiftInBwd(dp=_p(dp), h=_p(h), z=_p(z), ypos_eff=_p(ypos_eff), mean=_p(mean), invstd=_p(invstd),
                         scale=_p(scale), shift=_p(shift), k1=_p(k1), m1=_p(m1), m2=_p(m2), zmean=_p(zmean),
-                        zinvstd=_p(zinvstd), sums=_d(sums), vd_sums=_d(vd_sums), gh=_p(gh), n_samples=int(n_samples),
-                        T=T, V=V, C=C, relu_h=int(relu_h))
-    _launch("tshift_in_bwd[%s]" % ("stats", "apply")[mode], 1, _nbytes(dp, h, z, gh), lib.sgcn_tshift_in_bwd,
-            ctypes.byref(p), mode, _stream())
+                        zinvstd=_p(zinvstd), sums=_d(sums), vd_sums=_d(vd_sums), gh=_p(gh), pos_sums=_d(pos_sums),
+                        gate=_p(gate, torch.int32, "gate"), n_samples=int(n_samples), T=T, V=V, C=C, relu_h=int(relu_h))
+    # a gated statistics pass normally returns at once (its sums came from tshift_in_bwd_sums): no algorithmic bytes
+    _launch("tshift_in_bwd[%s]" % ("stats", "apply")[mode] + ("(gated)" if gate is not None else ""), 1,
+            0 if gate is not None else _nbytes(dp, h, z, gh), lib.sgcn_tshift_in_bwd, ctypes.byref(p), mode, _stream())
+
+
+def tshift_in_bwd_sums(*, dp, ypos_eff, Wt, dWt, dbt, mean, invstd, scale, shift, sums, gate, n_samples, T, V, C):
+    """BN(h) backward sums from dW_t and the conv-bias gradient (include/shiftgcn_b200.h:SgcnTShiftInSums)."""
+    lib = _lib.load()
+    p = SgcnTShiftInSums(dp=_p(dp), ypos_eff=_p(ypos_eff), Wt=_p(Wt, name="Wt"), dWt=_p(dWt, name="dWt"), dbt=_p(dbt),
+                         mean=_p(mean), invstd=_p(invstd), scale=_p(scale), shift=_p(shift), sums=_d(sums),
+                         gate=_p(gate, torch.int32, "gate"), n_samples=int(n_samples), T=T, V=V, C=C)
+    _launch("tshift_in_bwd[sums]", 3, 0, lib.sgcn_tshift_in_bwd_sums, ctypes.byref(p), _stream())
+
+
+def shift_pos_finalize(pos_sums, C, n_batch, want_raw=False):
+    """K5 on the reduced position-gradient sums -> (grad_xpos, grad_ypos, raw means or None)"""
+    _count()
+    lib = _lib.load()
+    out = torch.empty(3, C, device=pos_sums.device, dtype=torch.float32)
+    _lib.check(lib.sgcn_shift_pos_finalize(_d(pos_sums), _p(out[0]), _p(out[1]), _p(out[2]) if want_raw else None, C,
+                                           float(n_batch), _stream()), "shift position finalize")
+    return out[0], out[1], (out[2] if want_raw else None)
 
 
 def channel_stats(x, stats, rows, C):

@@ -122,6 +122,25 @@ def test_shift_tcn(cuda_device, C, V, n, T, stride, train):
 
 
 @pytest.mark.parametrize("train", [True, False])
+def test_shift_tcn_degenerate_bn_weight(cuda_device, train):
+    """a zero / tiny weight of Shift_tcn.bn makes the algebraic BatchNorm-backward sums (division by gamma)
+    ill-conditioned: the device-side gate must route the step through the exact statistics pass"""
+    from shiftgcn_b200.modules import Shift_tcn
+    torch.manual_seed(1)
+    mod = Shift_tcn(64, 64, stride=1)
+    ref = model_ref.RefShiftTcn(64, 64, stride=1)
+    fill_pair(mod, ref)
+    with torch.no_grad():
+        for m in (mod, ref):
+            m.bn.weight[5] = 0.0
+            m.bn.weight[9] = 1e-6
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(2, 64, 21, 25, generator=g)
+    go = torch.randn(2, 64, 21, 25, generator=g)
+    _compare(mod, ref, x, go, train, cuda_device)
+
+
+@pytest.mark.parametrize("train", [True, False])
 @pytest.mark.parametrize("C,D,V,n,T,stride,residual", [
     (64, 64, 25, 2, 12, 1, True),        # identity unit -> UnitFn (fully fused)
     (128, 128, 33, 1, 9, 1, True),
