@@ -56,6 +56,18 @@ int sgcn_shift_bwd_nchw_f64(const double* grad_out, const double* in, const doub
                             double* grad_in, double* grad_xpos, double* grad_ypos, double* raw_pos, double* scratch,
                             long long n, int c, int h, int w, int stride, void* stream);
 
+/* ---------------------------------------------------------------- input streams of the ensemble ---------- */
+/* Bone / motion / bone-motion streams derived from the joint batch on the device.  Replaces the numpy loops of
+ * inference_pipeline.py:284-309 (derive_modalities), data_gen/gen_bone_data.py:44-58 and
+ * data_gen/gen_motion_data.py:18-34 (bit-identical fp32 results):
+ *   joint [N, C, T, V, M];  parent: int[V] (0-based parent joint, parent[v] == v for the root) or NULL = no bone step;
+ *   motion != 0: out(t) = s(t+1) - s(t), last frame 0.
+ * rows == 0: out keeps the [N, C, T, V, M] layout.  rows != 0: out is the channels-last row tensor [(N*M), T, V, C]
+ * the units consume, and scale / shift (both [M*V*C], feature (m, v, c), or both NULL) apply the model's input
+ * BatchNorm in inference form (model/shift_gcn.py:193-198): out = value * scale + shift. */
+int sgcn_input_stream(const float* joint, float* out, const int* parent, const float* scale, const float* shift,
+                      long long N, int C, int T, int V, int M, int motion, int rows, void* stream);
+
 /* ---------------------------------------------------------------- first spatial unit (3 input channels) -- */
 /* l1.gcn1 = Shift_gcn(3, 64) (model/shift_gcn.py:178, 121-142) including its `down` branch (1x1 conv + BatchNorm2d,
  * :82-86).  z and the conv output are recomputed from x wherever needed; only h, g cross HBM at full size.
@@ -115,7 +127,7 @@ typedef struct SgcnRowGemm {
   const float* epi_b;  /* ROT_FUSED: BN shift [V,N]                                                        */
   const float* res;    /* ROT_FUSED: residual rows [rows,N] | SPATIAL_BWD: gradient added as-is (or NULL)  */
   const float* res2;   /* SPATIAL_BWD: block-residual gradient g_y (or NULL)                               */
-  const float* res2m;  /* SPATIAL_BWD: block output y; g_y counts where y > 0                              */
+  const float* res2m;  /* SPATIAL_BWD: block output y; g_y counts where y > 0 (NULL: g_y is already masked)    */
   const float* xin;    /* SPATIAL_BWD: unit input x (for the mask gradient)                                */
   double* stats;       /* ROT_RAW: per-(v,n) {sum, sum of squares}, accumulated                            */
   double* red0;        /* SPATIAL_BWD: raw mask gradient [V,N], accumulated                                */
@@ -125,7 +137,8 @@ typedef struct SgcnRowGemm {
   int T;               /* frames per sample (LERP bounds)                                                  */
   int K;               /* contraction width = input channels (64/128/256)                                  */
   int N;               /* output channels (64/128/256)                                                     */
-  int relu;            /* ROT_FUSED / LINEAR: apply ReLU                                                   */
+  int relu;            /* ROT_FUSED / LINEAR: apply ReLU | SPATIAL_BWD: out *= [xin > 0] (pre-masked gradient
+                          for the unit whose ReLU produced xin)                                           */
   /* PLAIN x LINEAR only (conv + BatchNorm side branches, model/shift_gcn.py:82-86, 31-45); all 0 = plain dense GEMM   */
   int k0;              /* > 0: the first k0 input channels come from in0 [rows, k0], the other K-k0 from in1      */
   int in0_gs, in1_gs;  /* frame stride of the input rows: group g reads group g*gs (strided 1x1 convolution)       */

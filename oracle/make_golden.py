@@ -16,7 +16,7 @@ import os
 import numpy as np
 import torch
 
-from . import model_ref, ref_import, shift_c, shift_torch
+from . import modalities, model_ref, ref_import, shift_c, shift_torch
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -133,6 +133,37 @@ def main():
         for k, v in dict(x=x, go=go, xpos=xpos, ypos=ypos, out=out, gin=gin, raw_y=ry, gy=gy).items():
             rec[f"s{stride}/{k}"] = v
     np.savez_compressed(os.path.join(OUT, "shift_op.npz"), **rec)
+    # ---- 7. ensemble streams: the reference's own derive_modalities (inference_pipeline.py:284-309, executed from its
+    #         source) on MediaPipe windows; for NTU the reference only has file-rewriting scripts, so its pair table
+    #         (gen_bone_data.py:5-31) is read from the source and applied with the statements of :52-58 / :30-34
+    ref_derive, ref_pairs, ref_paris = modalities.reference_objects()
+    assert tuple(map(tuple, ref_pairs)) == modalities.MEDIAPIPE_PAIRS
+    assert all(tuple(v) == modalities.NTU_PAIRS for v in ref_paris.values())
+    rng = np.random.default_rng(7)
+    rec = {}
+    jm = rng.standard_normal((3, 3, 9, 33, 1)).astype(np.float32)          # three windows (C, T, V, M)
+    rec["mp/joint"] = jm
+    per_window = [ref_derive(w) for w in jm]
+    for name in modalities.MODALITIES[1:]:
+        rec["mp/" + name] = np.stack([d[name] for d in per_window])
+    jn = rng.standard_normal((2, 3, 7, 25, 2)).astype(np.float32)
+    bone = jn.copy()
+    for v1, v2 in ref_paris["ntu/xview"]:
+        v1 -= 1
+        v2 -= 1
+        bone[:, :, :, v1, :] = jn[:, :, :, v1, :] - jn[:, :, :, v2, :]
+
+    def _motion(data):
+        out = np.zeros_like(data)
+        T = data.shape[2]
+        for t in range(T - 1):
+            out[:, :, t, :, :] = data[:, :, t + 1, :, :] - data[:, :, t, :, :]
+        out[:, :, T - 1, :, :] = 0
+        return out
+
+    rec["ntu/joint"], rec["ntu/bone"] = jn, bone
+    rec["ntu/joint_motion"], rec["ntu/bone_motion"] = _motion(jn), _motion(bone)
+    np.savez_compressed(os.path.join(OUT, "modalities.npz"), **rec)
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} files, {total / 1e6:.2f} MB -> {OUT}")
 

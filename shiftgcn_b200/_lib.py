@@ -65,6 +65,7 @@ SIGNATURES = {
     "sgcn_shift_fwd_nchw_f64": [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
     "sgcn_shift_bwd_nchw_f32": [_vp] * 9 + [_ll, _i, _i, _i, _i, _vp],
     "sgcn_shift_bwd_nchw_f64": [_vp] * 9 + [_ll, _i, _i, _i, _i, _vp],
+    "sgcn_input_stream": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp],
     "sgcn_stem_fwd": [ctypes.POINTER(SgcnStem), _i, _vp],
     "sgcn_stem_bwd": [ctypes.POINTER(SgcnStem), _i, _vp],
     "sgcn_rowgemm": [ctypes.POINTER(SgcnRowGemm), _i, _i, _vp],

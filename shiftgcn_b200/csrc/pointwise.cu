@@ -88,6 +88,22 @@ __device__ __forceinline__ float tap(const float* __restrict__ base, int tt, int
   return inside(tt, T) ? v : 0.f;
 }
 
+// U consecutive frames [t, t+U) of a column, zero padded outside [0, T).  Fast path (all U frames inside): one base
+// address and U loads at compile-time offsets u*PITCH (PITCH = V*C floats, 0 = run-time pitch) -- no clamping, no
+// per-load address arithmetic; this took the walkers from ~21 to ~8 issued instructions per 128-byte line.  The branch
+// is per thread (the shift differs per channel) but both sides fill the same registers with independent loads.
+template <int U, int PITCH>
+__device__ __forceinline__ void load_frames(float (&d)[U], const float* __restrict__ base, int t, int T, int pitch) {
+  if (t >= 0 && t + U <= T) {
+    const float* __restrict__ q = base + (size_t)t * (size_t)(PITCH ? PITCH : pitch);
+#pragma unroll
+    for (int u = 0; u < U; ++u) d[u] = __ldg(q + (size_t)u * (size_t)(PITCH ? PITCH : pitch));
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; ++u) d[u] = tap(base, t + u, T, pitch);
+  }
+}
+
 struct LerpCh {
   int y1;
   float f, g;    // weights of tap y1+1 and of tap y1  (g = 1 - f)
@@ -103,6 +119,7 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 // ------------------------------------------------------------------------------------------------
 // h = relu(z * sc[v,d] + sh[v,d] + res)          stats_out[d] += {sum h, sum h^2}
 // walks row GROUPS (frames of any sample): groups [g0, g1) of the chunk
+template <int PITCH>
 __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) bn_res_relu_fwd_kernel(const float* __restrict__ z,
                                                                          const float* __restrict__ res,
                                                                          float* __restrict__ h,
@@ -126,12 +143,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) bn_res_
     float* hp = h + o0;
     for (int g = 0; g < ng; g += kUnroll) {
       float zv[kUnroll], rv[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int gg = min(g + u, ng - 1);                 // tail iterations re-read the last row (results unused)
-        zv[u] = __ldg(zp + (size_t)gg * pitch);
-        rv[u] = __ldg(rp + (size_t)gg * pitch);
-      }
+      load_frames<kUnroll, PITCH>(zv, zp, g, ng, pitch);
+      load_frames<kUnroll, PITCH>(rv, rp, g, ng, pitch);
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u)
         if (g + u < ng) {
@@ -149,7 +162,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) bn_res_
 // ------------------------------------------------------------------------------------------------ temporal shift, forward
 // s(to) = g * Q(to*stride + y1) + f * Q(to*stride + y1 + 1), Q zero padded           (K1 with xpos = 0)
 // MODE 0: stats[c] += {sum s, sum s^2};  MODE 1: out = [relu](s*sc + sh + res)
-template <int MODE, bool S1>
+template <int MODE, bool S1, int PITCH>
 __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_fwd_kernel(const SgcnTShift p, int tper, int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32 * 2];
   const Col k = col_of(p.C, nchunks, rev);
@@ -163,18 +176,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
   for (int v = k.warp; v < V; v += k.nw) {
     const float* qb = p.q + ((size_t)k.n * Ti * V + v) * C + k.c;
     const size_t ob = ((size_t)k.n * To * V + v) * C + k.c;
-    const float* resb = (MODE == 1 && p.res) ? p.res + ob : qb;   // no residual: any valid address, value ignored
     float qa = S1 ? tap(qb, to0 + L.y1, Ti, pitch) : 0.f;
     for (int to = to0; to < to1; to += U) {
       float q0[S1 ? 1 : U], q1[U], rv[MODE == 1 ? U : 1];
+      if (S1) {
+        load_frames<U, PITCH>(q1, qb, to + L.y1 + 1, Ti, pitch);
+      } else {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int tc = min(to + u, to1 - 1);
-        const int ta = tc * st + L.y1;
-        q1[u] = tap(qb, ta + 1, Ti, pitch);
-        if (!S1) q0[u] = tap(qb, ta, Ti, pitch);
-        if (MODE == 1) rv[u] = __ldg(resb + (size_t)tc * pitch);
+        for (int u = 0; u < U; ++u) {
+          const int ta = min(to + u, to1 - 1) * st + L.y1;
+          q1[u] = tap(qb, ta + 1, Ti, pitch);
+          q0[u] = tap(qb, ta, Ti, pitch);
+        }
       }
+      if (MODE == 1) load_frames<(MODE == 1 ? U : 1), PITCH>(rv, MODE == 1 && p.res ? p.res + ob : qb, to, MODE == 1 && p.res ? To : Ti, pitch);
 #pragma unroll
       for (int u = 0; u < U; ++u)
         if (to + u < to1) {
@@ -199,7 +214,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
 // ------------------------------------------------------------------------------------------------ output shift + BN, backward
 // sums5[c] += { g, g*shat, g*dq, dq, shat*dq }   with g = gy*[y>0] (if relu), s = Shift(q), shat = (s-mean)*invstd,
 // dq = Q(ta+1) - Q(ta)  (d s / d ypos, K4 with xpos = 0)
-template <bool S1>
+template <bool S1, int PITCH>
 __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_bwd_stats_kernel(const SgcnTShiftBwd p, int tper, int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32 * 5];
   const Col k = col_of(p.C, nchunks, rev);
@@ -215,15 +230,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
     float qa = S1 ? tap(qb, to0 + L.y1, Ti, pitch) : 0.f;
     for (int to = to0; to < to1; to += kUnrollWide) {
       float q0[S1 ? 1 : kUnrollWide], q1[kUnrollWide], gv[kUnrollWide], yv[kUnrollWide];
+      if (S1) {
+        load_frames<kUnrollWide, PITCH>(q1, qb, to + L.y1 + 1, Ti, pitch);
+      } else {
 #pragma unroll
-      for (int u = 0; u < kUnrollWide; ++u) {
-        const int tc = min(to + u, to1 - 1);
-        const int ta = tc * st + L.y1;
-        q1[u] = tap(qb, ta + 1, Ti, pitch);
-        if (!S1) q0[u] = tap(qb, ta, Ti, pitch);
-        gv[u] = __ldg(p.gy + ob + (size_t)tc * pitch);
-        yv[u] = __ldg(yb + (size_t)tc * pitch);
+        for (int u = 0; u < kUnrollWide; ++u) {
+          const int ta = min(to + u, to1 - 1) * st + L.y1;
+          q1[u] = tap(qb, ta + 1, Ti, pitch);
+          q0[u] = tap(qb, ta, Ti, pitch);
+        }
       }
+      load_frames<kUnrollWide, PITCH>(gv, p.gy + ob, to, To, pitch);
+      load_frames<kUnrollWide, PITCH>(yv, yb, to, To, pitch);
 #pragma unroll
       for (int u = 0; u < kUnrollWide; ++u)
         if (to + u < to1) {
@@ -268,6 +286,7 @@ __device__ __forceinline__ float ds_eval(bool valid, float g, float y, int relu,
 
 // stride 1:  dpre(t) = [Q(t) > 0] * ( g*ds(t-y1) + f*ds(t-y1-1) ),  ds(to) uses s(to) = g*Q(to+y1) + f*Q(to+y1+1)
 // walk over input frames t; to = t - y1; the previous ds and the tap Q(t+1) slide along in registers
+template <int PITCH>
 __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_bwd_apply_s1_kernel(const SgcnTShiftBwd p, int tper,
                                                                             int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32];
@@ -295,14 +314,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
     }
     for (int t = t0; t < t1; t += kUnroll) {
       float q1[kUnroll], gv[kUnroll], yv[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int tc = min(t + u, t1 - 1);
-        const int to = tc - L.y1;
-        q1[u] = tap(qb, tc + 1, T, pitch);
-        gv[u] = ldrow(gb, to, T, pitch);
-        yv[u] = ldrow(yb, to, T, pitch);
-      }
+      load_frames<kUnroll, PITCH>(q1, qb, t + 1, T, pitch);
+      load_frames<kUnroll, PITCH>(gv, gb, t - L.y1, T, pitch);      // frames outside [0, T) are masked by ds_eval
+      load_frames<kUnroll, PITCH>(yv, yb, t - L.y1, T, pitch);
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u)
         if (t + u < t1) {
@@ -422,6 +436,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
 
 // gh(t) = [h(t) > 0] * k*(du(t) - m1 - hhat(t)*m2),  du(t) = g*dp(t-y1) + f*dp(t-y1-1);
 // per-(v,c) sums for the BN1d backward of the spatial unit: { gh, gh * zhat }
+template <int PITCH>
 __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_in_bwd_apply_kernel(const SgcnTShiftInBwd p, int tper,
                                                                             int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32];
@@ -457,13 +472,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
     float ah = 0.f;
     for (int t = t0; t < t1; t += kUnroll) {
       float d0[kUnroll], hv[kUnroll], zv[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int tc = min(t + u, t1 - 1);
-        d0[u] = tap(dpb, tc - L.y1, T, pitch);
-        hv[u] = __ldg(hb + (size_t)tc * pitch);
-        zv[u] = __ldg(zb + (size_t)tc * pitch);
-      }
+      load_frames<kUnroll, PITCH>(d0, dpb, t - L.y1, T, pitch);
+      load_frames<kUnroll, PITCH>(hv, hb, t, T, pitch);
+      load_frames<kUnroll, PITCH>(zv, zb, t, T, pitch);
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u)
         if (t + u < t1) {
@@ -549,6 +560,7 @@ __global__ void __launch_bounds__(256) tshift_in_combine_kernel(const SgcnTShift
 
 // ------------------------------------------------------------------------------------------------ group walkers
 // stats[c] += { sum x, sum x^2 }   (BatchNorm2d statistics of a stand-alone Shift_tcn input, model/shift_gcn.py:66)
+template <int PITCH>
 __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) channel_stats_kernel(const float* __restrict__ x,
                                                                        double* __restrict__ stats, long long groups,
                                                                        int gper, int nchunks, int V, int C, int rev) {
@@ -562,11 +574,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) channel
     const float* xp = x + ((size_t)g0 * V + v) * C + k.c;
     for (int g = 0; g < ng; g += kUnrollMax) {
       float xv[kUnrollMax];
-#pragma unroll
-      for (int u = 0; u < kUnrollMax; ++u) {
-        const float val = __ldg(xp + (size_t)min(g + u, ng - 1) * pitch);
-        xv[u] = (g + u < ng) ? val : 0.f;
-      }
+      load_frames<kUnrollMax, PITCH>(xv, xp, g, ng, pitch);        // zero padded past the chunk
 #pragma unroll
       for (int u = 0; u < kUnrollMax; ++u) {
         acc[0] += xv[u];
@@ -649,6 +657,24 @@ static Geo geometry(int C, int V, long long outer, long long len, int min_per) {
   return g;
 }
 
+// compile-time frame pitch (V*C floats) for the shapes of the reference's two skeletons (25 / 33 joints) and of the
+// pseudo-groups of sgcn_channel_stats (32 rows); anything else takes the run-time pitch
+#define SGCN_PITCH_CASE(N, ...) \
+  case N: {                     \
+    constexpr int P = N;        \
+    __VA_ARGS__;                \
+  } break;
+#define SGCN_PITCH_DISPATCH(pitch, ...)                                                             \
+  switch (pitch) {                                                                                  \
+    SGCN_PITCH_CASE(1600, __VA_ARGS__) SGCN_PITCH_CASE(3200, __VA_ARGS__) SGCN_PITCH_CASE(6400, __VA_ARGS__) \
+    SGCN_PITCH_CASE(2112, __VA_ARGS__) SGCN_PITCH_CASE(4224, __VA_ARGS__) SGCN_PITCH_CASE(8448, __VA_ARGS__) \
+    SGCN_PITCH_CASE(2048, __VA_ARGS__) SGCN_PITCH_CASE(4096, __VA_ARGS__) SGCN_PITCH_CASE(8192, __VA_ARGS__) \
+    default: {                                                                                      \
+      constexpr int P = 0;                                                                          \
+      __VA_ARGS__;                                                                                  \
+    }                                                                                               \
+  }
+
 static int check_cv(int C, int V) {
   if (C != 64 && C != 128 && C != 256) return set_error("pointwise: channel count must be 64, 128 or 256");
   if (V < 1 || V > 2 * kMaxWarps) return set_error("pointwise: num_point must be in [1, 40]");
@@ -667,8 +693,9 @@ extern "C" int sgcn_bn_res_relu_fwd(const float* z, const float* res, float* h, 
   if (rows % V != 0) return set_error("sgcn_bn_res_relu_fwd: rows must be a multiple of V");
   const long long groups = rows / V;
   const Geo g = geometry(D, V, 1, groups, 8);
-  bn_res_relu_fwd_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(z, res, h, scale, shift, stats_out, groups,
-                                                                        g.per, g.nchunks, V, D, relu, next_direction());
+  const int rev = next_direction();
+  SGCN_PITCH_DISPATCH(V * D, (bn_res_relu_fwd_kernel<P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(
+                                 z, res, h, scale, shift, stats_out, groups, g.per, g.nchunks, V, D, relu, rev)))
   return check_launch("bn_res_relu_fwd_kernel");
 }
 
@@ -681,12 +708,18 @@ extern "C" int sgcn_tshift_fwd(const SgcnTShift* p, int mode, void* stream) {
   const int rev = next_direction();
   if (mode == 0) {
     if (!p->stats) return set_error("sgcn_tshift_fwd(stats): null stats");
-    if (p->stride == 1) tshift_fwd_kernel<0, true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
-    else tshift_fwd_kernel<0, false><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
+    if (p->stride == 1) {
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_fwd_kernel<0, true, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+    } else {
+      tshift_fwd_kernel<0, false, 0><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
+    }
   } else {
     if (!p->out || !p->scale || !p->shift) return set_error("sgcn_tshift_fwd(apply): null pointer");
-    if (p->stride == 1) tshift_fwd_kernel<1, true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
-    else tshift_fwd_kernel<1, false><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
+    if (p->stride == 1) {
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_fwd_kernel<1, true, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+    } else {
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_fwd_kernel<1, false, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+    }
   }
   return check_launch("tshift_fwd_kernel");
 }
@@ -702,14 +735,17 @@ extern "C" int sgcn_tshift_bwd(const SgcnTShiftBwd* p, int mode, void* stream) {
     if (!p->sums) return set_error("sgcn_tshift_bwd(stats): null sums");
     if (p->T_out <= 0) return 0;
     const Geo g = geometry(p->C, p->V, p->n_samples, p->T_out, 8);
-    if (p->stride == 1) tshift_bwd_stats_kernel<true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
-    else tshift_bwd_stats_kernel<false><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
+    if (p->stride == 1) {
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_stats_kernel<true, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+    } else {
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_stats_kernel<false, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+    }
     return check_launch("tshift_bwd_stats_kernel");
   }
   if (!p->dpre || !p->dbias || !p->k1 || !p->m1 || !p->m2) return set_error("sgcn_tshift_bwd(apply): null pointer");
   if (p->stride == 1) {
     const Geo g = geometry(p->C, p->V, p->n_samples, p->T_in, 8);
-    tshift_bwd_apply_s1_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
+    SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_apply_s1_kernel<P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
     return check_launch("tshift_bwd_apply_s1_kernel");
   }
   if (p->stride == 2) {   // the reference's backward exists for strides 1 and 2 only (shift_cuda_kernel.cu:156-256)
@@ -736,7 +772,7 @@ extern "C" int sgcn_tshift_in_bwd(const SgcnTShiftInBwd* p, int mode, void* stre
   if (!p->pos_sums || !p->scale || !p->shift) return set_error("sgcn_tshift_in_bwd(apply): null pos_sums / scale / shift");
   if (p->z && (!p->zmean || !p->zinvstd || !p->vd_sums)) return set_error("sgcn_tshift_in_bwd(apply): null BN1d tables");
   const Geo g = geometry(p->C, p->V, p->n_samples, p->T, 16);
-  tshift_in_bwd_apply_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
+  SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_in_bwd_apply_kernel<P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
   return check_launch("tshift_in_bwd_apply_kernel");
 }
 
@@ -765,12 +801,13 @@ extern "C" int sgcn_channel_stats(const float* x, double* stats, long long rows,
   const long long groups = rows / V;
   if (groups > 0) {
     const Geo g = geometry(C, V, 1, groups, 8);
-    channel_stats_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(x, stats, groups, g.per, g.nchunks, V, C, next_direction());
+    const int rev = next_direction();
+    SGCN_PITCH_DISPATCH(V * C, (channel_stats_kernel<P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(x, stats, groups, g.per, g.nchunks, V, C, rev)))
     if (int rc = check_launch("channel_stats_kernel")) return rc;
   }
   const int tail = (int)(rows - groups * V);
   if (tail > 0) {
-    channel_stats_kernel<<<C / 32, 32 * ceil_div(tail, 2), 0, (cudaStream_t)stream>>>(x + (size_t)groups * V * C, stats,
+    channel_stats_kernel<0><<<C / 32, 32 * ceil_div(tail, 2), 0, (cudaStream_t)stream>>>(x + (size_t)groups * V * C, stats,
                                                                                      1, 1, 1, tail, C, 0);
     return check_launch("channel_stats_kernel(tail)");
   }

@@ -376,14 +376,15 @@ __global__ void __launch_bounds__(kThreads, rowgemm_min_blocks<EPI, NCH>()) rowg
                   const bool in = g < ng;
                   rv[g] = (res_ && in) ? __ldg(res_ + o) : 0.f;
                   gv[g] = (res2_ && in) ? __ldg(res2_ + o) : 0.f;
-                  yv[g] = (res2_ && in) ? __ldg(res2m_ + o) : 0.f;
+                  yv[g] = (res2_ && in) ? (res2m_ ? __ldg(res2m_ + o) : 1.f) : 0.f;   // no y: g_y is already masked
                   xv[g] = in ? __ldg(xin_ + o) : 0.f;
                 }
                 float dmk = 0.f;
 #pragma unroll
                 for (int g = 0; g < kGMax; ++g)
                   if (g < ng) {
-                    out_[o0 + (size_t)g * V * N] = fmaf(zv[g], mm, rv[g]) + (yv[g] > 0.f ? gv[g] : 0.f);
+                    const float gxv = fmaf(zv[g], mm, rv[g]) + (yv[g] > 0.f ? gv[g] : 0.f);
+                    out_[o0 + (size_t)g * V * N] = (p.relu && !(xv[g] > 0.f)) ? 0.f : gxv;
                     dmk = fmaf(zv[g], xv[g], dmk);
                   }
                 if (kAccSmem) sAcc0[sv * N + d] += dmk;

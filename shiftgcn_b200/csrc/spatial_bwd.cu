@@ -207,7 +207,9 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
     const float rsel = p.res ? 1.f : 0.f, r2sel = p.res2 ? 1.f : 0.f;
     const float* res = p.res ? p.res : p.xin;                      // absent streams alias x (loads stay branch free)
     const float* res2 = p.res2 ? p.res2 : p.xin;
-    const float* res2m = p.res2 ? p.res2m : p.xin;
+    const float* res2m = (p.res2 && p.res2m) ? p.res2m : p.xin;
+    const bool r2all = p.res2 && !p.res2m;                         // g_y arrives with its ReLU mask already applied
+    const bool premask = p.relu != 0;                              // hand gx * [x > 0] to the unit that produced x
     float dm[NCH][C::kEpiRounds][4];
 #pragma unroll
     for (int a = 0; a < NCH; ++a)
@@ -287,10 +289,16 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
 #pragma unroll
                   for (int j = 0; j < 4; ++j) val[j] = *(const float*)(sSt + stage_off((uint32_t)(g * V + u[j]), (uint32_t)c4, (uint32_t)j));
                   float4 out;
-                  out.x = fmaf(val[0], mm[0], fmaf(rsel, rv[i].x, (yv[i].x > 0.f ? r2sel : 0.f) * gy[i].x));
-                  out.y = fmaf(val[1], mm[1], fmaf(rsel, rv[i].y, (yv[i].y > 0.f ? r2sel : 0.f) * gy[i].y));
-                  out.z = fmaf(val[2], mm[2], fmaf(rsel, rv[i].z, (yv[i].z > 0.f ? r2sel : 0.f) * gy[i].z));
-                  out.w = fmaf(val[3], mm[3], fmaf(rsel, rv[i].w, (yv[i].w > 0.f ? r2sel : 0.f) * gy[i].w));
+                  out.x = fmaf(val[0], mm[0], fmaf(rsel, rv[i].x, ((r2all || yv[i].x > 0.f) ? r2sel : 0.f) * gy[i].x));
+                  out.y = fmaf(val[1], mm[1], fmaf(rsel, rv[i].y, ((r2all || yv[i].y > 0.f) ? r2sel : 0.f) * gy[i].y));
+                  out.z = fmaf(val[2], mm[2], fmaf(rsel, rv[i].z, ((r2all || yv[i].z > 0.f) ? r2sel : 0.f) * gy[i].z));
+                  out.w = fmaf(val[3], mm[3], fmaf(rsel, rv[i].w, ((r2all || yv[i].w > 0.f) ? r2sel : 0.f) * gy[i].w));
+                  if (premask) {
+                    out.x = xv[i].x > 0.f ? out.x : 0.f;
+                    out.y = xv[i].y > 0.f ? out.y : 0.f;
+                    out.z = xv[i].z > 0.f ? out.z : 0.f;
+                    out.w = xv[i].w > 0.f ? out.w : 0.f;
+                  }
                   *(float4*)(p.out + o + (size_t)g * V * N) = out;
                   dm[nc][rd][0] = fmaf(val[0], xv[i].x, dm[nc][rd][0]);
                   dm[nc][rd][1] = fmaf(val[1], xv[i].y, dm[nc][rd][1]);

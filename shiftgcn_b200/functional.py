@@ -28,6 +28,7 @@ BN_EPS = 1e-5
 # Function.forward always runs with grad mode off, and needs_input_grad ignores torch.no_grad(): the modules record the
 # caller's grad mode here right before .apply so that inference takes the fully fused (nothing saved) kernels
 GRAD_MODE = True
+PREMASK = True      # chained units hand each other ReLU-masked gradients (see _links); False = every unit masks for itself
 
 
 def _bn_args(bn):
@@ -97,9 +98,11 @@ def spatial_forward(x, res, W, bias, mask, bn, training, ws, fuse_eval, h_stats=
     return h, saved
 
 
-def spatial_backward(saved, gh, W, mask, gamma, vd_sums_ready, ws, unit_res=None, side_fn=None):
+def spatial_backward(saved, gh, W, mask, gamma, vd_sums_ready, ws, unit_res=None, side_fn=None, premask=False):
     """gh: grad wrt the gcn output with the ReLU mask already applied when ``vd_sums_ready`` (fused unit),
-    otherwise the raw incoming gradient.  unit_res = (g_y, y) adds the block's identity-residual gradient.
+    otherwise the raw incoming gradient.  unit_res = (g_y, y) adds the block's identity-residual gradient
+    (y None: g_y already carries its ReLU mask).  premask: return gx * [x > 0] -- for the unit whose ReLU produced x,
+    which would apply that mask itself and can now skip reading its own output (see `_links`).
     side_fn(gh, column sums of gh) -> input gradient of the conv side branches, added inside the kernel.
 
     Returns dict(gx, gres, dW, dbias, dmask, dgamma, dbeta).
@@ -124,7 +127,7 @@ def spatial_backward(saved, gh, W, mask, gamma, vd_sums_ready, ws, unit_res=None
                 pro_a=fin["alpha"], pro_b=fin["beta"], pro_c=fin["gamma"], epi_a=mm,
                 res=gh if identity else side_dx,
                 res2=unit_res[0] if unit_res is not None else None,
-                res2m=unit_res[1] if unit_res is not None else None, xin=x, red0=dmask_raw)
+                res2m=unit_res[1] if unit_res is not None else None, xin=x, red0=dmask_raw, relu=1 if premask else 0)
     dW = torch.zeros((C, D), device=dev, dtype=torch.float32)
     ops.wgrad(ops.WG_SPATIAL, a_src=x, a_tab0=saved["mm_rot"], b_src=gh, b_src2=z, b_tab0=fin["alpha"], b_tab1=fin["beta"],
               b_tab2=fin["gamma"], dw=dW, groups=R, V=V, CA=C, CB=D)
@@ -313,7 +316,7 @@ def temporal_forward(h, res, relu, bn, ypos_in, Wt, bt, ypos_out, bn2, stride, t
 
 
 def temporal_backward(saved, gy, gamma_a, Wt, gamma_b, ws, spatial_saved=None, spatial_ws=None, relu_h=False,
-                      want_raw=False):
+                      want_raw=False, gy_masked=False):
     """Returns dict(gh, dWt, dbt, dgamma_a, dbeta_a, dgamma_b, dbeta_b, gx_in, gy_in, gx_out, gy_out[, raw_in, raw_out]).
 
     With ``spatial_saved`` (fused unit) the last kernel also applies the gcn ReLU mask and accumulates the
@@ -325,7 +328,7 @@ def temporal_backward(saved, gy, gamma_a, Wt, gamma_b, ws, spatial_saved=None, s
     To = T // stride
     dev = h.device
     training = saved["training"]
-    relu = saved["relu"]
+    relu = 1 if (saved["relu"] and not gy_masked) else 0   # a pre-masked g_y needs no look at y (1a less per pass)
     sums5 = ws.get("tshift_bwd", 5 * C, dev)
     common = dict(q=q, gy=gy, y=y if relu else None, relu=relu, ypos_eff=saved["ypos_out_eff"], mean=saved["mean_b"],
                   invstd=saved["invstd_b"], n_samples=n, T_in=T, T_out=To, V=V, C=C, stride=stride)
@@ -400,6 +403,30 @@ def _unstash(ctx):
     for gname, entries in ctx._layout.items():
         out[gname] = None if entries is None else {k: (tensors[v] if kind == "t" else v) for k, (kind, v) in entries.items()}
     return out
+
+
+def _links(ctx, owner, produces_gx=True):
+    """Pre-masked gradients between chained units.  `Model.forward` joins consecutive units with a small dict per
+    boundary (`owner._in_link` / `owner._out_link`, live only during that unit's forward call).  A unit whose input x is
+    the ReLU output y of the previous unit can return gx * [x > 0] at no cost (its spatial backward kernel reads x
+    anyway); it says so by setting link["masked"] when its backward runs, and the previous unit -- whose backward runs
+    next and would multiply the incoming gradient by [y > 0] itself -- then skips reading y in three kernels.  The
+    mask is idempotent, so a producer that does not mask (any non-fused path) leaves the flag unset and nothing
+    changes."""
+    ctx.in_link = getattr(owner, "_in_link", None) if produces_gx else None
+    ctx.out_link = getattr(owner, "_out_link", None)
+
+
+def _premask_now(ctx):
+    """called by the backward of the unit that produces gx: decide and publish whether gx carries the mask"""
+    pm = bool(PREMASK and ctx.in_link is not None)
+    if ctx.in_link is not None:
+        ctx.in_link["masked"] = pm
+    return pm
+
+
+def _gy_masked(ctx):
+    return bool(ctx.out_link is not None and ctx.out_link.get("masked"))
 
 
 class SpatialFn(torch.autograd.Function):
@@ -485,6 +512,7 @@ class TemporalFn(torch.autograd.Function):
                                     ypos_out, module.bn2, module.shift_out.stride, module.training, module._ws, False)
         ctx.module = module
         ctx.has_res = res is not None
+        _links(ctx, module, produces_gx=False)
         _stash(ctx, t=saved, p=dict(ga=ga, Wt=Wt, gb=gb))
         return y
 
@@ -495,13 +523,14 @@ class TemporalFn(torch.autograd.Function):
         Wt = p["Wt"]
         gy = gy.contiguous()
         want_raw = getattr(ctx.module.shift_in, "_export_raw", False)
+        masked = _gy_masked(ctx)
         r = temporal_backward(saved, gy, p["ga"], Wt.reshape(Wt.shape[0], Wt.shape[1]), p["gb"], ctx.module._ws,
-                              want_raw=want_raw)
+                              want_raw=want_raw, gy_masked=masked)
         if want_raw:        # raw (pre-K5) means for the post-all-reduce constraint of dp.FlatSGDTrainer
             ctx.module.shift_in._raw_ypos_grad, ctx.module.shift_out._raw_ypos_grad = r["raw_in"], r["raw_out"]
         gres = None
         if ctx.has_res:
-            gres = ops.relu_mask_grad(gy, saved["y"]) if saved["relu"] else gy
+            gres = ops.relu_mask_grad(gy, saved["y"]) if (saved["relu"] and not masked) else gy
             ctx.module._res_sg = r["dbeta_b"] if saved["relu"] else None   # column sums of gres (conv residual branch)
         return (r["gh"], gres, r["dgamma_a"], r["dbeta_a"], r["gx_in"], r["gy_in"], r["dWt"], r["dbt"], r["gx_out"],
                 r["gy_out"], r["dgamma_b"], r["dbeta_b"], None, None)
@@ -523,6 +552,7 @@ class UnitFn(torch.autograd.Function):
         y, t_saved = temporal_forward(h, x, 1, tcn.bn, ypos_in, Wt.reshape(C, C), bt, ypos_out, tcn.bn2, 1, training,
                                       tcn._ws, h_stats_ready=training)
         ctx.unit = unit
+        _links(ctx, unit)
         if s_saved is not None:
             s_saved["identity_res"] = True
         _stash(ctx, s=s_saved, t=t_saved, p=dict(W=W, mask=mask, g1=g1, ga=ga, Wt=Wt, gb=gb))
@@ -536,12 +566,13 @@ class UnitFn(torch.autograd.Function):
         gy = gy.contiguous()
         C = p["W"].shape[0]
         want_raw = getattr(unit.tcn1.shift_in, "_export_raw", False)
+        masked = _gy_masked(ctx)
         t = temporal_backward(t_saved, gy, p["ga"], p["Wt"].reshape(C, C), p["gb"], unit.tcn1._ws, spatial_saved=s_saved,
-                              spatial_ws=unit.gcn1._ws, want_raw=want_raw)
+                              spatial_ws=unit.gcn1._ws, want_raw=want_raw, gy_masked=masked)
         if want_raw:
             unit.tcn1.shift_in._raw_ypos_grad, unit.tcn1.shift_out._raw_ypos_grad = t["raw_in"], t["raw_out"]
         s = spatial_backward(s_saved, t["gh"], p["W"], p["mask"], p["g1"], True, unit.gcn1._ws,
-                             unit_res=(gy, t_saved["y"]))
+                             unit_res=(gy, None if masked else t_saved["y"]), premask=_premask_now(ctx))
         return (s["gx"], s["dW"], s["dbias"], s["dmask"], s["dgamma"], s["dbeta"], t["dgamma_a"], t["dbeta_a"],
                 t["gx_in"], t["gy_in"], t["dWt"], t["dbt"], t["gx_out"], t["gy_out"], t["dgamma_b"], t["dbeta_b"], None)
 
@@ -568,6 +599,7 @@ class ConvUnitFn(torch.autograd.Function):
         y, t_saved = temporal_forward(h, res_r, 1, tcn.bn, ypos_in, Wt.reshape(D, D), bt, ypos_out, tcn.bn2, stride,
                                       training, tcn._ws, h_stats_ready=training)
         ctx.unit = unit
+        _links(ctx, unit)
         if s_saved is not None:
             s_saved["identity_res"] = False
         _stash(ctx, s=s_saved, t=t_saved, sd=sd_saved, sr=sr_saved,
@@ -584,11 +616,12 @@ class ConvUnitFn(torch.autograd.Function):
         D = p["W"].shape[1]
         stride = t_saved["stride"]
         want_raw = getattr(tcn.shift_in, "_export_raw", False)
+        masked = _gy_masked(ctx)
         t = temporal_backward(t_saved, gy, p["ga"], p["Wt"].reshape(D, D), p["gb"], tcn._ws, spatial_saved=s_saved,
-                              spatial_ws=gcn._ws, want_raw=want_raw)
+                              spatial_ws=gcn._ws, want_raw=want_raw, gy_masked=masked)
         if want_raw:
             tcn.shift_in._raw_ypos_grad, tcn.shift_out._raw_ypos_grad = t["raw_in"], t["raw_out"]
-        gres = ops.relu_mask_grad(gy, t_saved["y"])                      # gradient into the conv residual branch
+        gres = gy if masked else ops.relu_mask_grad(gy, t_saved["y"])   # gradient into the conv residual branch
         rr = side_backward(sr_saved, gres, t["dbeta_b"], p["Wr"], p["br"], p["gr"], tcn._ws)
         rd = {}
 
@@ -601,7 +634,8 @@ class ConvUnitFn(torch.autograd.Function):
                 dx[:, ::stride].add_(rr["dx"])                           # transposed frame stride of the 1x1 conv
             return dx
 
-        s = spatial_backward(s_saved, t["gh"], p["W"], p["mask"], p["g1"], True, gcn._ws, side_fn=side_fn)
+        s = spatial_backward(s_saved, t["gh"], p["W"], p["mask"], p["g1"], True, gcn._ws, side_fn=side_fn,
+                             premask=_premask_now(ctx))
         return (s["gx"], s["dW"], s["dbias"], s["dmask"], s["dgamma"], s["dbeta"], rd["dWd"], rd["dbd"], rd["dgamma"],
                 rd["dbeta"], t["dgamma_a"], t["dbeta_a"], t["gx_in"], t["gy_in"], t["dWt"], t["dbt"], t["gx_out"],
                 t["gy_out"], t["dgamma_b"], t["dbeta_b"], rr["dWd"], rr["dbd"], rr["dgamma"], rr["dbeta"], None)

@@ -268,6 +268,7 @@ class TCN_GCN_unit(nn.Module):
             return from_rows(y)
         h = gcn(x)
         if tcn1.fused_supported(h):
+            tcn1._out_link = getattr(self, "_out_link", None)             # see functional._links
             if self._res_mode == "none":
                 res = None
             elif self._res_mode == "conv" and side_supported(self.residual.conv, x.shape[3]) \
@@ -279,7 +280,10 @@ class TCN_GCN_unit(nn.Module):
                 res = FN.SideBranchFn.apply(xs, conv.weight, conv.bias, bn.weight, bn.bias, bn, tcn1, "_res_sg")
             else:
                 res = to_rows(self.residual(x))
-            return from_rows(tcn1.forward_rows(to_rows(h), res, 1))
+            try:
+                return from_rows(tcn1.forward_rows(to_rows(h), res, 1))
+            finally:
+                tcn1._out_link = None
         return self.relu(tcn1(h) + self.residual(x))
 
 
@@ -315,8 +319,44 @@ class Model(nn.Module):
         if self.training and bn.track_running_stats:
             bn.num_batches_tracked += 1
         x = x.view(N, T, M, V, C).permute(0, 2, 1, 3, 4).reshape(N * M, T, V, C).permute(0, 3, 1, 2)
+        return self._trunk(x, N, M)
+
+    def forward_stream(self, joint, modality="joint", parents=None):
+        """Logits of this model's ensemble stream straight from the JOINT batch (N, C, T, V, M): the bone / motion
+        derivation (inference_pipeline.py:284-309, data_gen/gen_bone_data.py, gen_motion_data.py) runs on the device.
+        In inference it is one kernel together with data_bn and the layout change (sgcn_input_stream); in training
+        (batch statistics) the derived stream goes through ``forward``."""
+        from . import ensemble, ops
+        _require_cuda(joint, "Model.forward_stream")
+        bone, motion = ensemble.stream_flags(modality)
+        bn = self.data_bn
+        if self.training or torch.is_grad_enabled() or not bn.track_running_stats or bn.running_mean is None:
+            return self.forward(ensemble.derive_modality(joint, modality, parents))
+        N, C, T, V, M = joint.shape
+        scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+        shift = bn.bias.detach() - bn.running_mean * scale
+        par = None
+        if bone:
+            par = torch.as_tensor(parents if parents is not None else ensemble.bone_parents(V), dtype=torch.int32,
+                                  device=joint.device)
+        rows = ops.input_stream(joint.contiguous().float(), parent=par, motion=motion, rows=True,
+                                scale=scale.float().contiguous(), shift=shift.float().contiguous())
+        return self._trunk(rows.permute(0, 3, 1, 2), N, M)
+
+    def _trunk(self, x, N, M):
+        """l1..l10, pooling over (T, V) and persons, fc (reference :200-216); x: logical (N*M, C, T, V), channels-last"""
+        # consecutive units exchange ReLU-masked gradients (functional._links): one dict per unit boundary, attached
+        # only for the duration of the unit's forward call so that a unit used on its own never sees a stale link
+        links = [dict(masked=False) for _ in range(9)] if torch.is_grad_enabled() else None
         for i in range(1, 11):
-            x = getattr(self, f"l{i}")(x)
+            unit = getattr(self, f"l{i}")
+            if links is not None:
+                unit._in_link = links[i - 2] if i >= 2 else None
+                unit._out_link = links[i - 1] if i <= 9 else None
+            try:
+                x = unit(x)
+            finally:
+                unit._in_link = unit._out_link = None
         c_new = x.size(1)
         x = x.mean(dim=(2, 3)).view(N, M, c_new).mean(1)      # == view(N, M, C, T*V).mean(3).mean(1), stride-agnostic
         return self.fc(x)

@@ -349,3 +349,24 @@ def relu_mask_grad(g, y):
     out = torch.empty_like(g)
     _launch("relu_mask_grad", 1, _nbytes(g, y, out), lib.sgcn_relu_mask_grad, _p(g), _p(y), _p(out), g.numel(), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ input streams
+def input_stream(joint, parent=None, motion=False, rows=False, scale=None, shift=None):
+    """bone / motion / bone-motion stream of a joint batch (N, C, T, V, M) on the device (sgcn_input_stream).
+
+    parent: int32 CUDA tensor [V] of 0-based parent joints or None; rows=True returns the channels-last row tensor
+    (N*M, T, V, C), optionally with the input BatchNorm folded into scale / shift [M*V*C]."""
+    lib = _lib.load()
+    if joint.dim() != 5:
+        raise RuntimeError("input_stream expects a joint batch of shape (N, C, T, V, M)")
+    N, C, T, V, M = joint.shape
+    if parent is not None and (parent.numel() != V or parent.dtype != torch.int32):
+        raise RuntimeError("parent must be an int32 tensor with one entry per joint")
+    if (scale is None) != (shift is None) or (scale is not None and (not rows or scale.numel() != M * V * C)):
+        raise RuntimeError("scale / shift come together, need rows=True and M*V*C entries each")
+    out = torch.empty((N * M, T, V, C) if rows else (N, C, T, V, M), device=joint.device, dtype=torch.float32)
+    _launch("input_stream", 1, _nbytes(joint, out), lib.sgcn_input_stream, _p(joint, name="joint"), _p(out),
+            _p(parent, torch.int32, "parent"), _p(scale), _p(shift), N, C, T, V, M, 1 if motion else 0, 1 if rows else 0,
+            _stream())
+    return out

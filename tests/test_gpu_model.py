@@ -84,3 +84,38 @@ def test_model_train_step(cuda_device, num_class, V, M):
     assert rel_l2(got, want) < 0.1
     bad = {k: v for k, v in worst.items() if v > 0.3}
     assert not bad, f"gradient mismatch: {sorted(bad.items(), key=lambda kv: -kv[1])[:8]}"
+
+
+@pytest.mark.parametrize("num_class,V,M", [(60, 25, 2), (2, 33, 1)])
+def test_premasked_gradients_between_units_change_nothing(cuda_device, num_class, V, M):
+    """functional._links: a unit that returns gx * [x > 0] to the unit whose ReLU produced x (which then skips reading
+    its own output) must give the same parameter and input gradients as every unit masking for itself.  One forward,
+    two backward passes over the same graph, so the only noise is the order of the fp64 atomics."""
+    from shiftgcn_b200 import functional as FN
+    mod, _ = _build(num_class, V, M, cuda_device)
+    mod.train()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 3, 32, V, M, generator=g).to(cuda_device).requires_grad_(True)
+    label = torch.randint(0, num_class, (4,), generator=g).to(cuda_device)
+    loss = torch.nn.functional.cross_entropy(mod(x), label)
+    for unit in (mod.l1, mod.l5, mod.l10):                       # links are gone after the forward call
+        assert getattr(unit, "_in_link", None) is None and getattr(unit, "_out_link", None) is None
+    params = [p for p in mod.parameters() if p.requires_grad]
+    names = [k for k, p in mod.named_parameters() if p.requires_grad]
+    grads = {}
+    for flag in (False, True):
+        FN.PREMASK = flag
+        try:
+            grads[flag] = torch.autograd.grad(loss, [x] + params, retain_graph=True, allow_unused=True)
+        finally:
+            FN.PREMASK = True
+    for k, a, b in zip(["__input__"] + names, grads[False], grads[True]):
+        assert (a is None) == (b is None), k
+        if a is None or k.endswith("pos"):                       # K5 keeps only the sign of the position sums
+            continue
+        # identical arithmetic; what is left is the order of the fp64 atomics behind the BatchNorm coefficients, whose
+        # last-bit changes flip TF32 operand roundings downstream (~1e-4 after 20 contractions).  A mask applied at
+        # the wrong place, or not at all, shows up as O(0.1 .. 1).
+        scale = max(a.abs().max().item(), 1e-12)
+        assert (a - b).abs().max().item() <= 2e-3 * scale, k
+        assert rel_l2(b, a) < 1e-3, k

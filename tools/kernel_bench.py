@@ -74,6 +74,9 @@ for C in [int(c) for c in args.layers.split(",")]:
     common = dict(q=h, gy=gy, y=h, relu=1, ypos_eff=ypos, mean=mean, invstd=inv, n_samples=n, T_in=T, T_out=T, V=V, C=C, stride=1)
     timeit(lambda: ops.tshift_bwd(0, sums=cstats, **common), 3 * a, "tshift_bwd stats (3a) " + tag)
     timeit(lambda: ops.tshift_bwd(1, k1=k1, m1=m1, m2=m2, dpre=out, dbias=cstats, **common), 4 * a, "tshift_bwd apply (4a) " + tag)
+    pm = dict(common, y=None, relu=0)                     # g_y pre-masked by the next unit (functional._links)
+    timeit(lambda: ops.tshift_bwd(0, sums=cstats, **pm), 2 * a, "tshift_bwd stats, pre-masked g_y (2a) " + tag)
+    timeit(lambda: ops.tshift_bwd(1, k1=k1, m1=m1, m2=m2, dpre=out, dbias=cstats, **pm), 3 * a, "tshift_bwd apply, pre-masked g_y (3a) " + tag)
     timeit(lambda: ops.rowgemm(ops.PRO_PLAIN, ops.EPI_LINEAR, in0=gy, out=out, wimg=wimg, groups=R, V=V, K=C, N=C, relu=0), 2 * a, "rowgemm plain/linear (2a) " + tag)
     timeit(lambda: ops.wgrad(ops.WG_TEMPORAL, a_src=gy, b_src=h, b_tab0=sc, b_tab1=sh, b_tab2=ypos, dw=dW, groups=R, V=V, CA=C, CB=C, T=T), 2 * a, "wgrad temporal (2a) " + tag)
     cin = dict(dp=gy, h=h, ypos_eff=ypos, mean=mean, invstd=inv, n_samples=n, T=T, V=V, C=C)
@@ -81,6 +84,7 @@ for C in [int(c) for c in args.layers.split(",")]:
     pos = torch.zeros(C, device=dev, dtype=torch.float64)
     timeit(lambda: ops.tshift_in_bwd(1, k1=k1, m1=m1, m2=m2, gh=out, relu_h=1, z=z, zmean=A, zinvstd=B_, vd_sums=stats, scale=sc, shift=sh, pos_sums=pos, **cin), 4 * a, "tshift_in_bwd apply (4a) " + tag)
     timeit(lambda: ops.rowgemm(ops.PRO_DY, ops.EPI_SPATIAL_BWD, in0=gy, in1=z, out=out, wimg=wimg, groups=R, V=V, K=C, N=C, pro_a=A, pro_b=B_, pro_c=G_, epi_a=mm, res=gy, res2=gy, res2m=h, xin=x, red0=dmask), 6 * a, "rowgemm dy/spatial_bwd (6a) " + tag)
+    timeit(lambda: ops.rowgemm(ops.PRO_DY, ops.EPI_SPATIAL_BWD, in0=gy, in1=z, out=out, wimg=wimg, groups=R, V=V, K=C, N=C, pro_a=A, pro_b=B_, pro_c=G_, epi_a=mm, res=gy, res2=h, xin=x, red0=dmask, relu=1), 5 * a, "rowgemm dy/spatial_bwd, pre-masked (5a) " + tag)
     timeit(lambda: ops.wgrad(ops.WG_SPATIAL, a_src=x, a_tab0=mm, b_src=gy, b_src2=z, b_tab0=A, b_tab1=B_, b_tab2=G_, dw=dW, groups=R, V=V, CA=C, CB=C), 3 * a, "wgrad spatial (3a) " + tag)
     del x, z, h, gy, out
     torch.cuda.empty_cache()
