@@ -164,6 +164,7 @@ typedef struct SgcnWgrad {
   int V, G, T;
   int CA, CB;
   int a_gs;             /* PLAIN: row group g of A is group g*a_gs of a_src (strided 1x1 convolution), 0 or 1 = dense  */
+  int b_gs;             /* PLAIN: the same for B / b_src                                                           */
 } SgcnWgrad;
 
 /* PLAIN: dW[a, b] = sum_rows a_src[row, a] * b_src[row, b] with both operands copied as they are (Gram matrices and
@@ -268,8 +269,57 @@ int sgcn_tshift_fwd(const SgcnTShift* p, int mode, void* stream);
 int sgcn_tshift_bwd(const SgcnTShiftBwd* p, int mode, void* stream);
 int sgcn_tshift_in_bwd(const SgcnTShiftInBwd* p, int mode, void* stream);
 
+/* ---------------------------------------------------------------- conv + BatchNorm side branches ---------- */
+/* Parameter-sized fp64 arithmetic of BatchNorm2d(Conv2d 1x1(x)) (`down`, model/shift_gcn.py:82-86; strided `tcn`
+ * residual, :31-45,157-158).  The full-size work is four tensor-core contractions (sgcn_wgrad PLAIN, sgcn_rowgemm
+ * PLAIN x LINEAR); these entry points turn their small results into the folded weights and the gradients. */
+typedef struct SgcnSideFold {
+  double* sx_sums;            /* training: [C][2] channel sums of x from sgcn_channel_stats; handed back zeroed          */
+  const float* XX;            /* training: [C, C] Gram matrix x^T x                                                   */
+  const float* Wd;            /* [D, C] conv weight                                                                   */
+  const float* bd;            /* [D] conv bias or NULL                                                                */
+  const float* gamma;         /* [D] BatchNorm weight / bias                                                          */
+  const float* beta;
+  float* running_mean;        /* [D] updated when training (may be NULL then), read otherwise                         */
+  float* running_var;
+  long long* num_batches_tracked; /* or NULL                                                                          */
+  float* Wf;                  /* out [D, C]: gamma*invstd*Wd                                                          */
+  float* bf;                  /* out [D]:    beta + gamma*invstd*(bd - mean_r)                                        */
+  double* mean_r;             /* out [D]: batch (or running) mean / invstd of the conv output                         */
+  double* invstd;
+  double* sx;                 /* out [C]: channel sums of x (training)                                                */
+  int* counter;               /* zeroed int scratch (training); handed back zeroed                                    */
+  double rows, eps, momentum;
+  int C, D, training;
+} SgcnSideFold;
+int sgcn_side_fold(const SgcnSideFold* p, void* stream);
+
+typedef struct SgcnSideBwd {
+  const float* P;             /* [C, D] correlation x^T G                                                             */
+  const float* sg;            /* [D] column sums of G                                                                 */
+  const float* XX;            /* training: [C, C]                                                                     */
+  const double* sx;           /* training: [C]                                                                        */
+  const float* Wd;            /* [D, C]                                                                               */
+  const float* bd;            /* [D] or NULL                                                                          */
+  const float* gamma;         /* [D]                                                                                  */
+  const double* invstd;       /* [D] from sgcn_side_fold                                                              */
+  const double* mean_r;
+  float* dgamma;              /* out [D]                                                                              */
+  float* dbeta;               /* out [D]                                                                              */
+  float* dWd;                 /* out [D, C]                                                                           */
+  float* dbd;                 /* out [D]                                                                              */
+  float* Wcat;                /* out [D + C, C]: dx = [G | x] Wcat + kvec                                             */
+  float* kvec;                /* out [C]                                                                              */
+  double* coef;               /* scratch [2 * D]                                                                      */
+  double rows;
+  int C, D, training;
+} SgcnSideBwd;
+int sgcn_side_bwd(const SgcnSideBwd* p, void* stream);
+
 /* stats[c][2] += {sum, sumsq} over rows */
 int sgcn_channel_stats(const float* x, double* stats, long long rows, int C, void* stream);
+/* the same over `groups` row groups of V rows, group g being group g*gs of x (the frames a strided 1x1 conv reads) */
+int sgcn_channel_stats_groups(const float* x, double* stats, long long groups, int V, int C, int gs, void* stream);
 /* gh = g*[h>0]; vd_sums[v,c][2] += {gh, gh*zhat} */
 int sgcn_relu_bn1d_bwd_stats(const float* g, const float* h, const float* z, const float* zmean, const float* zinvstd,
                              float* gh, double* vd_sums, long long groups, int V, int C, void* stream);

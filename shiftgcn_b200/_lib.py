@@ -21,7 +21,7 @@ class SgcnRowGemm(ctypes.Structure):
 
 class SgcnWgrad(ctypes.Structure):
     _fields_ = [(n, _vp) for n in ("a_src", "a_tab0", "b_src", "b_src2", "b_tab0", "b_tab1", "b_tab2", "dw")] + \
-               [("groups", _ll), ("V", _i), ("G", _i), ("T", _i), ("CA", _i), ("CB", _i), ("a_gs", _i)]
+               [("groups", _ll), ("V", _i), ("G", _i), ("T", _i), ("CA", _i), ("CB", _i), ("a_gs", _i), ("b_gs", _i)]
 
 
 class SgcnTShift(ctypes.Structure):
@@ -54,6 +54,18 @@ class SgcnStem(ctypes.Structure):
                [("groups", _ll), ("V", _i), ("D", _i)]
 
 
+class SgcnSideFold(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("sx_sums", "XX", "Wd", "bd", "gamma", "beta", "running_mean", "running_var",
+                                   "num_batches_tracked", "Wf", "bf", "mean_r", "invstd", "sx", "counter")] + \
+               [("rows", _d), ("eps", _d), ("momentum", _d), ("C", _i), ("D", _i), ("training", _i)]
+
+
+class SgcnSideBwd(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("P", "sg", "XX", "sx", "Wd", "bd", "gamma", "invstd", "mean_r", "dgamma", "dbeta",
+                                   "dWd", "dbd", "Wcat", "kvec", "coef")] + \
+               [("rows", _d), ("C", _i), ("D", _i), ("training", _i)]
+
+
 # name -> argtypes (restype is always int unless noted); must list every symbol of include/shiftgcn_b200.h
 SIGNATURES = {
     "sgcn_abi_version": [],
@@ -66,6 +78,8 @@ SIGNATURES = {
     "sgcn_shift_bwd_nchw_f32": [_vp] * 9 + [_ll, _i, _i, _i, _i, _vp],
     "sgcn_shift_bwd_nchw_f64": [_vp] * 9 + [_ll, _i, _i, _i, _i, _vp],
     "sgcn_input_stream": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp],
+    "sgcn_side_fold": [ctypes.POINTER(SgcnSideFold), _vp],
+    "sgcn_side_bwd": [ctypes.POINTER(SgcnSideBwd), _vp],
     "sgcn_stem_fwd": [ctypes.POINTER(SgcnStem), _i, _vp],
     "sgcn_stem_bwd": [ctypes.POINTER(SgcnStem), _i, _vp],
     "sgcn_rowgemm": [ctypes.POINTER(SgcnRowGemm), _i, _i, _vp],
@@ -78,6 +92,7 @@ SIGNATURES = {
     "sgcn_shift_pos_finalize": [_vp, _vp, _vp, _vp, _i, _d, _vp],
     "sgcn_relu_bn1d_bwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "sgcn_channel_stats": [_vp, _vp, _ll, _i, _vp],
+    "sgcn_channel_stats_groups": [_vp, _vp, _ll, _i, _i, _i, _vp],
     "sgcn_relu_mask_grad": [_vp, _vp, _vp, _ll, _vp],
     "sgcn_bn_fwd_finalize": [_vp] * 10 + [_i, _d, _d, _d, _i, _vp],
     "sgcn_tshift_bwd_finalize": [_vp] * 11 + [_i, _d, _d, _i, _vp],

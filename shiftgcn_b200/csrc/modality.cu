@@ -64,8 +64,9 @@ extern "C" int sgcn_input_stream(const float* joint, float* out, const int* pare
                                  const float* shift, long long N, int C, int T, int V, int M, int motion, int rows,
                                  void* stream) {
   using namespace sgcn;
-  if (!joint || !out) return set_error("sgcn_input_stream: null pointer");
   if (N < 0 || C < 1 || T < 1 || V < 1 || M < 1) return set_error("sgcn_input_stream: bad shape");
+  if (N == 0) return 0;                                         // empty batch: nothing to do (pointers may be NULL)
+  if (!joint || !out) return set_error("sgcn_input_stream: null pointer");
   if ((scale == nullptr) != (shift == nullptr)) return set_error("sgcn_input_stream: scale and shift come together");
   if (joint == out && (parent || motion)) return set_error("sgcn_input_stream: in-place derivation is not possible");
   const long long total = N * C * T * V * M;

@@ -241,7 +241,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
         }
       }
       load_frames<kUnrollWide, PITCH>(gv, p.gy + ob, to, To, pitch);
-      load_frames<kUnrollWide, PITCH>(yv, yb, to, To, pitch);
+      if (p.relu) {                                        // grid-uniform: a pre-masked g_y skips the third stream
+        load_frames<kUnrollWide, PITCH>(yv, yb, to, To, pitch);
+      } else {
+#pragma unroll
+        for (int u = 0; u < kUnrollWide; ++u) yv[u] = 1.f;
+      }
 #pragma unroll
       for (int u = 0; u < kUnrollWide; ++u)
         if (to + u < to1) {
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
           const float s = fmaf(L.f, q1[u], L.g * a);
           const float dq = q1[u] - a;
           qa = q1[u];
-          const float g = (!p.relu || yv[u] > 0.f) ? gv[u] : 0.f;
+          const float g = yv[u] > 0.f ? gv[u] : 0.f;
           acc[0] += g;
           acc[1] = fmaf(g, s, acc[1]);
           acc[2] = fmaf(g, dq, acc[2]);
@@ -316,7 +321,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
       float q1[kUnroll], gv[kUnroll], yv[kUnroll];
       load_frames<kUnroll, PITCH>(q1, qb, t + 1, T, pitch);
       load_frames<kUnroll, PITCH>(gv, gb, t - L.y1, T, pitch);      // frames outside [0, T) are masked by ds_eval
-      load_frames<kUnroll, PITCH>(yv, yb, t - L.y1, T, pitch);
+      if (relu) {                                                   // grid-uniform, see tshift_bwd_stats_kernel
+        load_frames<kUnroll, PITCH>(yv, yb, t - L.y1, T, pitch);
+      } else {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) yv[u] = 1.f;
+      }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u)
         if (t + u < t1) {
@@ -563,15 +573,15 @@ __global__ void __launch_bounds__(256) tshift_in_combine_kernel(const SgcnTShift
 template <int PITCH>
 __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) channel_stats_kernel(const float* __restrict__ x,
                                                                        double* __restrict__ stats, long long groups,
-                                                                       int gper, int nchunks, int V, int C, int rev) {
+                                                                       int gper, int nchunks, int V, int C, int gs, int rev) {
   __shared__ float scratch[kMaxWarps * 32 * 2];
   const Col k = col_of(C, nchunks, rev);
   const long long g0 = (long long)k.chunk * gper;
   const int ng = (int)((groups - g0) < gper ? (groups - g0) : gper);
-  const int pitch = V * C;
+  const int pitch = V * C * gs;                                  // gs > 1: every gs-th group (frame) only
   float acc[2] = {0.f, 0.f};
   for (int v = k.warp; v < V; v += k.nw) {
-    const float* xp = x + ((size_t)g0 * V + v) * C + k.c;
+    const float* xp = x + ((size_t)g0 * gs * V + v) * C + k.c;
     for (int g = 0; g < ng; g += kUnrollMax) {
       float xv[kUnrollMax];
       load_frames<kUnrollMax, PITCH>(xv, xp, g, ng, pitch);        // zero padded past the chunk
@@ -802,16 +812,29 @@ extern "C" int sgcn_channel_stats(const float* x, double* stats, long long rows,
   if (groups > 0) {
     const Geo g = geometry(C, V, 1, groups, 8);
     const int rev = next_direction();
-    SGCN_PITCH_DISPATCH(V * C, (channel_stats_kernel<P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(x, stats, groups, g.per, g.nchunks, V, C, rev)))
+    SGCN_PITCH_DISPATCH(V * C, (channel_stats_kernel<P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(x, stats, groups, g.per, g.nchunks, V, C, 1, rev)))
     if (int rc = check_launch("channel_stats_kernel")) return rc;
   }
   const int tail = (int)(rows - groups * V);
   if (tail > 0) {
     channel_stats_kernel<0><<<C / 32, 32 * ceil_div(tail, 2), 0, (cudaStream_t)stream>>>(x + (size_t)groups * V * C, stats,
-                                                                                     1, 1, 1, tail, C, 0);
+                                                                                     1, 1, 1, tail, C, 1, 0);
     return check_launch("channel_stats_kernel(tail)");
   }
   return 0;
+}
+
+extern "C" int sgcn_channel_stats_groups(const float* x, double* stats, long long groups, int V, int C, int gs,
+                                         void* stream) {
+  if (!x || !stats) return set_error("sgcn_channel_stats_groups: null pointer");
+  if (int rc = check_cv(C, V)) return rc;
+  if (gs < 1) return set_error("sgcn_channel_stats_groups: group stride must be >= 1");
+  if (groups <= 0) return 0;
+  const Geo g = geometry(C, V, 1, groups, 8);
+  const int rev = next_direction();
+  SGCN_PITCH_DISPATCH(V * C * gs, (channel_stats_kernel<P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(
+                                      x, stats, groups, g.per, g.nchunks, V, C, gs, rev)))
+  return check_launch("channel_stats_kernel(groups)");
 }
 
 extern "C" int sgcn_relu_bn1d_bwd_stats(const float* g, const float* h, const float* z, const float* zmean,

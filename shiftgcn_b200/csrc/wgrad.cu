@@ -190,13 +190,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
         const int k = gt & (ppr - 1);
         const uint32_t kk = (uint32_t)k & 7u;
         const uint32_t poff = ((uint32_t)k >> 3) * BLK + ((kk & 1u) << 4);
-        const float* src = p.b_src + (size_t)g0 * V * CB + (size_t)k * 4;
+        const long long bgs = p.b_gs > 0 ? p.b_gs : 1;          // like a_gs: group g of the tile is group (g0+g)*b_gs
+        const float* src = p.b_src + (size_t)g0 * bgs * V * CB + (size_t)k * 4;
         constexpr int rstep = kWgGroupThreads / ppr;
         uint8_t* sBp = sA + (size_t)ablocks * BLK;
         for (int q = gt / ppr; q < ng * V; q += rstep) {
           const int g = q / V, v = q - g * V;
           const uint32_t r = (uint32_t)(g * VP + v);
-          cp_async16(sBp + poff + r * 128u + ((((kk >> 1) ^ (r & 3u))) << 5), src + (size_t)q * CB);
+          cp_async16(sBp + poff + r * 128u + ((((kk >> 1) ^ (r & 3u))) << 5), src + ((size_t)g * bgs * V + v) * CB);
         }
         cp_async_commit();
         cp_async_wait_all();

@@ -185,7 +185,7 @@ def stem_backward(saved, g, W, bias, mask, gamma1, Wd, bd, gamma2, ws):
 
 
 # ================================================================================================ conv + BN side branches
-def side_forward(x, Wd, bd, bn, training, ws):
+def side_forward(x, Wd, bd, bn, training, ws, gs=1):
     """BatchNorm2d(Conv2d_1x1(x)) on rows (`down` of Shift_gcn, model/shift_gcn.py:82-86; `tcn` residual, :31-45).
 
     x: (rows, C) with rows a multiple of V*... (any row count that is a multiple of the tile group size is fine: the
@@ -194,91 +194,73 @@ def side_forward(x, Wd, bd, bn, training, ws):
     so they cost one Gram-matrix contraction of x on the tensor cores (rounding errors of ~1e6 products average out)
     plus one channel-sum pass, and the normalisation is FOLDED into the conv weights before the only full-size GEMM:
     r' = x (sc*Wd)^T + (beta - sc*(Wd mu)).  The raw conv output is never stored.
+    gs > 1: the conv has frame stride gs -- every kernel reads frames 0, gs, 2gs, .. of x in place (no gathered copy).
     """
-    n, T, V, C = x.shape
+    n, Tx, V, C = x.shape
+    T = Tx // gs
     rows = n * T * V
     D = Wd.shape[0]
     dev = x.device
     gamma, beta, rmean, rvar, nbt, mom = _bn_args(bn)
-    Wd64 = Wd.detach().reshape(D, C).double()
-    saved = dict(x=x, training=training)
+    Wd2 = Wd.detach().reshape(D, C)
+    saved = dict(x=x, training=training, gs=gs)
+    st = XX = counter = None
     if training:
         st = ws.get("side_sx", 2 * C, dev)
-        ops.channel_stats(x, st, rows, C)
-        sx = ops.reduce_export(st).reshape(C, 2)[:, 0].double()
+        if gs == 1:
+            ops.channel_stats(x, st, rows, C)
+        else:
+            ops.channel_stats_groups(x, st, n * T, V, C, gs)
         XX = torch.zeros((C, C), device=dev, dtype=torch.float32)
-        ops.wgrad(ops.WG_PLAIN, a_src=x, b_src=x, dw=XX, groups=n * T, V=V, CA=C, CB=C)
-        mu = sx / rows
-        cov = XX.double() / rows - torch.outer(mu, mu)
-        wmu = Wd64 @ mu
-        mean_r = wmu + (bd.detach().double() if bd is not None else 0.0)
-        var_r = ((Wd64 @ cov) * Wd64).sum(1).clamp_min(0.0)
-        with torch.no_grad():
-            if bn.track_running_stats and rmean is not None:
-                unbiased = var_r * (rows / max(rows - 1, 1))
-                rmean.mul_(1 - mom).add_((mom * mean_r).float())
-                rvar.mul_(1 - mom).add_((mom * unbiased).float())
-                nbt.add_(1)
-        saved.update(sx=sx, XX=XX)
-    else:
-        mean_r = rmean.double()
-        var_r = rvar.double()
-        wmu = None
-    invstd = torch.rsqrt(var_r + bn.eps)
-    sc = gamma.detach().double() * invstd
-    Wf = (Wd64 * sc[:, None]).float().contiguous()
-    bias_r = bd.detach().double() if bd is not None else torch.zeros(D, device=dev, dtype=torch.float64)
-    bf = (beta.detach().double() + sc * (bias_r - mean_r)).float().contiguous()
-    wimg = ops.weight_image(Wf, C, 1, D, C)                        # B[n=d][k=c] = Wf[d][c]
+        ops.wgrad(ops.WG_PLAIN, a_src=x, b_src=x, dw=XX, groups=n * T, V=V, CA=C, CB=C, a_gs=gs, b_gs=gs)
+        counter = ws.get_int("side_counter", 1, dev)
+    track = bn.track_running_stats and rmean is not None
+    f = ops.side_fold(Wd2, None if bd is None else bd.detach(), gamma.detach(), beta.detach(), rmean if track else None,
+                      rvar if track else None, nbt if (track and training) else None, rows, bn.eps, mom, training,
+                      sx_sums=st, XX=XX, counter=counter)
+    if training:
+        saved.update(sx=f["sx"], XX=XX)
+    wimg = ops.weight_image(f["Wf"], C, 1, D, C)                   # B[n=d][k=c] = Wf[d][c]
     out = torch.empty((n, T, V, D), device=dev, dtype=torch.float32)
-    ops.rowgemm(ops.PRO_PLAIN, ops.EPI_LINEAR, in0=x, out=out, wimg=wimg, groups=n * T, V=V, K=C, N=D, bias=bf, relu=0)
-    saved.update(mean_r=mean_r, invstd=invstd)
+    ops.rowgemm(ops.PRO_PLAIN, ops.EPI_LINEAR, in0=x, out=out, wimg=wimg, groups=n * T, V=V, K=C, N=D, bias=f["bf"], relu=0,
+                in0_gs=gs if gs > 1 else 0)
+    saved.update(mean_r=f["mean_r"], invstd=f["invstd"])
     return out, saved
 
 
-def side_backward(saved, G, sg, Wd, bd, gamma, ws):
+def side_backward(saved, G, sg, Wd, bd, gamma, ws, accum_into=None):
     """Gradients of the conv + BN branch without touching the conv output: with P = x^T G (one plain contraction),
     XX = x^T x and sx from the forward, everything else is C x C x D arithmetic on the device (fp64):
         dgamma = invstd * (rowsum(Wd * P^T) + (bd - mean_r) * sg),  dbeta = sg,
         dr = al*G + be*r + ga  (BatchNorm backward as an affine map),   dWd = al*P^T + be*(Wd XX + bd sx^T) + ga sx^T,
         dx = G (al*Wd) + x (Wd^T be Wd) + Wd^T (be*bd + ga)           -- ONE GEMM over the concatenation [G | x].
+    accum_into: an existing gradient wrt the whole x; dx is then ADDED to it in the GEMM epilogue (at the strided
+    frames when the conv has a frame stride) and the returned dx is that tensor.
     """
     x = saved["x"]
-    n, T, V, C = x.shape
+    gs = saved.get("gs", 1)
+    n, Tx, V, C = x.shape
+    T = Tx // gs
     rows = n * T * V
     D = Wd.shape[0]
     dev = x.device
     training = saved["training"]
-    Wd64 = Wd.detach().reshape(D, C).double()
-    bd64 = bd.detach().double() if bd is not None else torch.zeros(D, device=dev, dtype=torch.float64)
     P = torch.zeros((C, D), device=dev, dtype=torch.float32)
-    ops.wgrad(ops.WG_PLAIN, a_src=x, b_src=G, dw=P, groups=n * T, V=V, CA=C, CB=D)
-    Pt = P.double().t()                                             # (D, C)
-    sg = sg.double()
-    invstd, mean_r = saved["invstd"], saved["mean_r"]
-    dgamma = invstd * ((Wd64 * Pt).sum(1) + (bd64 - mean_r) * sg)
-    dbeta = sg
-    k = gamma.detach().double() * invstd
-    if training:
-        m1, m2 = sg / rows, dgamma / rows
-        sx, XX = saved["sx"], saved["XX"].double()
+    ops.wgrad(ops.WG_PLAIN, a_src=x, b_src=G, dw=P, groups=n * T, V=V, CA=C, CB=D, a_gs=gs)
+    r = ops.side_bwd(P, sg.float().contiguous(), Wd.detach().reshape(D, C), None if bd is None else bd.detach(),
+                     gamma.detach(), saved["invstd"], saved["mean_r"], rows, training, sx=saved.get("sx"),
+                     XX=saved.get("XX"))
+    wimg = ops.weight_image(r["Wcat"], 1, C, C, D + C)             # B[n=c][k] = Wcat[k][c]: out[c] = sum_k in[k] Wcat[k][c]
+    if accum_into is None:
+        if gs != 1:
+            raise RuntimeError("side_backward: a strided branch adds its input gradient into accum_into")
+        dx = torch.empty((n, T, V, C), device=dev, dtype=torch.float32)
     else:
-        m1 = m2 = torch.zeros_like(sg)
-        sx = torch.zeros(C, device=dev, dtype=torch.float64)
-        XX = torch.zeros((C, C), device=dev, dtype=torch.float64)
-    al, be = k, -k * m2 * invstd
-    ga = -k * m1 + k * m2 * invstd * mean_r
-    dWd = al[:, None] * Pt + be[:, None] * (Wd64 @ XX + torch.outer(bd64, sx)) + torch.outer(ga, sx)
-    dbd = al * sg + be * (Wd64 @ sx + rows * bd64) + rows * ga
-    A1 = al[:, None] * Wd64                                         # (D, C)
-    M = Wd64.t() @ (be[:, None] * Wd64)                             # (C, C)
-    kvec = Wd64.t() @ (be * bd64 + ga)
-    Wcat = torch.cat([A1, M], 0).float().contiguous()              # (D + C, C): out[c] = sum_k in[k] Wcat[k][c]
-    wimg = ops.weight_image(Wcat, 1, C, C, D + C)                  # B[n=c][k] = Wcat[k][c]
-    dx = torch.empty((n, T, V, C), device=dev, dtype=torch.float32)
+        dx = accum_into
     ops.rowgemm(ops.PRO_PLAIN, ops.EPI_LINEAR, in0=G, in1=x, out=dx, wimg=wimg, groups=n * T, V=V, K=D + C, N=C, k0=D,
-                bias=kvec.float().contiguous(), relu=0)
-    return dict(dx=dx, dWd=dWd.float().reshape(Wd.shape), dbd=dbd.float(), dgamma=dgamma.float(), dbeta=dbeta.float())
+                bias=r["kvec"], relu=0, in1_gs=gs if gs > 1 else 0, out_gs=gs if gs > 1 else 0,
+                accum=0 if accum_into is None else 1)
+    return dict(dx=dx, dWd=r["dWd"].reshape(Wd.shape), dbd=r["dbd"], dgamma=r["dgamma"], dbeta=r["dbeta"])
 
 
 # ================================================================================================ temporal unit
@@ -594,8 +576,7 @@ class ConvUnitFn(torch.autograd.Function):
         h_stats = tcn._ws.get("bn_a", 2 * D, x.device) if training else None
         h, s_saved = spatial_forward(x, res_d, W, bias, mask, gcn.bn, training, gcn._ws,
                                      fuse_eval=(not training and not need_grad), h_stats=h_stats)
-        xs = x if stride == 1 else x[:, ::stride].contiguous()          # frames the strided 1x1 conv reads
-        res_r, sr_saved = side_forward(xs, Wr, br, unit.residual.bn, training, tcn._ws)
+        res_r, sr_saved = side_forward(x, Wr, br, unit.residual.bn, training, tcn._ws, gs=stride)   # strided in place
         y, t_saved = temporal_forward(h, res_r, 1, tcn.bn, ypos_in, Wt.reshape(D, D), bt, ypos_out, tcn.bn2, stride,
                                       training, tcn._ws, h_stats_ready=training)
         ctx.unit = unit
@@ -622,17 +603,14 @@ class ConvUnitFn(torch.autograd.Function):
         if want_raw:
             tcn.shift_in._raw_ypos_grad, tcn.shift_out._raw_ypos_grad = t["raw_in"], t["raw_out"]
         gres = gy if masked else ops.relu_mask_grad(gy, t_saved["y"])   # gradient into the conv residual branch
-        rr = side_backward(sr_saved, gres, t["dbeta_b"], p["Wr"], p["br"], p["gr"], tcn._ws)
-        rd = {}
+        rd, rr = {}, {}
 
         def side_fn(gh, sg):
+            # input gradients of both conv branches in ONE tensor: the `down` branch writes it, the (strided) residual
+            # branch adds into it inside its GEMM epilogue, the spatial backward kernel adds it to gx
             rd.update(side_backward(sd_saved, gh, sg, p["Wd"], p["bd"], p["gd"], gcn._ws))
-            dx = rd["dx"]
-            if stride == 1:
-                dx.add_(rr["dx"])
-            else:
-                dx[:, ::stride].add_(rr["dx"])                           # transposed frame stride of the 1x1 conv
-            return dx
+            rr.update(side_backward(sr_saved, gres, t["dbeta_b"], p["Wr"], p["br"], p["gr"], tcn._ws, accum_into=rd["dx"]))
+            return rd["dx"]
 
         s = spatial_backward(s_saved, t["gh"], p["W"], p["mask"], p["g1"], True, gcn._ws, side_fn=side_fn,
                              premask=_premask_now(ctx))

@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import SgcnRowGemm, SgcnStem, SgcnTShift, SgcnTShiftBwd, SgcnTShiftInBwd, SgcnTShiftInSums, SgcnWgrad
+from ._lib import SgcnRowGemm, SgcnSideBwd, SgcnSideFold, SgcnStem, SgcnTShift, SgcnTShiftBwd, SgcnTShiftInBwd, SgcnTShiftInSums, SgcnWgrad
 
 PRO_SPATIAL, PRO_LERP, PRO_PLAIN, PRO_DY = 0, 1, 2, 3
 EPI_ROT_RAW, EPI_ROT_FUSED, EPI_LINEAR, EPI_SPATIAL_BWD = 0, 1, 2, 3
@@ -236,11 +236,11 @@ def rowgemm(pro, epi, *, in0, out, wimg, groups, V, K, N, T=1, in1=None, pro_a=N
 
 
 def wgrad(mode, *, a_src, b_src, dw, groups, V, CA, CB, T=1, a_tab0=None, b_src2=None, b_tab0=None, b_tab1=None,
-          b_tab2=None, a_gs=1):
+          b_tab2=None, a_gs=1, b_gs=1):
     lib = _lib.load()
     p = SgcnWgrad(a_src=_p(a_src), a_tab0=_p(a_tab0), b_src=_p(b_src), b_src2=_p(b_src2), b_tab0=_p(b_tab0),
                   b_tab1=_p(b_tab1), b_tab2=_p(b_tab2), dw=_p(dw), groups=int(groups), V=V, G=groups_per_tile(V),
-                  T=int(T), CA=CA, CB=CB, a_gs=int(a_gs))
+                  T=int(T), CA=CA, CB=CB, a_gs=int(a_gs), b_gs=int(b_gs))
     nbytes = int(groups) * V * 4 * (CA + CB) if mode == WG_PLAIN else _nbytes(a_src, b_src, b_src2)
     _launch("wgrad[%s]" % ("spatial", "temporal", "plain")[mode], 1, nbytes, lib.sgcn_wgrad,
             ctypes.byref(p), mode, _stream())
@@ -338,6 +338,13 @@ def channel_stats(x, stats, rows, C):
     _launch("channel_stats", 1, _nbytes(x), lib.sgcn_channel_stats, _p(x), _d(stats), int(rows), C, _stream())
 
 
+def channel_stats_groups(x, stats, groups, V, C, gs):
+    """channel sums over `groups` frames of V rows, frame g being frame g*gs of x"""
+    lib = _lib.load()
+    _launch("channel_stats", 1, int(groups) * V * C * 4, lib.sgcn_channel_stats_groups, _p(x), _d(stats), int(groups), V, C,
+            int(gs), _stream())
+
+
 def relu_bn1d_bwd_stats(g, h, z, zmean, zinvstd, gh, vd_sums, groups, V, C):
     lib = _lib.load()
     _launch("relu_bn1d_bwd_stats", 1, _nbytes(g, h, z, gh), lib.sgcn_relu_bn1d_bwd_stats, _p(g), _p(h), _p(z), _p(zmean),
@@ -366,7 +373,49 @@ def input_stream(joint, parent=None, motion=False, rows=False, scale=None, shift
     if (scale is None) != (shift is None) or (scale is not None and (not rows or scale.numel() != M * V * C)):
         raise RuntimeError("scale / shift come together, need rows=True and M*V*C entries each")
     out = torch.empty((N * M, T, V, C) if rows else (N, C, T, V, M), device=joint.device, dtype=torch.float32)
+    if out.numel() == 0:
+        return out
     _launch("input_stream", 1, _nbytes(joint, out), lib.sgcn_input_stream, _p(joint, name="joint"), _p(out),
             _p(parent, torch.int32, "parent"), _p(scale), _p(shift), N, C, T, V, M, 1 if motion else 0, 1 if rows else 0,
             _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ conv + BN side branches
+def side_fold(Wd, bd, gamma, beta, running_mean, running_var, nbt, rows, eps, momentum, training, sx_sums=None, XX=None,
+              counter=None):
+    """sgcn_side_fold -> dict(Wf [D,C], bf [D], mean_r [D] f64, invstd [D] f64, sx [C] f64 or None)"""
+    _count()
+    lib = _lib.load()
+    D, C = Wd.shape
+    dev = Wd.device
+    Wf = torch.empty((D, C), device=dev, dtype=torch.float32)
+    bf = torch.empty(D, device=dev, dtype=torch.float32)
+    stat = torch.empty((2, D), device=dev, dtype=torch.float64)
+    sx = torch.empty(C, device=dev, dtype=torch.float64) if training else None
+    p = SgcnSideFold(sx_sums=_d(sx_sums), XX=_p(XX), Wd=_p(Wd, name="Wd"), bd=_p(bd), gamma=_p(gamma), beta=_p(beta),
+                     running_mean=_p(running_mean), running_var=_p(running_var),
+                     num_batches_tracked=_p(nbt, torch.int64), Wf=_p(Wf), bf=_p(bf), mean_r=_d(stat[0]), invstd=_d(stat[1]),
+                     sx=_d(sx), counter=_p(counter, torch.int32), rows=float(rows), eps=float(eps),
+                     momentum=float(momentum), C=C, D=D, training=1 if training else 0)
+    _lib.check(lib.sgcn_side_fold(ctypes.byref(p), _stream()), "side fold")
+    return dict(Wf=Wf, bf=bf, mean_r=stat[0], invstd=stat[1], sx=sx)
+
+
+def side_bwd(P, sg, Wd, bd, gamma, invstd, mean_r, rows, training, sx=None, XX=None):
+    """sgcn_side_bwd -> dict(dgamma, dbeta, dWd [D,C], dbd, Wcat [D+C,C], kvec [C])"""
+    _count(2)
+    lib = _lib.load()
+    D, C = Wd.shape
+    dev = Wd.device
+    vec = torch.empty((3, D), device=dev, dtype=torch.float32)
+    dWd = torch.empty((D, C), device=dev, dtype=torch.float32)
+    Wcat = torch.empty((D + C, C), device=dev, dtype=torch.float32)
+    kvec = torch.empty(C, device=dev, dtype=torch.float32)
+    coef = torch.empty(2 * D, device=dev, dtype=torch.float64)
+    p = SgcnSideBwd(P=_p(P, name="P"), sg=_p(sg, name="sg"), XX=_p(XX), sx=_d(sx), Wd=_p(Wd, name="Wd"), bd=_p(bd),
+                    gamma=_p(gamma), invstd=_d(invstd), mean_r=_d(mean_r), dgamma=_p(vec[0]), dbeta=_p(vec[1]),
+                    dWd=_p(dWd), dbd=_p(vec[2]), Wcat=_p(Wcat), kvec=_p(kvec), coef=_d(coef), rows=float(rows), C=C, D=D,
+                    training=1 if training else 0)
+    _lib.check(lib.sgcn_side_bwd(ctypes.byref(p), _stream()), "side backward")
+    return dict(dgamma=vec[0], dbeta=vec[1], dWd=dWd, dbd=vec[2], Wcat=Wcat, kvec=kvec)

@@ -116,6 +116,9 @@ def test_premasked_gradients_between_units_change_nothing(cuda_device, num_class
         # identical arithmetic; what is left is the order of the fp64 atomics behind the BatchNorm coefficients, whose
         # last-bit changes flip TF32 operand roundings downstream (~1e-4 after 20 contractions).  A mask applied at
         # the wrong place, or not at all, shows up as O(0.1 .. 1).
-        scale = max(a.abs().max().item(), 1e-12)
+        scale = a.abs().max().item()
+        if scale < 1e-5:                                         # analytically zero (a conv bias in front of a BatchNorm)
+            assert b.abs().max().item() < 1e-5, k
+            continue
         assert (a - b).abs().max().item() <= 2e-3 * scale, k
         assert rel_l2(b, a) < 1e-3, k
