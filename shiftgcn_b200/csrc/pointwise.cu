@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
 // ------------------------------------------------------------------------------------------------ output shift + BN, backward
 // sums5[c] += { g, g*shat, g*dq, dq, shat*dq }   with g = gy*[y>0] (if relu), s = Shift(q), shat = (s-mean)*invstd,
 // dq = Q(ta+1) - Q(ta)  (d s / d ypos, K4 with xpos = 0)
-template <bool S1, int PITCH>
+template <bool S1, bool RELU, int PITCH>
 __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_bwd_stats_kernel(const SgcnTShiftBwd p, int tper, int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32 * 5];
   const Col k = col_of(p.C, nchunks, rev);
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
         }
       }
       load_frames<kUnrollWide, PITCH>(gv, p.gy + ob, to, To, pitch);
-      if (p.relu) {                                        // grid-uniform: a pre-masked g_y skips the third stream
+      if (RELU) {                                          // compile time: a pre-masked g_y has no third stream
         load_frames<kUnrollWide, PITCH>(yv, yb, to, To, pitch);
       } else {
 #pragma unroll
@@ -291,7 +291,7 @@ __device__ __forceinline__ float ds_eval(bool valid, float g, float y, int relu,
 
 // stride 1:  dpre(t) = [Q(t) > 0] * ( g*ds(t-y1) + f*ds(t-y1-1) ),  ds(to) uses s(to) = g*Q(to+y1) + f*Q(to+y1+1)
 // walk over input frames t; to = t - y1; the previous ds and the tap Q(t+1) slide along in registers
-template <int PITCH>
+template <bool RELU, int PITCH>
 __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_bwd_apply_s1_kernel(const SgcnTShiftBwd p, int tper,
                                                                             int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32];
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
   const int pitch = V * C;
   const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
   const BwdCh B = bwd_of(p, k.c);
-  const int relu = p.relu;
+  const int relu = RELU ? 1 : 0;
   const int t0 = k.chunk * tper, t1 = min(T, t0 + tper);
   float acc[1] = {0.f};
   for (int v = k.warp; v < V; v += k.nw) {
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
       float q1[kUnroll], gv[kUnroll], yv[kUnroll];
       load_frames<kUnroll, PITCH>(q1, qb, t + 1, T, pitch);
       load_frames<kUnroll, PITCH>(gv, gb, t - L.y1, T, pitch);      // frames outside [0, T) are masked by ds_eval
-      if (relu) {                                                   // grid-uniform, see tshift_bwd_stats_kernel
+      if (RELU) {                                                   // compile time, see tshift_bwd_stats_kernel
         load_frames<kUnroll, PITCH>(yv, yb, t - L.y1, T, pitch);
       } else {
 #pragma unroll
@@ -545,13 +545,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
   block_reduce_channels<1>(acc, p.sums, k.c, scratch, 3);       // sums[c][0]
 }
 
-__global__ void __launch_bounds__(256) tshift_in_combine_kernel(const SgcnTShiftInSums p) {
-  __shared__ double part[2][4][64];
-  const int cl = threadIdx.x & 63, dg = threadIdx.x >> 6;         // 64 channels x 4 interleaved row groups
+__global__ void __launch_bounds__(1024) tshift_in_combine_kernel(const SgcnTShiftInSums p) {
+  __shared__ double part[2][16][64];
+  const int cl = threadIdx.x & 63, dg = threadIdx.x >> 6;         // 64 channels x 16 interleaved row groups
   const int c = blockIdx.x * 64 + cl, C = p.C;
   if (*p.gate) return;
   double s0 = 0.0, sw = 0.0;
-  for (int d = dg; d < C; d += 4) {
+  for (int d = dg; d < C; d += 16) {
     const double w = (double)__ldg(p.Wt + (size_t)d * C + c);
     s0 = fma(w, (double)__ldg(p.dbt + d), s0);
     sw = fma(w, (double)__ldg(p.dWt + (size_t)d * C + c), sw);
@@ -560,8 +560,12 @@ __global__ void __launch_bounds__(256) tshift_in_combine_kernel(const SgcnTShift
   part[1][dg][cl] = sw;
   __syncthreads();
   if (dg != 0) return;
-  s0 = part[0][0][cl] + part[0][1][cl] + part[0][2][cl] + part[0][3][cl];
-  sw = part[1][0][cl] + part[1][1][cl] + part[1][2][cl] + part[1][3][cl];
+  s0 = sw = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    s0 += part[0][j][cl];
+    sw += part[1][j][cl];
+  }
   s0 += p.sums[3 * (size_t)c];                                   // minus the boundary frames (tshift_in_boundary_kernel)
   const double duh = (sw - (double)p.shift[c] * s0) / (double)p.scale[c];   // sum du * h
   p.sums[3 * (size_t)c] = s0;
@@ -746,16 +750,26 @@ extern "C" int sgcn_tshift_bwd(const SgcnTShiftBwd* p, int mode, void* stream) {
     if (p->T_out <= 0) return 0;
     const Geo g = geometry(p->C, p->V, p->n_samples, p->T_out, 8);
     if (p->stride == 1) {
-      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_stats_kernel<true, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+      if (p->relu) {
+        SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_stats_kernel<true, true, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+      } else {
+        SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_stats_kernel<true, false, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+      }
+    } else if (p->relu) {
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_stats_kernel<false, true, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
     } else {
-      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_stats_kernel<false, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_stats_kernel<false, false, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
     }
     return check_launch("tshift_bwd_stats_kernel");
   }
   if (!p->dpre || !p->dbias || !p->k1 || !p->m1 || !p->m2) return set_error("sgcn_tshift_bwd(apply): null pointer");
   if (p->stride == 1) {
     const Geo g = geometry(p->C, p->V, p->n_samples, p->T_in, 8);
-    SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_apply_s1_kernel<P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+    if (p->relu) {
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_apply_s1_kernel<true, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+    } else {
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_apply_s1_kernel<false, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+    }
     return check_launch("tshift_bwd_apply_s1_kernel");
   }
   if (p->stride == 2) {   // the reference's backward exists for strides 1 and 2 only (shift_cuda_kernel.cu:156-256)
@@ -798,7 +812,7 @@ extern "C" int sgcn_tshift_in_bwd_sums(const SgcnTShiftInSums* p, void* stream) 
   const unsigned grid = (unsigned)((p->C / 32) * p->n_samples);
   tshift_in_boundary_kernel<<<grid, 32 * ceil_div(p->V, 2), 0, s>>>(*p);
   if (int rc = check_launch("tshift_in_boundary_kernel")) return rc;
-  tshift_in_combine_kernel<<<p->C / 64, 256, 0, s>>>(*p);
+  tshift_in_combine_kernel<<<p->C / 64, 1024, 0, s>>>(*p);
   return check_launch("tshift_in_combine_kernel");
 }
 

@@ -97,24 +97,34 @@ __global__ void bn1d_bwd_finalize_kernel(double* __restrict__ vd, const float* _
                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
                                          float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ gam,
                                          float* __restrict__ dbias, int V, int D, double count, int training) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= D) return;
+  // block = 32 channels x 8 joint lanes: the V joints of a channel are spread over threadIdx.y (the loop used to be
+  // serial per channel: V dependent round trips to L2 for a [V*D] table)
+  __shared__ double part[8][32];
+  const int d = blockIdx.x * 32 + threadIdx.x;
   double db = 0.0;
-  for (int v = 0; v < V; ++v) {
-    const size_t f = (size_t)v * D + d;
-    const double S0 = vd[2 * f], S1 = vd[2 * f + 1];
-    vd[2 * f] = 0.0;
-    vd[2 * f + 1] = 0.0;
-    const double is = (double)invstd[f], k = (double)gamma[f] * is;
-    const double m1 = training ? S0 / count : 0.0, m2 = training ? S1 / count : 0.0;
-    dbeta[f] = (float)S0;
-    dgamma[f] = (float)S1;
-    alpha[f] = (float)k;
-    beta[f] = (float)(-k * m2 * is);
-    gam[f] = (float)(-k * m1 + k * m2 * is * (double)mean[f]);
-    db += k * (S0 - count * m1);
+  if (d < D)
+    for (int v = threadIdx.y; v < V; v += 8) {
+      const size_t f = (size_t)v * D + d;
+      const double S0 = vd[2 * f], S1 = vd[2 * f + 1];
+      vd[2 * f] = 0.0;
+      vd[2 * f + 1] = 0.0;
+      const double is = (double)invstd[f], k = (double)gamma[f] * is;
+      const double m1 = training ? S0 / count : 0.0, m2 = training ? S1 / count : 0.0;
+      dbeta[f] = (float)S0;
+      dgamma[f] = (float)S1;
+      alpha[f] = (float)k;
+      beta[f] = (float)(-k * m2 * is);
+      gam[f] = (float)(-k * m1 + k * m2 * is * (double)mean[f]);
+      db += k * (S0 - count * m1);
+    }
+  part[threadIdx.y][threadIdx.x] = db;
+  __syncthreads();
+  if (threadIdx.y == 0 && d < D) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += part[j][threadIdx.x];
+    dbias[d] = (float)s;
   }
-  dbias[d] = (float)db;
 }
 
 __global__ void mask_prepare_kernel(const float* __restrict__ mask, float* __restrict__ mm, int n) {
@@ -210,7 +220,7 @@ extern "C" int sgcn_bn1d_bwd_finalize(double* vd_sums, const float* gamma, const
                                       int V, int D, double count, int training, void* stream) {
   if (!vd_sums || !gamma || !mean || !invstd || !dgamma || !dbeta || !alpha || !beta || !gam || !dbias)
     return set_error("sgcn_bn1d_bwd_finalize: null pointer");
-  bn1d_bwd_finalize_kernel<<<(D + 63) / 64, 64, 0, (cudaStream_t)stream>>>(vd_sums, gamma, mean, invstd, dgamma, dbeta,
+  bn1d_bwd_finalize_kernel<<<(D + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(vd_sums, gamma, mean, invstd, dgamma, dbeta,
                                                                           alpha, beta, gam, dbias, V, D, count,
                                                                           training);
   return check_launch("bn1d_bwd_finalize_kernel");

@@ -319,6 +319,151 @@ __global__ void __launch_bounds__(832, 1) stem_bwd_kernel(const SgcnStem p, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, apply
+// dz, dr from the finalised BatchNorm tables; dW, dWd, dbd, dMask accumulate in registers over the whole walk; dx in
+// two phases per chunk of kGB groups (no shared-memory atomics, no per-element warp reductions):
+//   phase A  thread = (joint v, channel d): loads g and h (coalesced), recomputes z and r from the staged x, keeps the
+//            parameter gradients in registers and leaves dz, dr [g][v][d] in shared memory
+//   phase B  warp = one (group g, joint w) at a time, lanes = channels d and d+32:
+//            dx[g,w,c] = m[u,c] * sum_d dz[g,(u+d)%V,d] W[c,d]  +  sum_d dr[g,w,d] Wd[d,c],   u = (w-c) mod V
+//            -- conflict-free row gathers from shared memory (bank = d), one warp reduction per output value
+constexpr int kGB = 8;
+
+template <int kMaxJ>
+__global__ void __launch_bounds__(832, 1) stem_bwd_apply_kernel(const SgcnStem p, int gper, int rev) {
+  extern __shared__ __align__(16) float dyn[];                     // dz [kGB][V][64], dr [kGB][V][64]
+  __shared__ float sx[kGB * 40 * 3];
+  __shared__ float smk[40 * 3];
+  __shared__ float scratch[16 * 8 * D];
+  const Lay l = layout(p.V);
+  const int V = p.V;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int cb = warp / l.nwj, jw = warp - cb * l.nwj, d = cb * 32 + lane;
+  float* sDz = dyn;
+  float* sDr = dyn + (size_t)kGB * V * D;
+  const long long g0 = (long long)(rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * gper;   // snake traversal
+  const int ng = (int)((p.groups - g0) < gper ? (p.groups - g0) : gper);
+  // weights of this thread's channel d (phase A) and of the channel d ^ 32 of the other half (phase B needs both)
+  float wc[3], wd[3], wco[3], wdo[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    wc[c] = __ldg(p.W + c * D + d);
+    wd[c] = __ldg(p.Wd + d * 3 + c);
+    wco[c] = __ldg(p.W + c * D + (d ^ 32));
+    wdo[c] = __ldg(p.Wd + (d ^ 32) * 3 + c);
+  }
+  for (int i = threadIdx.x; i < V * 3; i += blockDim.x) smk[i] = __ldg(p.maskmul + i);
+  const float b = p.bias ? __ldg(p.bias + d) : 0.f, bd = p.bd ? __ldg(p.bd + d) : 0.f;
+  const float a2 = __ldg(p.a2 + d), b2 = __ldg(p.b2 + d), c2 = __ldg(p.c2 + d);
+  const int lm0 = lane % V, lm1 = (lane + 32) % V;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};         // dW[3], dWd[3], dbd, unused
+  float dM[kMaxJ][3];
+#pragma unroll
+  for (int j = 0; j < kMaxJ; ++j) dM[j][0] = dM[j][1] = dM[j][2] = 0.f;
+
+  for (int gs = 0; gs < ng; gs += kGB) {
+    const int n = min(kGB, ng - gs);
+    __syncthreads();                                               // phase B of the previous chunk is done
+    stage_x(p, sx, g0 + gs, n);
+    __syncthreads();
+    // ---------------------------------------------------------------- phase A
+#pragma unroll
+    for (int j = 0; j < kMaxJ; ++j) {
+      const int v = jw + j * l.nwj;
+      if (j < l.jp && v < V) {                                     // warp uniform
+        int u = v - d % V;
+        if (u < 0) u += V;
+        int xo[3];
+        float mk[3], mw[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          int uc = u + c;
+          if (uc >= V) uc -= V;
+          xo[c] = uc * 3 + c;
+          mk[c] = smk[u * 3 + c];
+          mw[c] = mk[c] * wc[c];
+        }
+        const int f = v * D + d;
+        const float k0 = __ldg(p.al + f), k1 = __ldg(p.be + f), k2 = __ldg(p.ga + f);
+        const float* xp = sx + v * 3;
+        const size_t ob = ((size_t)(g0 + gs) * V + v) * D + d;
+        float* dzp = sDz + (size_t)v * D + d;
+        float* drp = sDr + (size_t)v * D + d;
+        for (int gb = 0; gb < n; gb += kUn) {
+          float gv[kUn], hv[kUn];
+#pragma unroll
+          for (int q = 0; q < kUn; ++q) {
+            const size_t o = ob + (size_t)min(gb + q, n - 1) * V * D;
+            gv[q] = __ldg(p.g + o);
+            hv[q] = __ldg(p.h + o);
+          }
+#pragma unroll
+          for (int q = 0; q < kUn; ++q)
+            if (gb + q < n) {
+              const int o = (gb + q) * V * 3;
+              const float x0 = sx[o + xo[0]], x1 = sx[o + xo[1]], x2 = sx[o + xo[2]];
+              const float p0 = xp[o], p1 = xp[o + 1], p2 = xp[o + 2];
+              const float z = fmaf(x0, mw[0], fmaf(x1, mw[1], fmaf(x2, mw[2], b)));
+              const float r = fmaf(p0, wd[0], fmaf(p1, wd[1], fmaf(p2, wd[2], bd)));
+              const float gm = hv[q] > 0.f ? gv[q] : 0.f;
+              const float dz = fmaf(k0, gm, fmaf(k1, z, k2));
+              const float dr = fmaf(a2, gm, fmaf(b2, r, c2));
+              // Linear_weight / Feature_Mask gradients (autograd of :128-131)
+              acc[0] = fmaf(x0 * mk[0], dz, acc[0]);
+              acc[1] = fmaf(x1 * mk[1], dz, acc[1]);
+              acc[2] = fmaf(x2 * mk[2], dz, acc[2]);
+              dM[j][0] = fmaf(dz * wc[0], x0, dM[j][0]);
+              dM[j][1] = fmaf(dz * wc[1], x1, dM[j][1]);
+              dM[j][2] = fmaf(dz * wc[2], x2, dM[j][2]);
+              // down conv weight / bias gradients
+              acc[3] = fmaf(p0, dr, acc[3]);
+              acc[4] = fmaf(p1, dr, acc[4]);
+              acc[5] = fmaf(p2, dr, acc[5]);
+              acc[6] += dr;
+              dzp[(size_t)(gb + q) * V * D] = dz;
+              drp[(size_t)(gb + q) * V * D] = dr;
+            }
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------------------------------------------------------- phase B
+    float* dxo = p.dx + (size_t)(g0 + gs) * V * 3;
+    for (int pair = warp; pair < n * V; pair += nwarps) {
+      const int g = pair / V, w = pair - g * V;
+      const float* dzg = sDz + (size_t)g * V * D;
+      const float* drw = sDr + ((size_t)g * V + w) * D;
+      const float dr0 = drw[lane], dr1 = drw[lane + 32];
+      float sc[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        int u = w - c;
+        if (u < 0) u += V;
+        int r0 = u + lm0, r1 = u + lm1;
+        if (r0 >= V) r0 -= V;
+        if (r1 >= V) r1 -= V;
+        // channel `lane` uses this thread's own weights when cb == 0, the other half's when cb == 1 (warp uniform)
+        const float a0 = dzg[r0 * D + lane], a1 = dzg[r1 * D + lane + 32];
+        const float t = cb == 0 ? fmaf(a0, wc[c], a1 * wco[c]) : fmaf(a0, wco[c], a1 * wc[c]);
+        const float e = cb == 0 ? fmaf(dr0, wd[c], dr1 * wdo[c]) : fmaf(dr0, wdo[c], dr1 * wd[c]);
+        sc[c] = warp_sum(fmaf(t, smk[u * 3 + c], e));
+      }
+      if (lane < 3) dxo[(size_t)pair * 3 + lane] = lane == 0 ? sc[0] : (lane == 1 ? sc[1] : sc[2]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxJ; ++j) {
+    const int v = jw + j * l.nwj;
+    if (j < l.jp && v < V) {
+      int u = v - d % V;
+      if (u < 0) u += V;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) atomicAdd(p.dmask_raw + u * 3 + c, (double)dM[j][c]);
+    }
+  }
+  reduce_channels<8>(acc, p.dw_raw, d, scratch, l.nwj);            // [d][8]: dW[0..2][d], dWd[d][0..2], dbd[d], unused
+}
+
 static int check(const SgcnStem* p) {
   if (!p || !p->x || !p->maskmul || !p->W || !p->Wd) return set_error("sgcn_stem: null pointer");
   if (p->D != D) return set_error("sgcn_stem: the first unit has 64 output channels");
@@ -373,8 +518,18 @@ extern "C" int sgcn_stem_bwd(const SgcnStem* p, int mode, void* stream) {
   } else {
     if (!p->al || !p->be || !p->ga || !p->a2 || !p->b2 || !p->c2 || !p->dw_raw || !p->dmask_raw || !p->dx)
       return set_error("sgcn_stem_bwd(apply): null pointer");
-    if (l.jp <= 2) stem::stem_bwd_kernel<1, 2><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
-    else stem::stem_bwd_kernel<1, 3><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
+    const size_t smem = (size_t)2 * stem::kGB * p->V * stem::D * sizeof(float);
+    static thread_local bool configured = false;
+    if (!configured) {
+      const int cap = 2 * stem::kGB * 39 * stem::D * (int)sizeof(float);
+      cudaError_t e = cudaFuncSetAttribute(stem::stem_bwd_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stem::stem_bwd_apply_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e != cudaSuccess) return set_cuda_error("stem_bwd_apply smem attribute", e);
+      configured = true;
+    }
+    if (l.jp <= 2) stem::stem_bwd_apply_kernel<2><<<grid, threads, smem, (cudaStream_t)stream>>>(*p, per, rev);
+    else stem::stem_bwd_apply_kernel<3><<<grid, threads, smem, (cudaStream_t)stream>>>(*p, per, rev);
   }
   return check_launch("stem_bwd_kernel");
 }

@@ -13,3 +13,18 @@ for spec in "$@"; do
     -o gpurun_out/ncu_$i python tools/kernel_bench.py --only "$name" --layers ${NCU_LAYER:-64} --reps 1 > gpurun_out/ncu_$i.log 2>&1
 done
 tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench.json
+# optional extras, selected by environment variables
+if [ -n "$EXTRA_WORKLOADS" ]; then
+  for w in $EXTRA_WORKLOADS; do
+    timeout 300 python bench.py --workload $w > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
+  done
+fi
+if [ -n "$LAUNCH_LIST" ]; then
+  timeout 200 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/b_nograph.json 2>gpurun_out/b_nograph.err && \
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu.log 2>&1
+fi
+if [ -n "$TRAFFIC" ]; then   # ncu --set full of the 9 spatial-backward launches of one training step
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:spatial_bwd_kernel -s 27 -c 9 -f \
+    -o gpurun_out/ncu_spatial_bwd python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_traffic.log 2>&1
+fi
