@@ -258,6 +258,10 @@ def run_b200(args):
     torch.cuda.synchronize()
     ops.PROFILE = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # The eager step is host-bound (~0.3 s of Python for ~25 ms of kernels): without a head start the GPU idles between
+    # launches and every event pair would also time the host gap in front of its kernel.  A spin kernel keeps the stream
+    # busy while the host enqueues the whole step, so the events then measure back-to-back device execution.
+    torch.cuda._sleep(int(0.6 * getattr(torch.cuda.get_device_properties(dev), "clock_rate", 1.9e6) * 1e3))
     e0.record()
     if train:
         trainer.train_step(dev_x, dev_y)                     # eager (not the graph): per-call events need real launches

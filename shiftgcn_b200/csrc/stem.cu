@@ -324,9 +324,9 @@ __global__ void __launch_bounds__(832, 1) stem_bwd_kernel(const SgcnStem p, int 
 // two phases per chunk of kGB groups (no shared-memory atomics, no per-element warp reductions):
 //   phase A  thread = (joint v, channel d): loads g and h (coalesced), recomputes z and r from the staged x, keeps the
 //            parameter gradients in registers and leaves dz, dr [g][v][d] in shared memory
-//   phase B  warp = one (group g, joint w) at a time, lanes = channels d and d+32:
+//   phase B  thread = one output value (group g, joint w, channel c), serial over the 64 channels d:
 //            dx[g,w,c] = m[u,c] * sum_d dz[g,(u+d)%V,d] W[c,d]  +  sum_d dr[g,w,d] Wd[d,c],   u = (w-c) mod V
-//            -- conflict-free row gathers from shared memory (bank = d), one warp reduction per output value
+//            -- every lane starts its d loop at d = lane, so the row gathers are bank-conflict free (bank = d mod 32)
 constexpr int kGB = 8;
 
 template <int kMaxJ>
@@ -334,28 +334,30 @@ __global__ void __launch_bounds__(832, 1) stem_bwd_apply_kernel(const SgcnStem p
   extern __shared__ __align__(16) float dyn[];                     // dz [kGB][V][64], dr [kGB][V][64]
   __shared__ float sx[kGB * 40 * 3];
   __shared__ float smk[40 * 3];
+  __shared__ float sW[3 * D], sWd[3 * D];                          // W[c][d] and Wd[d][c] transposed to [c][d]
   __shared__ float scratch[16 * 8 * D];
   const Lay l = layout(p.V);
   const int V = p.V;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cb = warp / l.nwj, jw = warp - cb * l.nwj, d = cb * 32 + lane;
   float* sDz = dyn;
   float* sDr = dyn + (size_t)kGB * V * D;
   const long long g0 = (long long)(rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * gper;   // snake traversal
   const int ng = (int)((p.groups - g0) < gper ? (p.groups - g0) : gper);
-  // weights of this thread's channel d (phase A) and of the channel d ^ 32 of the other half (phase B needs both)
-  float wc[3], wd[3], wco[3], wdo[3];
+  float wc[3], wd[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     wc[c] = __ldg(p.W + c * D + d);
     wd[c] = __ldg(p.Wd + d * 3 + c);
-    wco[c] = __ldg(p.W + c * D + (d ^ 32));
-    wdo[c] = __ldg(p.Wd + (d ^ 32) * 3 + c);
   }
   for (int i = threadIdx.x; i < V * 3; i += blockDim.x) smk[i] = __ldg(p.maskmul + i);
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+    sW[i] = __ldg(p.W + i);
+    sWd[i] = __ldg(p.Wd + (i % D) * 3 + i / D);
+  }
   const float b = p.bias ? __ldg(p.bias + d) : 0.f, bd = p.bd ? __ldg(p.bd + d) : 0.f;
   const float a2 = __ldg(p.a2 + d), b2 = __ldg(p.b2 + d), c2 = __ldg(p.c2 + d);
-  const int lm0 = lane % V, lm1 = (lane + 32) % V;
+  const int lm0 = lane % V;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};         // dW[3], dWd[3], dbd, unused
   float dM[kMaxJ][3];
 #pragma unroll
@@ -429,26 +431,31 @@ __global__ void __launch_bounds__(832, 1) stem_bwd_apply_kernel(const SgcnStem p
     __syncthreads();
     // ---------------------------------------------------------------- phase B
     float* dxo = p.dx + (size_t)(g0 + gs) * V * 3;
-    for (int pair = warp; pair < n * V; pair += nwarps) {
+    for (int o = threadIdx.x; o < n * V * 3; o += blockDim.x) {
+      const int pair = o / 3, c = o - pair * 3;
       const int g = pair / V, w = pair - g * V;
+      int u = w - c;
+      if (u < 0) u += V;
       const float* dzg = sDz + (size_t)g * V * D;
-      const float* drw = sDr + ((size_t)g * V + w) * D;
-      const float dr0 = drw[lane], dr1 = drw[lane + 32];
-      float sc[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        int u = w - c;
-        if (u < 0) u += V;
-        int r0 = u + lm0, r1 = u + lm1;
-        if (r0 >= V) r0 -= V;
-        if (r1 >= V) r1 -= V;
-        // channel `lane` uses this thread's own weights when cb == 0, the other half's when cb == 1 (warp uniform)
-        const float a0 = dzg[r0 * D + lane], a1 = dzg[r1 * D + lane + 32];
-        const float t = cb == 0 ? fmaf(a0, wc[c], a1 * wco[c]) : fmaf(a0, wco[c], a1 * wc[c]);
-        const float e = cb == 0 ? fmaf(dr0, wd[c], dr1 * wdo[c]) : fmaf(dr0, wdo[c], dr1 * wd[c]);
-        sc[c] = warp_sum(fmaf(t, smk[u * 3 + c], e));
+      const float* drw = sDr + (size_t)pair * D;
+      const float* wrow = sW + c * D;
+      const float* wdrow = sWd + c * D;
+      float s_shift = 0.f, s_conv = 0.f;
+      int dd = lane, r = u + lm0;                                  // r = (u + dd) mod V
+      if (r >= V) r -= V;
+#pragma unroll 4
+      for (int i = 0; i < D; ++i) {
+        s_shift = fmaf(dzg[r * D + dd], wrow[dd], s_shift);
+        s_conv = fmaf(drw[dd], wdrow[dd], s_conv);
+        ++dd;
+        ++r;
+        if (r == V) r = 0;
+        if (dd == D) {
+          dd = 0;
+          r = u;
+        }
       }
-      if (lane < 3) dxo[(size_t)pair * 3 + lane] = lane == 0 ? sc[0] : (lane == 1 ? sc[1] : sc[2]);
+      dxo[o] = fmaf(s_shift, smk[u * 3 + c], s_conv);
     }
   }
 #pragma unroll
