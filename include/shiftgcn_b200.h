@@ -316,6 +316,10 @@ typedef struct SgcnSideBwd {
 } SgcnSideBwd;
 int sgcn_side_bwd(const SgcnSideBwd* p, void* stream);
 
+/* out[n, r, c] = g[n, c] * scale for every row r < rows_per_n: the gradient of the global mean over (T, V)
+ * (model/shift_gcn.py:212-214) written directly in the row layout */
+int sgcn_bcast_rows(const float* g, float* out, long long n, long long rows_per_n, int C, float scale, void* stream);
+
 /* stats[c][2] += {sum, sumsq} over rows */
 int sgcn_channel_stats(const float* x, double* stats, long long rows, int C, void* stream);
 /* the same over `groups` row groups of V rows, group g being group g*gs of x (the frames a strided 1x1 conv reads) */

@@ -650,6 +650,20 @@ __global__ void __launch_bounds__(256) relu_mask_grad_kernel(const float4* __res
   }
 }
 
+// out[n, r, c] = g[n, c] * scale for r in [0, rows_per_n): gradient of the global mean pooling (model/shift_gcn.py:212-214)
+// written straight into the row layout (autograd would expand, scale and copy: three passes over a full tensor)
+__global__ void __launch_bounds__(256) bcast_rows_kernel(const float4* __restrict__ g, float4* __restrict__ out,
+                                                         long long rows_per_n, int c4, float scale, long long total4) {
+  const long long per_n = rows_per_n * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / per_n;
+    const int c = (int)(i % c4);
+    float4 v = __ldg(g + n * c4 + c);
+    v.x *= scale, v.y *= scale, v.z *= scale, v.w *= scale;
+    out[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ launch geometry
 struct Geo {
   int threads, nchunks, per;
@@ -861,6 +875,20 @@ extern "C" int sgcn_relu_bn1d_bwd_stats(const float* g, const float* h, const fl
   relu_bn1d_bwd_stats_kernel<<<geo.grid, geo.threads, 0, (cudaStream_t)stream>>>(g, h, z, zmean, zinvstd, gh, vd_sums,
                                                                                 groups, geo.per, geo.nchunks, V, C, next_direction());
   return check_launch("relu_bn1d_bwd_stats_kernel");
+}
+
+extern "C" int sgcn_bcast_rows(const float* g, float* out, long long n, long long rows_per_n, int C, float scale,
+                               void* stream) {
+  if (!g || !out) return set_error("sgcn_bcast_rows: null pointer");
+  if (C < 4 || C % 4 != 0) return set_error("sgcn_bcast_rows: C must be a positive multiple of 4");
+  if (n <= 0 || rows_per_n <= 0) return 0;
+  const long long total4 = n * rows_per_n * (C / 4);
+  long long blocks = (total4 + 1023) / 1024;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  bcast_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)g, (float4*)out, rows_per_n, C / 4,
+                                                                       scale, total4);
+  return check_launch("bcast_rows_kernel");
 }
 
 extern "C" int sgcn_relu_mask_grad(const float* g, const float* y, float* out, long long numel, void* stream) {

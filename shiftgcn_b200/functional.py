@@ -11,13 +11,13 @@ Kernel schedule of one identity unit in training (a = one activation tensor pass
             BN + shift + 1x1 conv + ReLU (h -> q)             2a      sgcn_rowgemm  LERP / LINEAR
             output shift, BN2d sums of s                      1a      sgcn_tshift_fwd  mode 0
             shift + BN + residual + ReLU (-> y)               3a      sgcn_tshift_fwd  mode 1
-  backward  sums for bn2 / ypos_out                           3a      sgcn_tshift_bwd  mode 0
-            dpre = [q>0] * Shift^T(BN-bwd)                    4a      sgcn_tshift_bwd  mode 1
+  backward  sums for bn2 / ypos_out                           2a      sgcn_tshift_bwd  mode 0   (g_y arrives with its ReLU mask
+            dpre = [q>0] * Shift^T(BN-bwd)                    3a      sgcn_tshift_bwd  mode 1    applied, see _links: no y)
             dp = dpre * W_t                                   2a      sgcn_rowgemm  PLAIN / LINEAR
             dW_t                                              2a      sgcn_wgrad  TEMPORAL
             sums for bn (from dW_t, dbt: no tensor pass)      ~0      sgcn_tshift_in_bwd_sums
             gh = [h>0] * BN-bwd(Shift^T dp), BN1d + ypos_in   4a      sgcn_tshift_in_bwd  mode 1
-            g_x = spatial backward-data (+ both residuals)    6a      sgcn_rowgemm  DY / SPATIAL_BWD
+            g_x = spatial backward-data (+ both residuals)    5a      sgcn_rowgemm  DY / SPATIAL_BWD
             dW                                                3a      sgcn_wgrad  SPATIAL
 """
 import torch
@@ -617,3 +617,19 @@ class ConvUnitFn(torch.autograd.Function):
         return (s["gx"], s["dW"], s["dbias"], s["dmask"], s["dgamma"], s["dbeta"], rd["dWd"], rd["dbd"], rd["dgamma"],
                 rd["dbeta"], t["dgamma_a"], t["dbeta_a"], t["gx_in"], t["gy_in"], t["dWt"], t["dbt"], t["gx_out"],
                 t["gy_out"], t["dgamma_b"], t["dbeta_b"], rr["dWd"], rr["dbd"], rr["dgamma"], rr["dbeta"], None)
+
+
+class PoolRowsFn(torch.autograd.Function):
+    """Mean over the frames and joints of a row tensor (n, T, V, C) -> (n, C)  (model/shift_gcn.py:212-214).  The
+    backward writes the broadcast gradient once, in the row layout the last unit's backward kernels read (autograd's
+    own backward expands, scales and then copies: three full-tensor passes)."""
+
+    @staticmethod
+    def forward(ctx, rows):
+        ctx.shape = rows.shape
+        return rows.mean(dim=(1, 2))
+
+    @staticmethod
+    def backward(ctx, g):
+        n, T, V, C = ctx.shape
+        return ops.bcast_rows(g.contiguous().float(), T * V, 1.0 / (T * V)).view(n, T, V, C)

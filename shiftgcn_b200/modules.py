@@ -358,5 +358,9 @@ class Model(nn.Module):
             finally:
                 unit._in_link = unit._out_link = None
         c_new = x.size(1)
-        x = x.mean(dim=(2, 3)).view(N, M, c_new).mean(1)      # == view(N, M, C, T*V).mean(3).mean(1), stride-agnostic
+        if x.is_cuda and x.dtype == torch.float32 and c_new % 4 == 0 and x.permute(0, 2, 3, 1).is_contiguous():
+            x = FN.PoolRowsFn.apply(x.permute(0, 2, 3, 1))     # same mean; the gradient comes back in the row layout
+        else:
+            x = x.mean(dim=(2, 3))
+        x = x.view(N, M, c_new).mean(1)                       # == view(N, M, C, T*V).mean(3).mean(1), stride-agnostic
         return self.fc(x)

@@ -419,3 +419,14 @@ def side_bwd(P, sg, Wd, bd, gamma, invstd, mean_r, rows, training, sx=None, XX=N
                     training=1 if training else 0)
     _lib.check(lib.sgcn_side_bwd(ctypes.byref(p), _stream()), "side backward")
     return dict(dgamma=vec[0], dbeta=vec[1], dWd=dWd, dbd=vec[2], Wcat=Wcat, kvec=kvec)
+
+
+def bcast_rows(g, rows_per_n, scale):
+    """(n, C) -> (n, rows_per_n, C) with every row = g[n] * scale (gradient of a mean over the rows)"""
+    lib = _lib.load()
+    n, C = g.shape
+    out = torch.empty((n, rows_per_n, C), device=g.device, dtype=torch.float32)
+    if out.numel():
+        _launch("bcast_rows", 1, _nbytes(out), lib.sgcn_bcast_rows, _p(g, name="g"), _p(out), n, int(rows_per_n), C,
+                ctypes.c_float(scale), _stream())
+    return out
