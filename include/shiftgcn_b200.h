@@ -29,8 +29,10 @@ const char* sgcn_last_error(void);
 int sgcn_device_check(void);
 /* Traversal order of the full-tensor kernels (process-wide setting).  snake != 0: every kernel walks its
  * tiles in the opposite order of the kernel launched before it, so that it starts on the part of its inputs the
- * previous kernel touched last (still resident in the 126 MB L2); 0 (default): always ascending.  Results do not
- * depend on the order.  Returns the previous setting. */
+ * previous kernel touched last (still resident in the 126 MB L2); 0 (default): always ascending.  The call also
+ * restarts the alternation: after 1 the next kernel descends, after 2 it ascends (callers restart it at the top of
+ * every step so that all steps, and a captured CUDA graph, see the same orders).  Results do not depend on the
+ * order.  Returns the previous on/off setting. */
 int sgcn_set_traversal(int snake);
 /* tcgen05 descriptor self test (tests only): mode 0: D[128,N] = A[128,K] * B[N,K]^T; mode 1: D[128,N] = A[128,M]^T * B[128,N] */
 int sgcn_selftest_umma(const float* a, const float* b, float* d, int mode, int K, int N, int M, void* stream);

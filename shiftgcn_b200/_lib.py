@@ -109,6 +109,12 @@ SIGNATURES = {
 _lib = None
 
 
+def traversal_mode():
+    """SGCN_SNAKE: 0 = always ascending, 1 = snake (first kernel of a step descends, default), 2 = snake, first ascends"""
+    v = os.environ.get("SGCN_SNAKE", "1")
+    return int(v) if v in ("0", "1", "2") else 1
+
+
 def library_path():
     # SGCN_LIB: developer override for A/B runs of two builds of the same ABI
     return os.environ.get("SGCN_LIB") or _build.LIB_PATH
@@ -132,7 +138,7 @@ def load():
         fn.restype = ctypes.c_int
         fn.argtypes = argtypes
     # snake traversal of the full-tensor kernels (on unless SGCN_SNAKE=0), see include/shiftgcn_b200.h
-    lib.sgcn_set_traversal(0 if os.environ.get("SGCN_SNAKE", "1") == "0" else 1)
+    lib.sgcn_set_traversal(traversal_mode())
     _lib = lib
     return lib
 

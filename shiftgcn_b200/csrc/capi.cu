@@ -53,7 +53,7 @@ void mark_forward() { g_last_rev.store(0, std::memory_order_relaxed); }
 }  // namespace sgcn
 
 extern "C" int sgcn_set_traversal(int snake) {
-  sgcn::g_last_rev.store(0);
+  sgcn::g_last_rev.store(snake == 2 ? 1 : 0);                  // 1: the next kernel descends; 2: it ascends
   return sgcn::g_snake.exchange(snake ? 1 : 0);
 }
 

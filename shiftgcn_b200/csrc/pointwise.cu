@@ -30,9 +30,21 @@ constexpr int kMaxWarps = 20;     // ceil(V/2) warps, V <= 40
 #ifndef SGCN_WALKER_MINBLOCKS
 #define SGCN_WALKER_MINBLOCKS 2   // register cap of the walkers: 65536 / (640 * MINBLOCKS)
 #endif
-constexpr int kUnroll = 4;        // frames in flight per thread (kernels with >= 3 loads per frame)
-constexpr int kUnrollWide = 8;    // ... with 2 loads per frame
-constexpr int kUnrollMax = 16;    // ... with a single load per frame (read-only statistics passes are latency bound)
+#ifndef SGCN_UNROLL
+#define SGCN_UNROLL 4
+#endif
+#ifndef SGCN_UNROLL_WIDE
+#define SGCN_UNROLL_WIDE 8
+#endif
+#ifndef SGCN_UNROLL_MAX
+#define SGCN_UNROLL_MAX 16
+#endif
+#ifndef SGCN_GEOM_MULT
+#define SGCN_GEOM_MULT 8          // grid ~ this many blocks per SM (about two waves of the resident blocks)
+#endif
+constexpr int kUnroll = SGCN_UNROLL;           // frames in flight per thread (kernels with >= 3 loads per frame)
+constexpr int kUnrollWide = SGCN_UNROLL_WIDE;  // ... with 2 loads per frame
+constexpr int kUnrollMax = SGCN_UNROLL_MAX;    // ... with a single load per frame (read-only statistics passes are latency bound)
 
 // ------------------------------------------------------------------------------------------------ helpers
 struct Col {            // the walker's identity
@@ -141,12 +153,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) bn_res_
     const float* rp = res ? res + o0 : zp;                 // no residual: read z twice (L1 hit) and ignore it
     const float rsel = res ? 1.f : 0.f;
     float* hp = h + o0;
-    for (int g = 0; g < ng; g += kUnroll) {
-      float zv[kUnroll], rv[kUnroll];
-      load_frames<kUnroll, PITCH>(zv, zp, g, ng, pitch);
-      load_frames<kUnroll, PITCH>(rv, rp, g, ng, pitch);
+    for (int g = 0; g < ng; g += kUnrollWide) {
+      float zv[kUnrollWide], rv[kUnrollWide];
+      load_frames<kUnrollWide, PITCH>(zv, zp, g, ng, pitch);
+      load_frames<kUnrollWide, PITCH>(rv, rp, g, ng, pitch);
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u)
+      for (int u = 0; u < kUnrollWide; ++u)
         if (g + u < ng) {
           float y = fmaf(rv[u], rsel, fmaf(zv[u], a, b));
           if (relu) y = fmaxf(y, 0.f);
@@ -171,7 +183,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
   const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
   const float sc = MODE == 1 ? __ldg(p.scale + k.c) : 0.f, sh = MODE == 1 ? __ldg(p.shift + k.c) : 0.f;
   const int to0 = k.chunk * tper, to1 = min(To, to0 + tper);
-  constexpr int U = MODE == 0 ? kUnrollMax : kUnroll;   // the statistics pass has one load per frame: 16 in flight
+  // loads per frame: statistics pass 1 (16 frames in flight), stride-1 apply 2 (8), strided apply 3 (4)
+  constexpr int U = MODE == 0 ? kUnrollMax : (S1 ? kUnrollWide : kUnroll);
   float acc[2] = {0.f, 0.f};
   for (int v = k.warp; v < V; v += k.nw) {
     const float* qb = p.q + ((size_t)k.n * Ti * V + v) * C + k.c;
@@ -301,6 +314,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
   const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
   const BwdCh B = bwd_of(p, k.c);
   const int relu = RELU ? 1 : 0;
+  constexpr int U = RELU ? kUnroll : kUnrollWide;             // 3 or 2 loads per frame
   const int t0 = k.chunk * tper, t1 = min(T, t0 + tper);
   float acc[1] = {0.f};
   for (int v = k.warp; v < V; v += k.nw) {
@@ -317,18 +331,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
       ds_prev = ds_eval(inside(to, T), ldrow(gb, to, T, pitch), ldrow(yb, to, T, pitch), relu,
                         tap(qb, t0 - 1, T, pitch), qa, L, B);
     }
-    for (int t = t0; t < t1; t += kUnroll) {
-      float q1[kUnroll], gv[kUnroll], yv[kUnroll];
-      load_frames<kUnroll, PITCH>(q1, qb, t + 1, T, pitch);
-      load_frames<kUnroll, PITCH>(gv, gb, t - L.y1, T, pitch);      // frames outside [0, T) are masked by ds_eval
+    for (int t = t0; t < t1; t += U) {
+      float q1[U], gv[U], yv[U];
+      load_frames<U, PITCH>(q1, qb, t + 1, T, pitch);
+      load_frames<U, PITCH>(gv, gb, t - L.y1, T, pitch);      // frames outside [0, T) are masked by ds_eval
       if (RELU) {                                                   // compile time, see tshift_bwd_stats_kernel
-        load_frames<kUnroll, PITCH>(yv, yb, t - L.y1, T, pitch);
+        load_frames<U, PITCH>(yv, yb, t - L.y1, T, pitch);
       } else {
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) yv[u] = 1.f;
+        for (int u = 0; u < U; ++u) yv[u] = 1.f;
       }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u)
+      for (int u = 0; u < U; ++u)
         if (t + u < t1) {
           const int to = t + u - L.y1;
           const float ds = ds_eval((unsigned)to < (unsigned)T, gv[u], yv[u], relu, qa, q1[u], L, B);
@@ -674,7 +688,7 @@ static Geo geometry(int C, int V, long long outer, long long len, int min_per) {
   Geo g;
   g.threads = 32 * ceil_div(V, 2);
   const long long base = (long long)(C / 32) * (outer > 0 ? outer : 1);
-  const long long want = (long long)num_sms() * 8;            // ~2 waves of 4 resident blocks per SM
+  const long long want = (long long)num_sms() * SGCN_GEOM_MULT;   // ~2 waves of 4 resident blocks per SM
   long long nch = (want + base - 1) / base;
   const long long max_ch = (len + min_per - 1) / min_per;
   if (nch > max_ch) nch = max_ch;

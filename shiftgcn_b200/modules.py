@@ -14,6 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as FN
+from . import ops
 from .shift import Shift
 
 FUSED_CHANNELS = (64, 128, 256)
@@ -347,6 +348,7 @@ class Model(nn.Module):
         """l1..l10, pooling over (T, V) and persons, fc (reference :200-216); x: logical (N*M, C, T, V), channels-last"""
         # consecutive units exchange ReLU-masked gradients (functional._links): one dict per unit boundary, attached
         # only for the duration of the unit's forward call so that a unit used on its own never sees a stale link
+        ops.restart_traversal()
         links = [dict(masked=False) for _ in range(9)] if torch.is_grad_enabled() else None
         for i in range(1, 11):
             unit = getattr(self, f"l{i}")

@@ -74,6 +74,11 @@ def set_traversal(snake):
     return bool(_lib.load().sgcn_set_traversal(1 if snake else 0))
 
 
+def restart_traversal():
+    """restart the snake alternation (top of every step: all steps and a captured graph see the same tile orders)"""
+    _lib.load().sgcn_set_traversal(_lib.traversal_mode())
+
+
 def groups_per_tile(V):
     if V < 25 or V > 40:
         raise RuntimeError(f"shiftgcn_b200 fused kernels support 25 <= num_point <= 40, got {V}")
