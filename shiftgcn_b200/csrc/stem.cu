@@ -14,7 +14,7 @@
 //        mode 1  h, and the per-channel statistics of h the temporal unit's first BatchNorm needs
 //   bwd  mode 0  gm = g*[h>0]; BatchNorm backward sums per (v,d) and per d
 //        mode 1  dz, dr from the finalised tables; dW, dWd, dMask accumulate in registers over the whole walk, dx
-//                through shared-memory atomics (shift path) and warp reductions (conv path)
+//                in a second phase per chunk from dz / dr left in shared memory (no atomics)
 #include "capi_internal.h"
 #include "common.cuh"
 #include "pointwise.h"
@@ -175,14 +175,13 @@ __global__ void __launch_bounds__(832, 1) stem_fwd_kernel(const SgcnStem p, int 
   }
 }
 
-// ------------------------------------------------------------------------------------------------ backward
-// One pass over the block's groups PER JOINT the thread owns (the per-joint constants and accumulators of all joints
-// at once do not fit in registers; x is tiny and is simply staged again).
-template <int MODE, int kMaxJ>
-__global__ void __launch_bounds__(832, 1) stem_bwd_kernel(const SgcnStem p, int gper, int rev) {
+// ------------------------------------------------------------------------------------------------ backward, statistics
+// gm = g*[h>0]; BatchNorm backward sums per (v,d) (of z) and per d (of the conv output r), both recomputed from x.
+// One pass over the block's groups PER JOINT the thread owns (x is tiny and is simply staged again).
+template <int kMaxJ>
+__global__ void __launch_bounds__(832, 1) stem_bwd_stats_kernel(const SgcnStem p, int gper, int rev) {
   __shared__ float sx[kGS * 40 * 3];
-  __shared__ float sdx[kGS * 40 * 3];
-  __shared__ float scratch[16 * 8 * D];
+  __shared__ float scratch[16 * 2 * D];
   const Lay l = layout(p.V);
   const int V = p.V;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,16 +195,8 @@ __global__ void __launch_bounds__(832, 1) stem_bwd_kernel(const SgcnStem p, int 
     wd[c] = __ldg(p.Wd + d * 3 + c);
   }
   const float b = p.bias ? __ldg(p.bias + d) : 0.f, bd = p.bd ? __ldg(p.bd + d) : 0.f;
-  float a2 = 0.f, b2 = 0.f, c2 = 0.f, m2 = 0.f, i2 = 0.f;
-  if (MODE == 0) {
-    m2 = __ldg(p.mean2 + d);
-    i2 = __ldg(p.invstd2 + d);
-  } else {
-    a2 = __ldg(p.a2 + d);
-    b2 = __ldg(p.b2 + d);
-    c2 = __ldg(p.c2 + d);
-  }
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};         // mode 0: {sum gm, sum gm*rhat}; mode 1: dW[3], dWd[3], dbd
+  const float m2 = __ldg(p.mean2 + d), i2 = __ldg(p.invstd2 + d);
+  float acc[2] = {0.f, 0.f};                                       // {sum gm, sum gm*rhat}
 
 #pragma unroll 1
   for (int j = 0; j < l.jp; ++j) {
@@ -215,25 +206,19 @@ __global__ void __launch_bounds__(832, 1) stem_bwd_kernel(const SgcnStem p, int 
     int u = v - d % V;
     if (u < 0) u += V;
     int xo[3];
-    float mk[3], mw[3], dM[3] = {0.f, 0.f, 0.f};
+    float mw[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       xo[c] = ((u + c) % V) * 3 + c;
-      mk[c] = __ldg(p.maskmul + u * 3 + c);
-      mw[c] = mk[c] * wc[c];
+      mw[c] = __ldg(p.maskmul + u * 3 + c) * wc[c];
     }
     const int f = v * D + d;
-    // mode 0: mean / invstd of z; mode 1: dz = k0*gm + k1*z + k2
-    const float k0 = MODE == 0 ? __ldg(p.mean1 + f) : __ldg(p.al + f);
-    const float k1 = MODE == 0 ? __ldg(p.invstd1 + f) : __ldg(p.be + f);
-    const float k2 = MODE == 0 ? 0.f : __ldg(p.ga + f);
+    const float k0 = __ldg(p.mean1 + f), k1 = __ldg(p.invstd1 + f);   // mean / invstd of z
     float s0 = 0.f, s1 = 0.f;
     for (int gs = 0; gs < ng; gs += kGS) {
       const int n = min(kGS, ng - gs);
       __syncthreads();
       stage_x(p, sx, g0 + gs, n);
-      if (MODE == 1)
-        for (int i = threadIdx.x; i < n * V * 3; i += blockDim.x) sdx[i] = 0.f;
       __syncthreads();
       if (own) {
         const float* xs = sx + xo[0];
@@ -252,71 +237,23 @@ __global__ void __launch_bounds__(832, 1) stem_bwd_kernel(const SgcnStem p, int 
           for (int q = 0; q < kUn; ++q)
             if (gb + q < n) {
               const int o = (gb + q) * V * 3;
-              const float x0 = xs[o], x1 = xs[o + o1], x2 = xs[o + o2];
-              const float p0 = xp[o], p1 = xp[o + 1], p2 = xp[o + 2];
-              const float z = fmaf(x0, mw[0], fmaf(x1, mw[1], fmaf(x2, mw[2], b)));
-              const float r = fmaf(p0, wd[0], fmaf(p1, wd[1], fmaf(p2, wd[2], bd)));
+              const float z = fmaf(xs[o], mw[0], fmaf(xs[o + o1], mw[1], fmaf(xs[o + o2], mw[2], b)));
+              const float r = fmaf(xp[o], wd[0], fmaf(xp[o + 1], wd[1], fmaf(xp[o + 2], wd[2], bd)));
               const float gm = hv[q] > 0.f ? gv[q] : 0.f;
-              if (MODE == 0) {
-                s0 += gm;
-                s1 = fmaf(gm, (z - k0) * k1, s1);
-                acc[0] += gm;
-                acc[1] = fmaf(gm, (r - m2) * i2, acc[1]);
-              } else {
-                const float dz = fmaf(k0, gm, fmaf(k1, z, k2));
-                const float dr = fmaf(a2, gm, fmaf(b2, r, c2));
-                // Linear_weight / Feature_Mask gradients (autograd of :128-131)
-                acc[0] = fmaf(x0 * mk[0], dz, acc[0]);
-                acc[1] = fmaf(x1 * mk[1], dz, acc[1]);
-                acc[2] = fmaf(x2 * mk[2], dz, acc[2]);
-                const float e0 = dz * wc[0], e1 = dz * wc[1], e2 = dz * wc[2];     // dxm[g,u,c] contributions
-                dM[0] = fmaf(e0, x0, dM[0]);
-                dM[1] = fmaf(e1, x1, dM[1]);
-                dM[2] = fmaf(e2, x2, dM[2]);
-                // down conv weight / bias gradients
-                acc[3] = fmaf(p0, dr, acc[3]);
-                acc[4] = fmaf(p1, dr, acc[4]);
-                acc[5] = fmaf(p2, dr, acc[5]);
-                acc[6] += dr;
-                // dx: shift path scatters to row (u+c)%V, conv path reduces over the warp's 32 channels into row v
-                atomicAdd(sdx + o + xo[0], e0 * mk[0]);
-                atomicAdd(sdx + o + xo[1], e1 * mk[1]);
-                atomicAdd(sdx + o + xo[2], e2 * mk[2]);
-                const float r0 = warp_sum(dr * wd[0]), r1 = warp_sum(dr * wd[1]), r2 = warp_sum(dr * wd[2]);
-                if (lane == 0) {
-                  atomicAdd(sdx + o + v * 3, r0);
-                  atomicAdd(sdx + o + v * 3 + 1, r1);
-                  atomicAdd(sdx + o + v * 3 + 2, r2);
-                }
-              }
+              s0 += gm;
+              s1 = fmaf(gm, (z - k0) * k1, s1);
+              acc[0] += gm;
+              acc[1] = fmaf(gm, (r - m2) * i2, acc[1]);
             }
         }
       }
-      if (MODE == 1) {
-        __syncthreads();
-        float* dst = p.dx + (size_t)(g0 + gs) * V * 3;
-        if (j == 0)
-          for (int i = threadIdx.x; i < n * V * 3; i += blockDim.x) dst[i] = sdx[i];
-        else
-          for (int i = threadIdx.x; i < n * V * 3; i += blockDim.x) dst[i] += sdx[i];
-      }
     }
     if (own) {
-      if (MODE == 0) {
-        atomicAdd(p.vd_sums + 2 * (size_t)f, (double)s0);
-        atomicAdd(p.vd_sums + 2 * (size_t)f + 1, (double)s1);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) atomicAdd(p.dmask_raw + u * 3 + c, (double)dM[c]);
-      }
+      atomicAdd(p.vd_sums + 2 * (size_t)f, (double)s0);
+      atomicAdd(p.vd_sums + 2 * (size_t)f + 1, (double)s1);
     }
   }
-  if (MODE == 0) {
-    const float a[2] = {acc[0], acc[1]};
-    reduce_channels<2>(a, p.r_sums, d, scratch, l.nwj);
-  } else {
-    reduce_channels<8>(acc, p.dw_raw, d, scratch, l.nwj);          // [d][8]: dW[0..2][d], dWd[d][0..2], dbd[d], unused
-  }
+  reduce_channels<2>(acc, p.r_sums, d, scratch, l.nwj);
 }
 
 // ------------------------------------------------------------------------------------------------ backward, apply
@@ -520,8 +457,8 @@ extern "C" int sgcn_stem_bwd(const SgcnStem* p, int mode, void* stream) {
   if (mode == 0) {
     if (!p->mean1 || !p->invstd1 || !p->mean2 || !p->invstd2 || !p->vd_sums || !p->r_sums)
       return set_error("sgcn_stem_bwd(stats): null pointer");
-    if (l.jp <= 2) stem::stem_bwd_kernel<0, 2><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
-    else stem::stem_bwd_kernel<0, 3><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
+    if (l.jp <= 2) stem::stem_bwd_stats_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
+    else stem::stem_bwd_stats_kernel<3><<<grid, threads, 0, (cudaStream_t)stream>>>(*p, per, rev);
   } else {
     if (!p->al || !p->be || !p->ga || !p->a2 || !p->b2 || !p->c2 || !p->dw_raw || !p->dmask_raw || !p->dx)
       return set_error("sgcn_stem_bwd(apply): null pointer");

@@ -163,9 +163,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
       const long long g0 = tile * G;
       const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
       const long long use = j / NG;
-      if (use > 0) mbar_wait(&bar_free[grp], (uint32_t)((use - 1) & 1));   // the MMAs of the previous use are done
+      // the MMAs of the previous use of this stage must be done before it is overwritten.  SPATIAL stages everything
+      // through registers, so it waits only in front of its first shared-memory store -- the first batch of global
+      // loads is already in flight while the tensor core drains the stage.
+      // TEMPORAL does the same with the register-staged B operand: its first batch of loads is issued, then the wait
+      // and the cp.async copy of A (`stage_ready`).
+      if (MODE == WG_PLAIN && use > 0) mbar_wait(&bar_free[grp], (uint32_t)((use - 1) & 1));
+      bool a_pending = MODE == WG_TEMPORAL;
 
-      if (MODE == WG_TEMPORAL || MODE == WG_PLAIN) {
+      auto issue_a = [&]() {
         // ---- A = rows as they are: 16-byte cp.async pieces straight into the swizzled blocks (the tensor core reads
         //      fp32 bit patterns as TF32).  PLAIN: row group g of the tile comes from group (g0+g)*a_gs (strided 1x1 conv)
         {
@@ -183,7 +189,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
           }
           cp_async_commit();
         }
-      }
+      };
+      auto stage_ready = [&]() {                             // TEMPORAL: called in front of the first store of a tile
+        if (a_pending) {
+          if (use > 0) mbar_wait(&bar_free[grp], (uint32_t)((use - 1) & 1));
+          issue_a();
+          a_pending = false;
+        }
+      };
+      if (MODE == WG_PLAIN) issue_a();
       if (MODE == WG_PLAIN) {
         // ---- B = rows as they are
         constexpr int ppr = CB >> 2;
@@ -235,6 +249,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
                 for (int k = 0; k <= G; ++k) L[b][sl][k] = __ldg(src + k * (V * CB) + dv);
               }
             }
+            stage_ready();
 #pragma unroll
             for (int b = 0; b < NBT; ++b) {
               const uint32_t dst = sB32 + (blk0 + b) * (uint32_t)BLK + toff;
@@ -287,6 +302,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
               }
             }
           }
+          stage_ready();
 #pragma unroll
           for (int b = 0; b < NBT; ++b) {
             const uint32_t dst = sB32 + (blk0 + b) * (uint32_t)BLK + toff;
@@ -354,6 +370,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
               for (int g = 0; g < G; ++g) val[b][sl][g] = __ldg(src + (kFull ? g : min(g, ng - 1)) * gstride + sv * CA);
             }
           }
+          if (blk0 == 0 && use > 0) mbar_wait(&bar_free[grp], (uint32_t)((use - 1) & 1));
 #pragma unroll
           for (int b = 0; b < NB; ++b) {
             const uint32_t dst = sA32 + (blk0 + b) * (uint32_t)BLK + (((uint32_t)lane & 7u) << 2);
