@@ -122,3 +122,17 @@ def test_premasked_gradients_between_units_change_nothing(cuda_device, num_class
             continue
         assert (a - b).abs().max().item() <= 2e-3 * scale, k
         assert rel_l2(b, a) < 1e-3, k
+
+
+def test_pool_rows_matches_autograd_mean(cuda_device):
+    """PoolRowsFn: mean over (T, V) of a row tensor; its backward writes the broadcast gradient with sgcn_bcast_rows"""
+    from shiftgcn_b200 import functional as FN
+    g = torch.Generator().manual_seed(6)
+    rows = torch.randn(6, 7, 25, 64, generator=g).to(cuda_device)
+    go = torch.randn(6, 64, generator=g).to(cuda_device)
+    a = rows.clone().requires_grad_(True)
+    FN.PoolRowsFn.apply(a).backward(go)
+    b = rows.clone().requires_grad_(True)
+    b.mean(dim=(1, 2)).backward(go)
+    assert torch.allclose(FN.PoolRowsFn.apply(rows), rows.mean(dim=(1, 2)))
+    assert a.grad.shape == b.grad.shape and torch.allclose(a.grad, b.grad, rtol=1e-6, atol=1e-9)
