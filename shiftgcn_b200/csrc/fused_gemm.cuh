@@ -438,6 +438,24 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
       const int buf = ti & 1;
       int wv = warp;                                               // opaque per tile: keeps the per-(pair, chunk) address
       asm volatile("" : "+r"(wv));                                 // set from being hoisted out of the tile loop (registers)
+      // ROT_FUSED: the BatchNorm tables and the residual rows of a 64-channel chunk do not depend on the accumulator;
+      // they are requested before the wait for it (chunk 0) / before the TMEM copy (later chunks) instead of right in
+      // front of their use, where every (joint, half) pair paid a full global-load latency.
+      constexpr int kPF = EPI == EPI_ROT_FUSED ? C::kJ : 1;
+      float scp[kPF], shp[kPF], rvp[kPF][G];
+      auto prefetch = [&](int nc) {
+        const int d = nc * 64 + (wv & 1) * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < kPF; ++k) {
+          const int v = min((k * kEpiWarps + wv) >> 1, V - 1);
+          scp[k] = __ldg(p.epi_a + v * N + d);
+          shp[k] = __ldg(p.epi_b + v * N + d);
+          const float* rptr = res + row0 * N + d + v * N;
+#pragma unroll
+          for (int g = 0; g < G; ++g) rvp[k][g] = __ldg(rptr + min(g, ng - 1) * V * N);
+        }
+      };
+      if constexpr (EPI == EPI_ROT_FUSED) prefetch(0);
       if (warp < 8) {    // only the TMEM readers (who gate acc_free) wait for the accumulator, see spatial_bwd.cu
         mbar_wait(&acc_full[buf], (uint32_t)((ti >> 1) & 1));
         tc_fence_after();
@@ -498,8 +516,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
           epi_sync();                                              // staging is reused by the next step / tile
         }
       } else {
-#pragma unroll
+      // ROT_RAW keeps per-chunk statistics in registers (compile-time indices: full unroll); ROT_FUSED has no such
+      // arrays and, for four chunks, stays rolled so that only one chunk's prefetch is live (measured: 246 -> 178 us
+      // at N = 256; two chunks are faster unrolled, 204 vs 246 us)
+      constexpr int kNcUnroll = (EPI == EPI_ROT_FUSED && NCH > 2) ? 1 : NCH;
+#pragma unroll kNcUnroll
       for (int nc = 0; nc < NCH; ++nc) {
+        if constexpr (EPI == EPI_ROT_FUSED)
+          if (nc > 0) prefetch(nc);
         if (warp < 8) {   // TMEM -> staging: lane quarter (warp & 3), column half (warp >> 2)
           const int qd = warp & 3, hf = warp >> 2;
           const uint32_t row = (uint32_t)(qd * 32 + lane);
@@ -539,12 +563,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
                 const uint32_t sb = stb + (uint32_t)u * 256u, u16 = (uint32_t)u << 4;
                 float sc = 0.f, sh = 0.f, rv[G];
                 if (EPI == EPI_ROT_FUSED) {
-                  sc = __ldg(p.epi_a + v * N + d);
-                  sh = __ldg(p.epi_b + v * N + d);
-                  const float* rptr = res + row0 * N + d + v * N;
+                  sc = scp[EPI == EPI_ROT_FUSED ? k : 0];
+                  sh = shp[EPI == EPI_ROT_FUSED ? k : 0];
 #pragma unroll
-                  for (int g = 0; g < G; ++g)
-                    if (kFull || g < ng) rv[g] = __ldg(rptr + g * V * N);
+                  for (int g = 0; g < G; ++g) rv[g] = rvp[EPI == EPI_ROT_FUSED ? k : 0][g];
                 }
 #pragma unroll
                 for (int g = 0; g < G; ++g)

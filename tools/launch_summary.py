@@ -16,7 +16,9 @@ for n, x in zip(names[a:b], t[a:b]):
     agg[n][0] += 1
     agg[n][1] += x
 tot = sum(v[1] for v in agg.values())
-ours = sum(v[1] for k, v in agg.items() if "sgcn::" in k)
-print(f"# {b - a} launches in one step, {tot / 1e3:.2f} ms serialised; sgcn:: kernels {ours / 1e3:.2f} ms ({ours / tot * 100:.1f}%)")
+OURS = ("sgcn::", "sb::", "fg::", "stem::", "side::")   # ncu prints the innermost namespace of libshiftgcn_b200.so kernels
+ours = sum(v[1] for k, v in agg.items() if any(t in k for t in OURS))
+n_ours = sum(v[0] for k, v in agg.items() if any(t in k for t in OURS))
+print(f"# {b - a} launches in one step, {tot / 1e3:.2f} ms serialised; libshiftgcn_b200 kernels: {n_ours} launches, {ours / 1e3:.2f} ms ({ours / tot * 100:.1f}%)")
 for n, (c, x) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(sys.argv[3]) if len(sys.argv) > 3 else 70]:
     print(f"{x / tot * 100:5.1f}% {x / 1e3:8.2f} ms n={c:3d} avg={x / c:8.1f} us  {n}")
