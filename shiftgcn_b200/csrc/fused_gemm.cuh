@@ -318,7 +318,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         }
       };
       const uint32_t opb = sOp + (uint32_t)(lane & 3) * 4u;
-      for (int j = 0; j < RS; ++j) {
+      // RS - 1 raw chunks in flight.  ONE barrier per chunk: it says that every thread's pieces of chunk q have landed
+      // and that every thread is done with chunk q - 1, whose raw stage is refilled right away with chunk q + RS - 1.
+      for (int j = 0; j < RS - 1; ++j) {
         if (j < total_chunks) issue(j);
         cp_async_commit();
       }
@@ -326,8 +328,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         const int ti = q / KC, kc = q - ti * KC;
         const long long g0 = tile_of(ti) * G;
         const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
-        cp_wait<RS - 1>();
-        bld_sync();                                                // every thread's pieces of chunk q have landed
+        cp_wait<RS - 2>();
+        bld_sync();
+        if (q + RS - 1 < total_chunks) issue(q + RS - 1);
+        cp_async_commit();
         const int os = q % OS;
         if (q >= OS) mbar_wait(&op_free[os], (uint32_t)(((q / OS) - 1) & 1));
         const uint32_t raw = sRaw + (uint32_t)(q % RS) * C::kRawBytes + (uint32_t)lane * 4u;
@@ -414,9 +418,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         }
         fence_proxy_async();
         mbar_arrive(&op_full[os]);
-        bld_sync();                                                // raw stage q % RS is free again
-        if (q + RS < total_chunks) issue(q + RS);
-        cp_async_commit();
       }
     }
   } else {
