@@ -166,3 +166,53 @@ class FlatSGDTrainer:
         self._static_y.copy_(label, non_blocking=True)
         self._graph.replay()
         return self._static_loss
+
+
+class HostPrefetcher:
+    """Double-buffered pinned-host -> device staging on a side stream, so that the copy of batch i+1 overlaps the step
+    on batch i.  (The reference moves every batch synchronously inside the training loop, ``main.py:400-414``:
+    ``data.float().cuda(...)`` right before the forward pass.)
+
+        pf = HostPrefetcher(device)
+        pf.put(x0, y0)
+        for i in range(n):
+            x, y = pf.get()                 # current stream waits for the copy of batch i
+            if i + 1 < n: pf.put(x1, y1)    # starts once the work enqueued so far has released the other slot
+            step(x, y)
+    """
+
+    def __init__(self, device, slots=2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.slots = [None] * slots
+        self.events = [None] * slots
+        self._w = self._r = 0
+
+    def put(self, *host_tensors):
+        k = self._w % len(self.slots)
+        self._w += 1
+        if self.stream is None:                                   # CPU (tests of the host logic): plain copies
+            self.slots[k] = tuple(t.clone() for t in host_tensors)
+            return
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)                              # the slot's previous consumer has been enqueued before
+        with torch.cuda.stream(self.stream):
+            old = self.slots[k]
+            if old is None or any(o.shape != t.shape or o.dtype != t.dtype for o, t in zip(old, host_tensors)) \
+                    or len(old) != len(host_tensors):
+                old = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host_tensors)
+            for o, t in zip(old, host_tensors):
+                o.copy_(t, non_blocking=True)
+            self.slots[k] = old
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            self.events[k] = ev
+
+    def get(self):
+        if self._r >= self._w:
+            raise RuntimeError("HostPrefetcher.get() without a matching put()")
+        k = self._r % len(self.slots)
+        self._r += 1
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.events[k])
+        return self.slots[k]

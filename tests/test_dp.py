@@ -134,3 +134,19 @@ def test_flat_views_and_reference_sgd_semantics():
         assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), n
     assert reference_weight_decay("l1.gcn1.Linear_weight") == 1e-3 and reference_weight_decay("l1.gcn1.Feature_Mask") == 0.0
     assert reference_weight_decay("l1.tcn1.bn.weight") == 1e-4
+
+
+def test_host_prefetcher_order_and_errors():
+    """HostPrefetcher (CPU path: no streams): batches come back in put() order, slots are reused, get() needs a put()"""
+    import pytest
+    from shiftgcn_b200.dp import HostPrefetcher
+    pf = HostPrefetcher("cpu")
+    batches = [(torch.full((3,), float(i)), torch.tensor([i])) for i in range(5)]
+    pf.put(*batches[0])
+    for i in range(5):
+        x, y = pf.get()
+        if i + 1 < 5:
+            pf.put(*batches[i + 1])
+        assert torch.equal(x, batches[i][0]) and torch.equal(y, batches[i][1])
+    with pytest.raises(RuntimeError):
+        pf.get()
