@@ -14,7 +14,9 @@ from rank 0.  Keys beyond the base contract:
   e2e           same metric through the public nn.Module API with HOST inputs: pinned H2D copy of every batch and a
                 D2H read of the loss inside the timed region
 ``--impl reference`` times the reference's CPU implementation of the path (the oracle port; the reference itself is
-Python and cannot travel to the GPU box) on the same workload, bounded per step.
+Python and cannot travel to the GPU box) on the same workload, bounded per step.  ``--impl reference-gpu`` is the
+informational second baseline BASELINE.json asks for: the reference's PyTorch path (oracle/model_ref.py) with the
+reference's own compiled ``shift_cuda`` kernels (oracle/_ref) on one B200.
 """
 import argparse
 import json
@@ -155,6 +157,59 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def run_reference_gpu(args):
+    """--impl reference-gpu (informational second baseline of BASELINE.json's north_star): the reference's PyTorch
+    path -- restated module by module in oracle/model_ref.py (index_select gathers, einsum, BatchNorm, cuDNN 1x1
+    convs, torch.optim.SGD) -- on ONE B200 with the reference's OWN compiled shift_cuda kernels (oracle/_ref, built
+    from /root/reference's sources).  None of this repository's kernels run in this arm."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import build_ref_ext, model_ref, shift_torch
+    if build_ref_ext.built_library() is None:
+        emit({"impl": "reference-gpu", "unavailable": "oracle/_ref/shift_cuda_ref*.so was not built (needs /root/reference)"})
+        return
+    shift_torch.REF_EXT = build_ref_ext.load()
+    num_class, V, M, T, batch, train, algo_mb, _ = WORKLOADS[args.workload]
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    torch.manual_seed(1)
+    model = model_ref.RefModel(num_class=num_class, num_point=V, num_person=M).to(dev).train(train)
+    x = torch.randn(batch, 3, T, V, M, device=dev)
+    y = torch.randint(0, num_class, (batch,), device=dev)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, nesterov=True) if train else None
+
+    def step():
+        if train:
+            opt.zero_grad(set_to_none=True)
+            torch.nn.functional.cross_entropy(model(x), y).backward()
+            opt.step()
+        else:
+            with torch.no_grad():
+                model(x)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    peak, peak_src = _peaks()
+    emit({"impl": "reference-gpu", "metric": "Shift-GCN fwd+bwd samples/sec (NTU 3x300x25x2)" if train else f"Shift-GCN samples/sec ({args.workload})",
+          "value": batch / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+          "ms_per_step": ms, "higher_is_better": True, "dtype": "f32 (cuDNN convolutions may use TF32, torch default)",
+          "data": "synthetic", "config": {"workload": args.workload, "per_gpu_batch": batch,
+                                          "note": "reference modules restated in oracle/model_ref.py + the reference's compiled shift_cuda"},
+          "roofline_step": {"achieved": algo_mb * 1e6 * batch / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": algo_mb * 1e6 * batch / (ms * 1e-3) / 1e9 / peak},
+          "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9, "gpu_launches": 0})
 
 
 def run_b200(args):
@@ -371,7 +426,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
     ap.add_argument("--workload", default="ntu60-train", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-batch", type=int, default=4, help="bounded CPU sample (samples per CPU step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -380,6 +435,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_b200(args)
 

@@ -94,6 +94,9 @@ def shift_constraint(gx, gy):
 # When set to a dict, every backward records its raw (pre-K5) position sums under id(xpos); the golden
 # generator uses it to store the magnitudes that decide where the K5 sign is numerically meaningful.
 RAW_POS_LOG = None
+# oracle/build_ref_ext.load(): when set, CUDA inputs go through the REFERENCE's compiled shift_cuda kernels (the
+# "reference PyTorch + custom-shift-CUDA on one B200" baseline of bench.py --impl reference-gpu)
+REF_EXT = None
 
 
 class OracleShiftFunction(torch.autograd.Function):
@@ -104,14 +107,24 @@ class OracleShiftFunction(torch.autograd.Function):
         inp = inp.contiguous()
         if stride != 1:
             ypos = ypos + 0.5
+        ctx.stride = stride
+        if REF_EXT is not None and inp.is_cuda:          # the reference's own kernels, called as cuda/shift.py:12-23 does
+            out = REF_EXT.forward(inp, xpos, ypos, stride)
+            ctx.save_for_backward(inp, out, xpos, ypos)
+            ctx.ref_ext = True
+            return out
         out = shift_forward(inp, xpos, ypos, stride)
         ctx.save_for_backward(inp, xpos, ypos)
-        ctx.stride = stride
+        ctx.ref_ext = False
         return out
 
     @staticmethod
     def backward(ctx, grad_output):
         grad_output = grad_output.contiguous()
+        if ctx.ref_ext:                                  # cuda/shift.py:26-30
+            inp, out, xpos, ypos = ctx.saved_tensors
+            gin, gx, gy = REF_EXT.backward(grad_output, inp, out, xpos, ypos, ctx.stride)
+            return gin, gx, gy, None
         inp, xpos, ypos = ctx.saved_tensors
         gin = shift_backward_input(grad_output, xpos, ypos, inp.shape[2], ctx.stride)
         gx, gy = shift_backward_pos_raw(inp, grad_output, xpos, ypos, ctx.stride)
