@@ -217,7 +217,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     from shiftgcn_b200 import ops
-    from shiftgcn_b200.dp import FlatSGDTrainer, HostPrefetcher
+    from shiftgcn_b200.dp import FlatSGDTrainer, GraphedInference, HostPrefetcher
     from shiftgcn_b200.modules import Model
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -251,9 +251,13 @@ def run_b200(args):
     graphed = False
     launches_per_step = None
 
+    infer_graph = None
+
     def step(x, y):
         if train:
             return trainer.replay(x, y) if graphed else trainer.train_step(x, y)
+        if infer_graph is not None:
+            return infer_graph.replay(x)
         with torch.no_grad():
             return model(x)
 
@@ -312,6 +316,15 @@ def run_b200(args):
             step(dev_x, dev_y)
         barrier()
         note("graph captured and replayed")
+    if not train and not args.no_graph:
+        l0 = ops.LAUNCHES
+        infer_graph = GraphedInference(model, dev_x, warmup=1)
+        launches_per_step = (ops.LAUNCHES - l0) // 2         # one eager warm-up call + the captured one
+        graphed = True
+        for _ in range(2):
+            step(dev_x, dev_y)
+        barrier()
+        note("inference graph captured and replayed")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -337,7 +350,8 @@ def run_b200(args):
     if train:
         trainer.train_step(dev_x, dev_y)                     # eager (not the graph): per-call events need real launches
     else:
-        step(dev_x, dev_y)
+        with torch.no_grad():
+            model(dev_x)                                     # eager, like the training branch
     e1.record()
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
