@@ -217,7 +217,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     from shiftgcn_b200 import ops
-    from shiftgcn_b200.dp import FlatSGDTrainer, GraphedInference, HostPrefetcher
+    from shiftgcn_b200.dp import FlatSGDTrainer, GraphedInference
     from shiftgcn_b200.modules import Model
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -244,7 +244,6 @@ def run_b200(args):
     host_x = torch.randn(batch, 3, T, V, M).pin_memory()
     host_y = torch.randint(0, num_class, (batch,)).pin_memory()
     dev_x, dev_y = host_x.to(dev), host_y.to(dev)
-    host_out = torch.zeros(1, dtype=torch.float32).pin_memory()
     trainer = FlatSGDTrainer(model, lr=0.1, momentum=0.9, nesterov=True) if train else None
     note("model and trainer ready")
 
@@ -273,25 +272,14 @@ def run_b200(args):
         e0.record()
         last = None
         if from_host:
-            # every step copies ITS batch from pinned host memory and its result is read back on the host, all inside
-            # the timed region; the copy of batch i+1 runs on a side stream during step i (HostPrefetcher), and the
-            # result of step i is read while step i+1 runs (pinned D2H + event), so neither stalls the device
-            pf = HostPrefetcher(dev)
-            pf.put(host_x, host_y)
-            pending = None
-            for i in range(n_steps):
-                x, y = pf.get()
-                if i + 1 < n_steps:
-                    pf.put(host_x, host_y)
+            # every step copies ITS batch from pinned host memory on the launching stream and its result is read back on
+            # the host before the next step starts (the plain user-level loop; dp.HostPrefetcher can overlap the copy
+            # with the previous step, but its benefit was not stable across boxes, so the headline uses the plain loop)
+            for _ in range(n_steps):
+                x = host_x.to(dev, non_blocking=True)
+                y = host_y.to(dev, non_blocking=True)
                 out = step(x, y)
-                if pending is not None:
-                    pending.synchronize()
-                    last = float(host_out[0])
-                host_out.copy_((out if train else out[0, 0]).reshape(1), non_blocking=True)
-                pending = torch.cuda.Event()
-                pending.record()
-            pending.synchronize()
-            last = float(host_out[0])
+                last = float(out.item()) if train else float(out[0, 0].item())     # D2H read of the step's result
         else:
             for _ in range(n_steps):
                 step(dev_x, dev_y)
