@@ -208,8 +208,8 @@ class Shift_gcn(nn.Module):
         return FN.SpatialFn.apply(x_rows, res, *self._args(), self)
 
     def _forward_general(self, x0):
-        """Unfused path for shapes the tensor-core kernels do not cover (e.g. the 3-channel first layer):
-        the same arithmetic with library ops.  TODO(next): SIMT kernels for C_in < 64."""
+        """Unfused path for shapes neither the tensor-core kernels (64 / 128 / 256 channels) nor the stem kernels
+        (3 -> 64, the model's first layer) cover: the same arithmetic with library ops on CUDA tensors."""
         n, c, t, v = x0.shape
         rows = x0.permute(0, 2, 3, 1).reshape(n * t, v * c)
         xs = torch.index_select(rows, 1, self.shift_in).view(n * t, v, c)     # backward = index_add_ (atomics), not the
