@@ -44,7 +44,8 @@ def test_abi_version_and_error_channel(lib):
 
 def test_struct_layouts_match_the_c_compiler(tmp_path):
     from shiftgcn_b200 import _lib
-    structs = ["SgcnRowGemm", "SgcnWgrad", "SgcnTShift", "SgcnTShiftBwd", "SgcnTShiftInBwd"]
+    structs = ["SgcnRowGemm", "SgcnWgrad", "SgcnTShift", "SgcnTShiftBwd", "SgcnTShiftInBwd", "SgcnTShiftInSums", "SgcnStem",
+               "SgcnSideFold", "SgcnSideBwd"]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void) {']
     for s in structs:
         cls = getattr(_lib, s)
