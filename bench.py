@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- Shift-GCN fwd+bwd samples/s on synthetic NTU tensors (BASELINE.json's metric), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ntu60-train|ntu60-infer|mediapipe-train]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload ntu60-train|ntu120-train|ntu60-infer|mediapipe-train|ensemble]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch of 64 synthetic samples per GPU: forward, cross-entropy, backward,
@@ -10,7 +11,11 @@ from rank 0.  Keys beyond the base contract:
   roofline      dominant kernel of the step (largest total device time in a CUDA-event profiling pass after the timed
                 region): algorithmic bytes per launch / mean launch duration, against MEASURED_PEAKS.json
   roofline_step whole-step algorithmic bytes (930.0 MB/sample NTU training) / step time
-  cpu_baseline  the oracle port (oracle/model_ref.py, torch CPU, all host threads) on a bounded sample, rank 0 only
+  cpu_baseline  the oracle port (oracle/model_ref.py, torch CPU, all host threads) on a bounded sample, N = 1 only, timed
+                BEFORE any GPU work; its `c1` entry is SURVEY.md section 8d's C1 (one Shift_gcn(64,64) eval forward on
+                (32,64,300,25)) on the host cores with this library's time for the same shape beside it
+Default workload: ntu60-train on one GPU, ntu120-train (BASELINE.json config 4: same tensors, 120 classes) on several;
+``--workload ensemble`` is config 5 (four streams placed on the ranks, one all-reduce of the weighted logits).
   e2e           same metric through the public nn.Module API with HOST inputs: pinned H2D copy of every batch and a
                 D2H read of the loss inside the timed region
 ``--impl reference`` times the reference's CPU implementation of the path (the oracle port; the reference itself is
@@ -41,18 +46,23 @@ WORKLOADS = {
 
 def _ncu_traffic(kernel, workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture
-    of the same step (profiles/r*_traffic_*.json); None when no capture exists for this kernel / workload."""
-    if workload not in ("ntu60-train", "ntu120-train"):
-        return None, None
+    of the same step (profiles/r*_traffic_*.json, newest round first); None when no capture exists for this kernel /
+    workload.  A file holds either one record or {"workload": .., "kernels": {name: bytes per launch}}."""
     import glob
+    family = "train" if workload in ("ntu60-train", "ntu120-train") else workload
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic_*.json")), reverse=True):
         try:
             with open(path) as f:
                 rec = json.load(f)
         except (OSError, ValueError):
             continue
+        rec_family = "train" if rec.get("workload", "ntu60-train") in ("ntu60-train", "ntu120-train") else rec.get("workload")
+        if rec_family != family:
+            continue
         if rec.get("kernel") == kernel:
             return float(rec["dram_bytes_per_launch"]), os.path.relpath(path, ROOT)
+        if kernel in rec.get("kernels", {}):
+            return float(rec["kernels"][kernel]), os.path.relpath(path, ROOT)
     return None, None
 
 
@@ -136,12 +146,65 @@ def _cpu_reference_rate(workload, batch, steps, warmup, train):
     return batch / dt, dt, cores
 
 
+def _c1_cpu(reps=5):
+    """Shift_gcn(64, 64, num_point=25) eval forward on x0 = randn(32, 64, 300, 25), CPU, all
+    host threads, 2 warm-up + `reps` timed calls -> (best seconds, median seconds)."""
+    import torch
+    from oracle import model_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1)
+    m = model_ref.RefShiftGcn(64, 64, None, num_point=25).eval()
+    x = torch.randn(32, 64, 300, 25)
+    ts = []
+    with torch.no_grad():
+        for i in range(2 + reps):
+            t0 = time.perf_counter()
+            m(x)
+            if i >= 2:
+                ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return ts[0], ts[len(ts) // 2]
+
+
+def _c1_gpu(dev, reps=20):
+    """the same C1 call through this package's Shift_gcn on the GPU (eval, no_grad; the input is 61 MB: a 256 MB buffer
+    is rewritten between calls so every call starts with a cold L2) -> median milliseconds"""
+    import torch
+    from shiftgcn_b200.modules import Shift_gcn
+    torch.manual_seed(1)
+    m = Shift_gcn(64, 64, None, num_point=25).to(dev).eval()
+    x = torch.randn(32, 64, 300, 25, device=dev).contiguous(memory_format=torch.channels_last)
+    flush = torch.empty(64 * 1024 * 1024, device=dev)
+    ts = []
+    with torch.no_grad():
+        for i in range(3 + reps):
+            flush.fill_(float(i))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            m(x)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def default_workload(args):
+    if args.workload:
+        return args.workload
+    return "ntu60-train" if max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) <= 1 else "ntu120-train"
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     workload = args.workload
+    if workload == "ensemble":
+        emit({"impl": "reference", "unavailable": "the ensemble workload has no CPU reference arm (four models; see tests)"})
+        return
     train = WORKLOADS[workload][5]
     batch = args.ref_batch
     rate, dt, cores = _cpu_reference_rate(workload, batch, args.steps, max(args.warmup, 1), train)
@@ -194,12 +257,15 @@ def run_reference_gpu(args):
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
     peak, peak_src = _peaks()
     emit({"impl": "reference-gpu", "metric": "Shift-GCN fwd+bwd samples/sec (NTU 3x300x25x2)" if train else f"Shift-GCN samples/sec ({args.workload})",
@@ -209,7 +275,7 @@ def run_reference_gpu(args):
                                           "note": "reference modules restated in oracle/model_ref.py + the reference's compiled shift_cuda"},
           "roofline_step": {"achieved": algo_mb * 1e6 * batch / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                             "frac": algo_mb * 1e6 * batch / (ms * 1e-3) / 1e9 / peak},
-          "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9, "gpu_launches": 0})
+          "clocks": clocks, "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9, "gpu_launches": 0})
 
 
 def run_b200(args):
@@ -228,6 +294,20 @@ def run_b200(args):
         if args.verbose:
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
 
+    num_class, V, M, T, batch, train, algo_mb, fwd_gf = WORKLOADS[args.workload]
+    # CPU baseline: N = 1 only, and BEFORE any GPU work or process group exists -- no GPU spins in a collective while
+    # the host cores are being timed, and the host cores are not shared with launch threads
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, dt, cores = _cpu_reference_rate(args.workload, args.ref_batch, 2, 1, train)
+        c1_best, c1_med = _c1_cpu()
+        cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"2 steps of batch {args.ref_batch} of the same workload ({'fwd+bwd+SGD' if train else 'fwd'}), "
+                         "oracle/model_ref.py on torch CPU",
+               "c1": {"what": "SURVEY 8d C1: Shift_gcn(64,64,num_point=25) eval forward on (32,64,300,25), 16 samples",
+                      "cpu_s_best": c1_best, "cpu_s_median": c1_med, "cpu_samples_per_s": 16 / c1_med}}
+        note("CPU baseline done")
+
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ops.device_check()
@@ -235,7 +315,6 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    num_class, V, M, T, batch, train, algo_mb, fwd_gf = WORKLOADS[args.workload]
     graph = "graph.ntu_rgb_d.Graph" if V == 25 else "graph.mediapipe_pose.Graph"
     torch.manual_seed(1)                                     # identical init on every rank (main.py:24-28 seeds 1)
     model = Model(num_class=num_class, num_point=V, num_person=M, graph=graph,
@@ -364,12 +443,10 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
 
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        rate, dt, cores = _cpu_reference_rate(args.workload, args.ref_batch, 2, 1, train)
-        cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"2 steps of batch {args.ref_batch} of the same workload ({'fwd+bwd+SGD' if train else 'fwd'}), "
-                         "oracle/model_ref.py on torch CPU"}
+    if cpu is not None:
+        gpu_ms = _c1_gpu(dev)
+        cpu["c1"].update(gpu_ms_median=gpu_ms, gpu_samples_per_s=16 / (gpu_ms * 1e-3),
+                         gpu_hbm_frac=2 * 32 * 64 * 300 * 25 * 4 / (gpu_ms * 1e-3) / 1e9 / peak)
     if rank == 0:
         value = batch * world / (ms_step * 1e-3)
         e2e = batch * world / (ms_e2e * 1e-3)
@@ -404,6 +481,107 @@ def run_b200(args):
         os._exit(0)
 
 
+def run_ensemble(args):
+    """--workload ensemble (BASELINE.json config 5): the 4-stream joint / bone / joint-motion / bone-motion ensemble
+    (weights 0.6 / 0.6 / 0.4 / 0.4, ensemble.py:18-27) as batched inference, streams placed on the ranks by
+    shiftgcn_b200.ensemble.placement (1 GPU: all four models; 2: two each; 4: one each; 8: two ranks per stream, batch
+    halved inside the pair).  Every rank receives the joint batch from pinned host memory, derives its stream on the
+    device, and ONE all-reduce of the weighted logits is the ensemble.  A step = one batch of 64 samples through all
+    four streams: total work is fixed, so scaling is "strong".  Rank 0 also evaluates all four streams alone and
+    reports the difference to the sharded result."""
+    import torch
+    import torch.distributed as dist
+
+    from shiftgcn_b200 import ensemble as E, ops
+    from shiftgcn_b200.modules import Model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ops.device_check()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N, T, V, M, ncls = 64, 300, 25, 2, 60
+
+    def build(k):
+        torch.manual_seed(100 + k)                      # same weights for stream k on whichever rank owns it
+        return Model(num_class=ncls, num_point=V, num_person=M, graph="graph.ntu_rgb_d.Graph",
+                     graph_args=dict(labeling_mode="spatial")).to(dev).eval()
+
+    def make(models):
+        fns = {name: (lambda jb, m=m, name=name: m.forward_stream(jb, name)) for name, m in models.items()}
+        return fns
+
+    mine = {E.MODALITIES[k]: build(k) for k, _, _ in E.placement(world, rank)}
+    ens = E.StreamEnsemble(make(mine), num_class=ncls, world_size=world, rank=rank, stream_fn=lambda jb, name: jb)
+    torch.manual_seed(1)
+    host = torch.randn(N, 3, T, V, M).pin_memory()
+    dev_x = host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, from_host):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        top = None
+        for _ in range(n_steps):
+            out = ens.logits(host.to(dev, non_blocking=True) if from_host else dev_x)
+            if from_host:
+                top = out.argmax(1).cpu()               # D2H read of the step's result
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / n_steps, out, top
+
+    for _ in range(max(args.warmup, 3)):
+        ens.logits(dev_x)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.LAUNCHES
+    ms_dev, _, _ = timed(args.steps, False)
+    launches = (ops.LAUNCHES - l0) // args.steps
+    timed(2, True)
+    ms_e2e, out, top = timed(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        full = {E.MODALITIES[k]: build(k) for k in range(4)} if world > 1 else mine
+        ref = E.StreamEnsemble(make(full), num_class=ncls, stream_fn=lambda jb, name: jb).logits(dev_x)
+        diff = (ref - out).abs().max().item() / ref.abs().max().item()
+        peak, peak_src = _peaks()
+        gbs = 4 * 196.0e6 * N / (ms_dev * 1e-3) / 1e9 / world    # per GPU: four streams' inference bytes over `world` GPUs
+        emit({"metric": "4-stream ensemble samples/sec (NTU 3x300x25x2, batch 64)", "value": N / (ms_dev * 1e-3),
+              "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+              "config": {"workload": "ensemble", "global_batch": N, "streams": list(E.MODALITIES),
+                         "weights": list(E.ENSEMBLE_WEIGHTS_DEFAULT),
+                         "placement": [E.placement(world, r) for r in range(world)],
+                         "l2": "activation tensors are 246 MB each on one GPU (> 126 MB L2)",
+                         "collective": "one all-reduce(sum) of the (64, 60) weighted logits"},
+              "e2e": {"value": N / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(host.numel() * 4),
+                      "d2h_bytes_per_step": N * 8, "ms_per_step": ms_e2e},
+              "gpu_launches": int(launches), "clocks": clocks,
+              "roofline_step": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                "algorithmic_mb_per_sample": 4 * 196.0, "peak_source": peak_src,
+                                "note": "per-GPU: 4 streams x 196 MB/sample inference bytes spread over n_gpus"},
+              "parity": {"rel_diff_vs_single_rank": diff, "top1_equal": bool((ref.argmax(1).cpu() == top).all())},
+              "cpu_baseline": None})
+    if world > 1:
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 _REAL_STDOUT = None
 
 
@@ -429,13 +607,17 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
-    ap.add_argument("--workload", default="ntu60-train", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["ensemble"],
+                    help="default: ntu60-train on one GPU, ntu120-train (config 4) on several")
     ap.add_argument("--ref-batch", type=int, default=4, help="bounded CPU sample (samples per CPU step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="progress notes on stderr")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of one CUDA graph")
     args = ap.parse_args()
-    if args.impl == "reference":
+    args.workload = default_workload(args)
+    if args.workload == "ensemble" and args.impl == "b200":
+        run_ensemble(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.impl == "reference-gpu":
         run_reference_gpu(args)

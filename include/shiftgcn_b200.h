@@ -27,13 +27,18 @@ int sgcn_abi_version(void);
 const char* sgcn_last_error(void);
 /* 0 when the current CUDA device is compute capability 10.x, error otherwise (there is no fallback path) */
 int sgcn_device_check(void);
-/* Traversal order of the full-tensor kernels (process-wide setting).  snake != 0: every kernel walks its
+/* Traversal order of the full-tensor kernels (process-wide on/off setting, alternation state per device).  snake != 0: every kernel walks its
  * tiles in the opposite order of the kernel launched before it, so that it starts on the part of its inputs the
  * previous kernel touched last (still resident in the 126 MB L2); 0 (default): always ascending.  The call also
  * restarts the alternation: after 1 the next kernel descends, after 2 it ascends (callers restart it at the top of
  * every step so that all steps, and a captured CUDA graph, see the same orders).  Results do not depend on the
  * order.  Returns the previous on/off setting. */
 int sgcn_set_traversal(int snake);
+/* Cap on the grid of the persistent tile kernels (sgcn_rowgemm, sgcn_wgrad); 0 = one CTA per SM (default).  Used by the
+ * parity tests: with a handful of CTAs a small tensor already gives every CTA many tiles, so the multi-tile steady
+ * state of the pipelines (second TMEM accumulator, stage-ring wrap, mbarrier phase parities, cross-tile dW accumulation,
+ * descending traversal) is compared against the oracle at sizes the oracle finishes in seconds.  Returns the previous cap. */
+int sgcn_set_max_ctas(int n);
 /* tcgen05 descriptor self test (tests only): mode 0: D[128,N] = A[128,K] * B[N,K]^T; mode 1: D[128,N] = A[128,M]^T * B[128,N] */
 int sgcn_selftest_umma(const float* a, const float* b, float* d, int mode, int K, int N, int M, void* stream);
 /* descriptor probe (tests only): D[128,N] = A*B, each operand K-major or MN-major with explicit swizzle / layout / LBO / SBO */
@@ -291,7 +296,7 @@ typedef struct SgcnSideFold {
   double* invstd;
   double* sx;                 /* out [C]: channel sums of x (training)                                                */
   int* counter;               /* zeroed int scratch (training); handed back zeroed                                    */
-  double rows, eps, momentum;
+  double rows, eps, momentum; /* momentum < 0: cumulative average 1 / num_batches_tracked (caller already incremented it) */
   int C, D, training;
 } SgcnSideFold;
 int sgcn_side_fold(const SgcnSideFold* p, void* stream);
@@ -335,7 +340,9 @@ int sgcn_relu_mask_grad(const float* g, const float* y, float* out, long long nu
 /* ---- small per-feature kernels (prep.cu) ---- */
 
 /* batch-norm forward finalize: {sum, sumsq} -> mean/invstd/scale/shift, running-stat update (momentum, unbiased var),
- * num_batches_tracked += 1, stats cleared.  training == 0: scale/shift from the running statistics, nothing updated. */
+ * num_batches_tracked += 1, stats cleared.  training == 0: scale/shift from the running statistics, nothing updated.
+ * momentum < 0 selects nn.BatchNorm(momentum=None): the caller has ALREADY incremented num_batches_tracked and the
+ * update factor is 1 / num_batches_tracked (cumulative moving average). */
 int sgcn_bn_fwd_finalize(double* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
                          long long* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
                          int features, double count, double momentum, double eps, int training, void* stream);
@@ -370,6 +377,19 @@ int sgcn_prep_weight_image(const float* src, long long ld_n, long long ld_k, int
 
 /* double -> float copy of a reduction buffer (+ clear) */
 int sgcn_reduce_export(double* src, float* dst, int n, double scale, void* stream);
+
+/* ---------------------------------------------------------------- optimizer step (optim.cu) ----------------- */
+/* The step after backward (main.py:301-322 parameter groups, :412-414 optimizer.step, App. E-7 of SURVEY.md), as ONE
+ * kernel over flat fp32 buffers of n_param elements:
+ *     g   = grad[i] * hyper[2]                                   (1/world after a summed all-reduce, else 1)
+ *     g   = K5(grad[n_param + ypos_src[i]])  where ypos_src[i] >= 0  (shift_cuda_kernel.cu:371-395 on the REDUCED raw
+ *           sums that ride behind the gradients: sign * 0.01, or 1e-4 when the sum is exactly 0);  ypos_src may be NULL
+ *     d   = g + weight_decay[i] * param[i];   buf = hyper[1] * buf + d   (zero-initialised momentum buffer)
+ *     param[i] -= hyper[0] * (nesterov ? d + hyper[1] * buf : buf);      grad[i] = g
+ * hyper = {lr, momentum, gradient scale} lives in DEVICE memory: a captured CUDA graph follows the learning-rate
+ * schedule (main.py:342-351) without re-capture. */
+int sgcn_sgd_epilogue(float* param, float* grad, float* momentum_buf, const float* weight_decay, const int* ypos_src,
+                      const float* hyper, long long n_param, int nesterov, void* stream);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,7 @@ SIGNATURES = {
     "sgcn_abi_version": [],
     "sgcn_device_check": [],
     "sgcn_set_traversal": [_i],
+    "sgcn_set_max_ctas": [_i],
     "sgcn_selftest_umma": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "sgcn_selftest_probe": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "sgcn_shift_fwd_nchw_f32": [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
@@ -104,6 +105,7 @@ SIGNATURES = {
     "sgcn_mask_grad_finalize": [_vp, _vp, _vp, _i, _vp],
     "sgcn_prep_weight_image": [_vp, _ll, _ll, _i, _i, _vp, _vp],
     "sgcn_reduce_export": [_vp, _vp, _i, _d, _vp],
+    "sgcn_sgd_epilogue": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp],
 }
 
 _lib = None

@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
     objs = [o for o, _ in results]
     rebuilt = any(r for _, r in results)
     if rebuilt or not os.path.exists(LIB_PATH):
-        cmd = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
+        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs, "-lcudart"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)

@@ -26,10 +26,15 @@ int check_launch(const char* kernel_name) {
   return 0;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+  return dev;
+}
+
 int num_sms() {
   static thread_local int cached_dev = -1, cached = 0;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  const int dev = current_device();
   if (dev != cached_dev) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
@@ -39,23 +44,48 @@ int num_sms() {
   return cached;
 }
 
-// process-wide (autograd runs the backward kernels from its own host thread); a race between two launching threads
-// can only pick a less favourable order, never a wrong result
-static std::atomic<int> g_snake{0}, g_last_rev{0};
+// Persistent-grid cap (sgcn_set_max_ctas; tests): with a few CTAs even a small tensor gives every CTA many tiles, i.e.
+// the multi-tile steady state of the pipelines (second accumulator, ring wrap, phase parities) the full-size runs use.
+static std::atomic<int> g_max_ctas{0};
+
+int tile_ctas() {
+  const int n = num_sms(), cap = g_max_ctas.load(std::memory_order_relaxed);
+  return (cap > 0 && cap < n) ? cap : n;
+}
+
+// The on/off setting is process-wide; the alternation itself is kept PER DEVICE: autograd runs the backward kernels of
+// a device from its own host thread, so the state cannot be per host thread, while threads that drive different
+// devices (nn.DataParallel replicas) never share an entry.  Two threads launching on the same device can only pick a
+// less favourable order, never a wrong result.
+constexpr int kMaxDevices = 64;
+static std::atomic<int> g_snake{0}, g_last_rev[kMaxDevices];
+
+static int dev_slot() { return current_device() % kMaxDevices; }
 
 int next_direction() {
   if (!g_snake.load(std::memory_order_relaxed)) return 0;
-  return g_last_rev.fetch_xor(1, std::memory_order_relaxed) ^ 1;
+  return g_last_rev[dev_slot()].fetch_xor(1, std::memory_order_relaxed) ^ 1;
 }
 
-void mark_forward() { g_last_rev.store(0, std::memory_order_relaxed); }
+void mark_forward() { g_last_rev[dev_slot()].store(0, std::memory_order_relaxed); }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE property of a kernel: remember which devices a
+// kernel has been configured on (one bit each) instead of a per-thread flag that a second GPU would inherit.
+bool needs_configure(std::atomic<unsigned long long>& done_mask) {
+  return !(done_mask.load(std::memory_order_acquire) >> dev_slot() & 1ull);
+}
+void mark_configured(std::atomic<unsigned long long>& done_mask) {
+  done_mask.fetch_or(1ull << dev_slot(), std::memory_order_release);
+}
 
 }  // namespace sgcn
 
 extern "C" int sgcn_set_traversal(int snake) {
-  sgcn::g_last_rev.store(snake == 2 ? 1 : 0);                  // 1: the next kernel descends; 2: it ascends
+  sgcn::g_last_rev[sgcn::dev_slot()].store(snake == 2 ? 1 : 0);   // 1: the next kernel descends; 2: it ascends
   return sgcn::g_snake.exchange(snake ? 1 : 0);
 }
+
+extern "C" int sgcn_set_max_ctas(int n) { return sgcn::g_max_ctas.exchange(n > 0 ? n : 0); }
 
 extern "C" const char* sgcn_last_error(void) { return sgcn::g_err; }
 

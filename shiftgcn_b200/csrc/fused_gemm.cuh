@@ -615,15 +615,15 @@ template <int PRO, int EPI, int V, int K, int N>
 static int launch(const SgcnRowGemm& p, cudaStream_t s) {
   using C = Cfg<PRO, EPI, V, K, N>;
   auto kern = fused_gemm_kernel<PRO, EPI, V, K, N>;
-  static thread_local bool configured = false;
-  if (!configured) {
+  static std::atomic<unsigned long long> configured{0};           // one bit per device (the attribute is per device)
+  if (needs_configure(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem);
     if (e != cudaSuccess) return set_cuda_error("fused_gemm smem attribute", e);
-    configured = true;
+    mark_configured(configured);
   }
   const long long ntiles = (p.groups + C::G - 1) / C::G;
   if (ntiles == 0) return 0;
-  long long grid = num_sms();
+  long long grid = tile_ctas();
   if (grid > ntiles) grid = ntiles;
   kern<<<(unsigned)grid, kThreads, C::kSmem, s>>>(p, next_direction());
   return check_launch("fused_gemm_kernel");

@@ -18,7 +18,10 @@ __global__ void bn_fwd_finalize_kernel(double* __restrict__ stats, const float* 
                                        float* __restrict__ scale_o, float* __restrict__ shift_o, int F, double count,
                                        double momentum, double eps, int training) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f == 0 && training && nbt) *nbt += 1;
+  // momentum < 0 = nn.BatchNorm(momentum=None): cumulative moving average with factor 1 / num_batches_tracked; the
+  // caller has already incremented the counter (every thread reads it here, so it cannot also be written here)
+  if (momentum < 0.0) momentum = (training && nbt && *nbt > 0) ? 1.0 / (double)*nbt : 0.0;
+  else if (f == 0 && training && nbt) *nbt += 1;
   if (f >= F) return;
   double mean, var;
   if (training) {

@@ -1,508 +1,26 @@
-// rowgemm.cu -- the fused "row tile x weight" tensor-core kernels of the Shift-GCN hot path.
+// rowgemm.cu -- entry point of the fused "row tile x weight" tensor-core kernels of the Shift-GCN hot path.
 //
-// Activations live channels-last: a logical (n, C, T, V) tensor is the row-major matrix [(n,t,v), C].
-// A CTA processes tiles of G whole (n,t) groups (G*V <= 128 rows), so the joint shift of the spatial
-// unit is a permutation inside the tile.  Per tile and per 64-channel K chunk:
-//     stage      cp.async of the raw input slab (prefetched one tile / chunk ahead into a ping-pong region)
-//     prologue   raw slab -> canonical SWIZZLE_128B operand chunk (TF32-rounded), fused gather / mask / BN / lerp
-//     contraction tcgen05.mma (kind::tf32, M = 128, N = out channels, fp32 accumulators in TMEM)
-//     epilogue   tcgen05.ld -> padded smem staging -> channel-contiguous pass with the fused tail
-//
-// Variants (template PRO x EPI), with the reference code each one replaces:
-//   PRO_SPATIAL  x[r,(u+c)%V,c] * (tanh(mask)+1)            model/shift_gcn.py:123-129
-//   PRO_LERP     temporal shift of BN(h), zero padded       model/shift_gcn.py:66-68, shift_cuda_kernel.cu:12-76
-//   PRO_PLAIN    rows as they are                           (backward data contraction of the 1x1 conv)
-//   PRO_DY       BN1d-backward + inverse output rotation    autograd of model/shift_gcn.py:135-137
-//   EPI_ROT_RAW    + bias, rotate z[v,d]=y[(v-d)%V,d], store, per-(v,d) batch statistics   :131-137 (training)
-//   EPI_ROT_FUSED  + bias, rotate, folded BN, + residual, ReLU                              :131-141 (eval)
-//   EPI_LINEAR     + bias, optional ReLU, store                                             :69-70
-//   EPI_SPATIAL_BWD  * mask, inverse input rotation, + residual gradients, dMask partials   autograd of :127-129,140
-//
-// Instruction economy: everything that does not depend on the tile (swizzled destination offsets, joint
-// permutations) lives in registers; the inner loops are LDS / FMA / CVT / STS only, with no integer division.
-// Thread mapping: lane <-> channel (conflict-free smem access, 128-byte coalesced global access),
-// warp <-> joint, loop over the tile's groups.
+// Activations live channels-last: a logical (n, C, T, V) tensor is the row-major matrix [(n,t,v), C].  sgcn_rowgemm
+// validates the parameter block and hands it to the warp-specialised kernels:
+//   fused_gemm.cuh (instantiated in spatial_fwd.cu / temporal_gemm.cu)
+//     PRO_SPATIAL  x[r,(u+c)%V,c] * (tanh(mask)+1)            model/shift_gcn.py:123-129
+//     PRO_LERP     temporal shift of BN(h), zero padded       model/shift_gcn.py:66-68, shift_cuda_kernel.cu:12-76
+//     PRO_PLAIN    rows as they are                           (1x1 conv side branches, backward data of the 1x1 conv)
+//     EPI_ROT_RAW    + bias, rotate z[v,d]=y[(v-d)%V,d], store, per-(v,d) batch statistics   :131-137 (training)
+//     EPI_ROT_FUSED  + bias, rotate, folded BN, + residual, ReLU                              :131-141 (eval)
+//     EPI_LINEAR     + bias, optional ReLU, store                                             :69-70
+//   spatial_bwd.cu
+//     PRO_DY x EPI_SPATIAL_BWD   BN1d-backward + inverse output rotation, * mask, inverse input rotation, + residual
+//                                gradients, dMask partial sums                      autograd of model/shift_gcn.py:123-141
+// The kernels exist for the skeletons of the reference's configs, num_point 25 (NTU) and 33 (MediaPipe); any other
+// joint count is an error (there is no generic fallback kernel).
 #include "capi_internal.h"
-#include "common.cuh"
 #include "rowgemm.h"
-#include "tile_builders.cuh"
 
 namespace sgcn {
 
 enum { PRO_SPATIAL = 0, PRO_LERP = 1, PRO_PLAIN = 2, PRO_DY = 3 };
 enum { EPI_ROT_RAW = 0, EPI_ROT_FUSED = 1, EPI_LINEAR = 2, EPI_SPATIAL_BWD = 3 };
-
-constexpr int kStagePitch = 68;                              // floats per staging row (64 + 4 pad)
-constexpr int kRegionBytes = kTileRows * kStagePitch * 4;    // 34816 = 34 KiB: raw slab / operand chunk / staging
-constexpr int kGMax = 5;                                     // groups per tile (V >= 25)
-constexpr int kUI = 5;                                       // joints per warp: ceil(V / 8), V <= 40
-constexpr int kWResidentMax = 64 * 1024;
-constexpr int kSmemPerSM = 232448;                           // 227 KiB usable per SM on sm_100
-
-__host__ __device__ inline size_t rowgemm_w_bytes(int K, int N) {
-  size_t full = (size_t)K * N * 4;
-  return full <= (size_t)kWResidentMax ? full : (size_t)N * 256;
-}
-__host__ __device__ constexpr int rowgemm_regions(int pro) {
-  // DY: raw gh, raw z, operand/staging.  SPATIAL: raw x <-> operand/staging (roles swap every tile).
-  // LERP / PLAIN build straight from global memory: one region serves as operand, then as staging.
-  return pro == PRO_DY ? 3 : (pro == PRO_SPATIAL ? 2 : 1);
-}
-template <int EPI, int NCH>
-__host__ __device__ constexpr int rowgemm_min_blocks() { return EPI == EPI_LINEAR ? (NCH == 1 ? 3 : 2) : (NCH == 1 ? 2 : 1); }
-// cross-tile per-(joint, channel) reductions: registers for 64 output channels, shared memory beyond that
-template <int EPI, int NCH>
-__host__ __device__ constexpr bool rowgemm_acc_in_smem() { return NCH > 1 && (EPI == EPI_ROT_RAW || EPI == EPI_SPATIAL_BWD); }
-__host__ __device__ inline size_t rowgemm_acc_bytes(int epi, int V, int N) {
-  if (N <= 64) return 0;
-  return epi == EPI_ROT_RAW ? (size_t)2 * V * N * 4 : (epi == EPI_SPATIAL_BWD ? (size_t)V * N * 4 : 0);
-}
-
-template <int PRO, int EPI, int NCH>
-__global__ void __launch_bounds__(kThreads, rowgemm_min_blocks<EPI, NCH>()) rowgemm_kernel(const SgcnRowGemm p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int V = p.V, G = p.G, K = p.K, N = p.N;
-  const int kchunks = K >> 6;
-  const bool w_resident = (size_t)K * N * 4 <= (size_t)kWResidentMax;
-
-  uint8_t* sW = smem;                                             // weight image (resident) or one streamed chunk
-  uint8_t* sR = sW + rowgemm_w_bytes(K, N);                       // 1..3 regions of kRegionBytes
-  float* sTab = (float*)(sR + rowgemm_regions(PRO) * kRegionBytes);
-  float* sBias = sTab;                                            // [N]
-  float* sLerp = sTab + N;                                        // LERP: [4][K] = floor(y), frac(y), scale, shift
-  constexpr bool kAccSmem = rowgemm_acc_in_smem<EPI, NCH>();
-  float* sAcc0 = sTab + N + (PRO == PRO_LERP ? 4 * K : 0);        // [V][N] (kAccSmem only)
-  float* sAcc1 = sAcc0 + V * N;
-  __shared__ uint64_t bar_mma;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ int sGrpT[8];                                        // LERP: frame index t of each group of the tile
-
-  // ---------------------------------------------------------------- one-time setup
-  if (tid == 0) {
-    mbar_init(&bar_mma, 1);
-    fence_mbar_init();
-  }
-  const uint32_t tmem_cols = N <= 64 ? 64u : (N <= 128 ? 128u : 256u);
-  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
-  for (int i = tid; i < N; i += kThreads) sBias[i] = p.bias ? p.bias[i] : 0.f;
-  if (PRO == PRO_LERP) load_lerp_tables(sLerp, p.pro_a, p.pro_b, p.pro_c, K, tid);
-  if (w_resident) {
-    const int n16 = (K * N * 4) >> 4;
-    for (int i = tid; i < n16; i += kThreads) cp_async16(sW + (size_t)i * 16, (const uint8_t*)p.wimg + (size_t)i * 16);
-    cp_async_commit();
-    cp_async_wait_all();
-    fence_proxy_async();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-  const uint32_t idesc = umma_idesc_tf32(128, N, 0, 0);
-  uint32_t mma_phase = 0;
-
-  // ---------------------------------------------------------------- tile-invariant per-thread tables
-  // swizzled operand offsets of rows (g, u = warp + 8 ui) for this lane (gather prologues)
-  uint32_t dst_off[kUI][kGMax];
-  if (PRO == PRO_SPATIAL || PRO == PRO_DY) {
-#pragma unroll
-    for (int ui = 0; ui < kUI; ++ui)
-#pragma unroll
-      for (int g = 0; g < kGMax; ++g) {
-        const int row = g * V + warp + ui * kWarps;
-        dst_off[ui][g] = canon_off(row < kTileRows ? row : 0, lane);
-      }
-  }
-  // rows r = warp + 8 i all share the swizzle phase (r & 7) == warp (row-wise prologues)
-  const uint32_t row_off0 = (uint32_t)(warp * 128 + ((((lane >> 2) ^ warp) & 7) << 4) + ((lane & 3) << 2));
-  const int step64 = 64 % V, lmod = lane % V, l32mod = (lane + 32) % V;
-
-  // per-thread reductions that live across tiles
-  constexpr int NACC = kAccSmem ? 1 : NCH;
-  float acc0[NACC][2][kUI];   // ROT_RAW: sum ; SPATIAL_BWD: dMask
-  float acc1[NACC][2][kUI];   // ROT_RAW: sum of squares
-#pragma unroll
-  for (int a = 0; a < NACC; ++a)
-#pragma unroll
-    for (int b = 0; b < 2; ++b)
-#pragma unroll
-      for (int c = 0; c < kUI; ++c) acc0[a][b][c] = 0.f, acc1[a][b][c] = 0.f;
-  if (kAccSmem) {   // every (joint, channel) slot is owned by exactly one thread: plain read-modify-write, no atomics
-    for (int i = tid; i < V * N * (EPI == EPI_ROT_RAW ? 2 : 1); i += kThreads) sAcc0[i] = 0.f;
-    __syncthreads();
-  }
-
-  constexpr bool kStaged = (PRO == PRO_SPATIAL || PRO == PRO_DY);
-  // region roles; SPATIAL: raw <-> operand swap every tile; DY: {gh, operand} swap, z stays in region 1
-  int r_raw = 0, r_op = (PRO == PRO_DY) ? 2 : ((PRO == PRO_SPATIAL) ? 1 : 0);
-  constexpr int r_z = 1;
-
-  const long long ntiles = (p.groups + G - 1) / G;
-  long long tile = blockIdx.x;
-  if (kStaged && tile < ntiles) {                      // prefetch chunk 0 of the first tile
-    const int ng0 = (int)((p.groups - tile * G) < G ? (p.groups - tile * G) : G);
-    stage_rows_async(sR + r_raw * kRegionBytes, p.in0, tile * G * V, ng0 * V, K, 0, tid);
-    if (PRO == PRO_DY) stage_rows_async(sR + r_z * kRegionBytes, p.in1, tile * G * V, ng0 * V, K, 0, tid);
-    cp_async_commit();
-  }
-
-  for (; tile < ntiles; tile += gridDim.x) {
-    const long long g0 = tile * G;
-    const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
-    const int rows_valid = ng * V;
-    const long long row0 = g0 * V;                       // first global row of the tile
-    const long long next_tile = tile + gridDim.x;
-    uint8_t* sRaw = sR + r_raw * kRegionBytes;
-    uint8_t* sOp = sR + r_op * kRegionBytes;
-
-    if (PRO == PRO_LERP) {
-      if (tid < G) sGrpT[tid] = (int)((g0 + tid) % p.T);
-    }
-    // ================================================================== K loop: prologue + MMA
-    for (int kc = 0; kc < kchunks; ++kc) {
-      if (kc > 0) {                                      // the previous chunk's MMAs still read sOp / sW
-        mbar_wait(&bar_mma, mma_phase);
-        mma_phase ^= 1;
-      }
-      if (!w_resident) {
-        const int n16 = (N * 256) >> 4;
-        const uint8_t* src = (const uint8_t*)p.wimg + (size_t)kc * N * 256;
-        for (int i = tid; i < n16; i += kThreads) cp_async16(sW + (size_t)i * 16, src + (size_t)i * 16);
-        cp_async_commit();
-      }
-      if (kStaged || !w_resident) cp_async_wait_all();
-      __syncthreads();                                   // raw slab landed; previous epilogue fully retired
-
-      // ---- build the operand chunk
-      const int ch0 = kc * 64;
-      if (PRO == PRO_SPATIAL || PRO == PRO_DY) {
-        const float* sX = (const float*)sRaw;
-        const float* sZ = (const float*)(sR + r_z * kRegionBytes);
-        const int kmod = (int)(((unsigned)kc * (unsigned)step64) % (unsigned)V);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int c = ch0 + j * 32 + lane;
-          int cm = (j ? l32mod : lmod) + kmod;            // c % V without dividing c
-          if (cm >= V) cm -= V;
-          uint8_t* blk = sOp + j * kBlockBytes;
-#pragma unroll
-          for (int ui = 0; ui < kUI; ++ui) {
-            const int u = warp + ui * kWarps;
-            if (u < V) {
-              int sv = u + cm;
-              if (sv >= V) sv -= V;
-              const float* src = sX + sv * 64 + j * 32 + lane;
-              float val[kGMax];
-              if (PRO == PRO_SPATIAL) {
-                const float mm = __ldg(p.pro_a + u * K + c);
-#pragma unroll
-                for (int g = 0; g < kGMax; ++g) val[g] = (g < ng) ? src[g * V * 64] * mm : 0.f;
-              } else {
-                const float* srz = sZ + sv * 64 + j * 32 + lane;
-                const float al = __ldg(p.pro_a + sv * K + c), be = __ldg(p.pro_b + sv * K + c),
-                            ga = __ldg(p.pro_c + sv * K + c);
-                float zz[kGMax];
-#pragma unroll
-                for (int g = 0; g < kGMax; ++g) {
-                  val[g] = (g < ng) ? src[g * V * 64] : 0.f;
-                  zz[g] = (g < ng) ? srz[g * V * 64] : 0.f;
-                }
-#pragma unroll
-                for (int g = 0; g < kGMax; ++g) val[g] = fmaf(al, val[g], fmaf(be, zz[g], ga));
-              }
-#pragma unroll
-              for (int g = 0; g < kGMax; ++g)
-                if (g < ng) *(float*)(blk + dst_off[ui][g]) = to_tf32(val[g]);
-            }
-          }
-        }
-      } else if (PRO == PRO_LERP) {
-        const int T = p.T;
-        const size_t frame = (size_t)V * K;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int c = ch0 + j * 32 + lane;
-          uint8_t* blk = sOp + j * kBlockBytes + row_off0;
-          const int y1 = (int)sLerp[c];
-          const float fy = sLerp[K + c], sa = sLerp[2 * K + c], sb = sLerp[3 * K + c];
-          const float* base = p.in0 + ((long long)row0 * K + c + (long long)y1 * (long long)frame);
-          int g = 0, v = warp;                           // rows r = warp + 8 i  ->  (g, v) by increments
-#pragma unroll 1
-          for (int ib = 0; ib < kTileRows / kWarps; ib += 8) {   // 16 independent loads in flight per batch
-            float u0[8], u1[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int r = warp + (ib + k) * kWarps;
-              const int ta = sGrpT[g] + y1;
-              const float* q = base + (size_t)r * K;
-              const bool in = r < rows_valid;
-              u0[k] = (in && ta >= 0 && ta < T) ? fmaf(sa, __ldg(q), sb) : 0.f;
-              u1[k] = (in && ta + 1 >= 0 && ta + 1 < T) ? fmaf(sa, __ldg(q + frame), sb) : 0.f;
-              v += kWarps;
-              if (v >= V) v -= V, ++g;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (warp + (ib + k) * kWarps < rows_valid)
-                *(float*)(blk + (ib + k) * 1024) = to_tf32(fmaf(fy, u1[k] - u0[k], u0[k]));
-          }
-        }
-      } else {  // PRO_PLAIN
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float* base = p.in0 + (size_t)row0 * K + ch0 + j * 32 + lane;
-          uint8_t* blk = sOp + j * kBlockBytes + row_off0;
-          float val[kTileRows / kWarps];
-#pragma unroll
-          for (int i = 0; i < kTileRows / kWarps; ++i)
-            val[i] = (warp + i * kWarps < rows_valid) ? __ldg(base + (size_t)(warp + i * kWarps) * K) : 0.f;
-#pragma unroll
-          for (int i = 0; i < kTileRows / kWarps; ++i)
-            if (warp + i * kWarps < rows_valid) *(float*)(blk + i * 1024) = to_tf32(val[i]);
-        }
-      }
-      fence_proxy_async();
-      __syncthreads();
-
-      // ---- prefetch the next raw slab of THIS tile (the raw region is free once the operand chunk is built)
-      if (kStaged && kc + 1 < kchunks) {
-        stage_rows_async(sRaw, p.in0, row0, rows_valid, K, (kc + 1) * 64, tid);
-        if (PRO == PRO_DY) stage_rows_async(sR + r_z * kRegionBytes, p.in1, row0, rows_valid, K, (kc + 1) * 64, tid);
-        cp_async_commit();
-      }
-
-      // ---- contraction: D[128 x N] (+)= A[128 x 64] * W[N x 64]^T
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(sOp);
-        const uint32_t w0 = smem_u32(sW) + (w_resident ? (uint32_t)kc * (uint32_t)N * 256u : 0u);
-#pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8) {
-          const uint32_t blk = k8 >> 2, sub = k8 & 3;
-          umma_tf32(tmem_base, umma_desc(a0 + blk * kBlockBytes + sub * 32, 16, 1024),
-                    umma_desc(w0 + blk * (uint32_t)N * 128u + sub * 32, 16, 1024), idesc, (kc | k8) ? 1u : 0u);
-        }
-        tc_commit(&bar_mma);
-      }
-    }
-    mbar_wait(&bar_mma, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after();
-
-    // ---- prefetch chunk 0 of the NEXT tile into the operand region (free now); the epilogue stages in the raw region
-    if (kStaged && next_tile < ntiles) {
-      const int ngn = (int)((p.groups - next_tile * G) < G ? (p.groups - next_tile * G) : G);
-      stage_rows_async(sOp, p.in0, next_tile * G * V, ngn * V, K, 0, tid);
-      if (PRO == PRO_DY) stage_rows_async(sR + r_z * kRegionBytes, p.in1, next_tile * G * V, ngn * V, K, 0, tid);
-      cp_async_commit();
-    }
-
-    // ================================================================== epilogue, 64 output channels at a time
-    float* sS = (float*)(kStaged ? sRaw : sOp);
-    float* __restrict__ out_ = p.out;
-    const float* __restrict__ res_ = p.res;
-    const float* __restrict__ res2_ = p.res2;
-    const float* __restrict__ res2m_ = p.res2m;
-    const float* __restrict__ xin_ = p.xin;
-#pragma unroll 1
-    for (int nc = 0; nc < NCH; ++nc) {
-      {  // TMEM -> staging: warp handles lane quarter (warp & 3), column half (warp >> 2)
-        const int q = warp & 3, hf = warp >> 2;
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(nc * 64 + hf * 32), v);
-        const int row = q * 32 + lane;
-        float4* dst = (float4*)(sS + row * kStagePitch + hf * 32);
-        const float* bb = sBias + nc * 64 + hf * 32;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst[i] = make_float4(v[4 * i] + bb[4 * i], v[4 * i + 1] + bb[4 * i + 1], v[4 * i + 2] + bb[4 * i + 2],
-                               v[4 * i + 3] + bb[4 * i + 3]);
-      }
-      tc_fence_before();
-      __syncthreads();
-
-      if (EPI == EPI_ROT_RAW || EPI == EPI_ROT_FUSED || EPI == EPI_SPATIAL_BWD) {
-        const int nmod = (int)(((unsigned)nc * (unsigned)step64) % (unsigned)V);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int dl = j * 32 + lane, d = nc * 64 + dl;
-          int dm = (j ? l32mod : lmod) + nmod;               // d % V
-          if (dm >= V) dm -= V;
-#pragma unroll
-          for (int vi = 0; vi < kUI; ++vi) {
-            const int v = warp + vi * kWarps;
-            if (v < V) {
-              int sv = v - dm;                               // (v - d) mod V
-              if (sv < 0) sv += V;
-              const float* src = sS + sv * kStagePitch + dl;
-              const size_t o0 = (size_t)(row0 + v) * N + d;
-              float zv[kGMax];
-#pragma unroll
-              for (int g = 0; g < kGMax; ++g) zv[g] = (g < ng) ? src[g * V * kStagePitch] : 0.f;
-              if (EPI == EPI_ROT_RAW) {
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int g = 0; g < kGMax; ++g)
-                  if (g < ng) {
-                    out_[o0 + (size_t)g * V * N] = zv[g];
-                    s1 += zv[g];
-                    s2 = fmaf(zv[g], zv[g], s2);
-                  }
-                if (kAccSmem) {
-                  sAcc0[v * N + d] += s1;
-                  sAcc1[v * N + d] += s2;
-                } else {
-                  acc0[0][j][vi] += s1;
-                  acc1[0][j][vi] += s2;
-                }
-              } else if (EPI == EPI_ROT_FUSED) {
-                const float sc = __ldg(p.epi_a + v * N + d), sh = __ldg(p.epi_b + v * N + d);
-                float rv[kGMax];
-#pragma unroll
-                for (int g = 0; g < kGMax; ++g) rv[g] = (res_ && g < ng) ? __ldg(res_ + o0 + (size_t)g * V * N) : 0.f;
-#pragma unroll
-                for (int g = 0; g < kGMax; ++g)
-                  if (g < ng) {
-                    const float r = fmaf(zv[g], sc, sh) + rv[g];
-                    out_[o0 + (size_t)g * V * N] = p.relu ? fmaxf(r, 0.f) : r;
-                  }
-              } else {  // EPI_SPATIAL_BWD: v is the input joint w, sv the operand joint u = (w - c) mod V
-                const float mm = __ldg(p.epi_a + sv * N + d);
-                float rv[kGMax], gv[kGMax], yv[kGMax], xv[kGMax];
-#pragma unroll
-                for (int g = 0; g < kGMax; ++g) {               // all independent loads first (20 in flight per thread)
-                  const size_t o = o0 + (size_t)g * V * N;
-                  const bool in = g < ng;
-                  rv[g] = (res_ && in) ? __ldg(res_ + o) : 0.f;
-                  gv[g] = (res2_ && in) ? __ldg(res2_ + o) : 0.f;
-                  yv[g] = (res2_ && in) ? (res2m_ ? __ldg(res2m_ + o) : 1.f) : 0.f;   // no y: g_y is already masked
-                  xv[g] = in ? __ldg(xin_ + o) : 0.f;
-                }
-                float dmk = 0.f;
-#pragma unroll
-                for (int g = 0; g < kGMax; ++g)
-                  if (g < ng) {
-                    const float gxv = fmaf(zv[g], mm, rv[g]) + (yv[g] > 0.f ? gv[g] : 0.f);
-                    out_[o0 + (size_t)g * V * N] = (p.relu && !(xv[g] > 0.f)) ? 0.f : gxv;
-                    dmk = fmaf(zv[g], xv[g], dmk);
-                  }
-                if (kAccSmem) sAcc0[sv * N + d] += dmk;
-                else acc0[0][j][vi] += dmk;
-              }
-            }
-          }
-        }
-      } else {  // EPI_LINEAR
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int dl = j * 32 + lane;
-          const float* src = sS + warp * kStagePitch + dl;
-          float* __restrict__ dst = out_ + (size_t)(row0 + warp) * N + nc * 64 + dl;
-          float zv[kTileRows / kWarps];
-#pragma unroll
-          for (int i = 0; i < kTileRows / kWarps; ++i) zv[i] = src[i * kWarps * kStagePitch];
-#pragma unroll
-          for (int i = 0; i < kTileRows / kWarps; ++i)
-            if (warp + i * kWarps < rows_valid) dst[(size_t)i * kWarps * N] = p.relu ? fmaxf(zv[i], 0.f) : zv[i];
-        }
-      }
-      if (nc + 1 < NCH) __syncthreads();   // staging is reused by the next 64-column chunk
-    }
-    tc_fence_before();
-    if (kStaged) {                          // roles swap: the operand region now holds the next tile's raw slab
-      const int t = r_raw;
-      r_raw = r_op;
-      r_op = t;
-    }
-    // (the __syncthreads at the top of the next tile's K loop retires this epilogue before anything is overwritten)
-  }
-
-  // ---------------------------------------------------------------- flush cross-tile reductions
-  if (kAccSmem) {
-    __syncthreads();
-    if (EPI == EPI_ROT_RAW) {
-      for (int i = tid; i < V * N; i += kThreads) {
-        atomicAdd(p.stats + 2 * (size_t)i, (double)sAcc0[i]);
-        atomicAdd(p.stats + 2 * (size_t)i + 1, (double)sAcc1[i]);
-      }
-    } else if (EPI == EPI_SPATIAL_BWD) {
-      for (int i = tid; i < V * N; i += kThreads) atomicAdd(p.red0 + i, (double)sAcc0[i]);
-    }
-  } else if (EPI == EPI_ROT_RAW) {
-#pragma unroll
-    for (int nc = 0; nc < NACC; ++nc)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int vi = 0; vi < kUI; ++vi) {
-          const int v = warp + vi * kWarps, d = nc * 64 + j * 32 + lane;
-          if (v < V) {
-            atomicAdd(p.stats + 2 * ((size_t)v * N + d), (double)acc0[nc][j][vi]);
-            atomicAdd(p.stats + 2 * ((size_t)v * N + d) + 1, (double)acc1[nc][j][vi]);
-          }
-        }
-  } else if (EPI == EPI_SPATIAL_BWD) {
-#pragma unroll
-    for (int nc = 0; nc < NACC; ++nc)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int vi = 0; vi < kUI; ++vi) {
-          const int w = warp + vi * kWarps, c = nc * 64 + j * 32 + lane;
-          if (w < V) atomicAdd(p.red0 + (size_t)pmod(w - c, V) * N + c, (double)acc0[nc][j][vi]);
-        }
-  }
-
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
-}
-
-// ------------------------------------------------------------------------------------------------ host side
-template <int PRO, int EPI, int NCH>
-static int launch_variant(const SgcnRowGemm& p, cudaStream_t s) {
-  const size_t smem = 1024 + rowgemm_w_bytes(p.K, p.N) + (size_t)rowgemm_regions(PRO) * kRegionBytes +
-                      (size_t)(p.N + (PRO == PRO_LERP ? 4 * p.K : 0)) * 4 + rowgemm_acc_bytes(EPI, p.V, p.N) + 64;
-  auto kern = rowgemm_kernel<PRO, EPI, NCH>;
-  static thread_local size_t configured = 0;            // per instantiation: largest dynamic smem requested so far
-  static thread_local int regs_per_thread = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_cuda_error("rowgemm smem attribute", e);
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return set_cuda_error("rowgemm carveout attribute", e);
-    cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, kern);
-    if (e != cudaSuccess) return set_cuda_error("rowgemm attributes", e);
-    regs_per_thread = fa.numRegs;
-    configured = smem;
-  }
-  // resident CTAs per SM: shared memory (1 KiB reserved per CTA), registers, TMEM columns
-  int occ = (int)(kSmemPerSM / (smem + 1024 + 64));
-  const int regs_alloc = ((regs_per_thread + 7) / 8) * 8;
-  const int occ_regs = regs_alloc > 0 ? 65536 / (regs_alloc * kThreads) : 1;
-  if (occ > occ_regs) occ = occ_regs;
-  const int tmem_cols = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256);
-  if (occ * tmem_cols > 512) occ = 512 / tmem_cols;
-  if (occ > 4) occ = 4;
-  if (occ < 1) return set_error("rowgemm: kernel does not fit on an SM");
-  const long long ntiles = (p.groups + p.G - 1) / p.G;
-  if (ntiles == 0) return 0;
-  long long grid = (long long)num_sms() * occ;
-  if (grid > ntiles) grid = ntiles;
-  kern<<<(unsigned)grid, kThreads, smem, s>>>(p);
-  return check_launch("rowgemm_kernel");
-}
-
-template <int PRO, int EPI>
-static int launch_nch(const SgcnRowGemm& p, cudaStream_t s) {
-  switch (p.N >> 6) {
-    case 1: return launch_variant<PRO, EPI, 1>(p, s);
-    case 2: return launch_variant<PRO, EPI, 2>(p, s);
-    case 4: return launch_variant<PRO, EPI, 4>(p, s);
-    default: return set_error("rowgemm: N must be 64, 128 or 256");
-  }
-}
 
 int spatial_bwd_launch(const SgcnRowGemm& p, cudaStream_t s);            // spatial_bwd.cu
 int spatial_fwd_launch(const SgcnRowGemm& p, int fused, cudaStream_t s);  // spatial_fwd.cu
@@ -514,43 +32,35 @@ extern "C" int sgcn_rowgemm(const SgcnRowGemm* pp, int pro, int epi, void* strea
   using namespace sgcn;
   if (!pp) return set_error("sgcn_rowgemm: null params");
   const SgcnRowGemm& p = *pp;
-  if (p.V < 25 || p.V > 8 * kUI) return set_error("sgcn_rowgemm: num_point must be in [25, 40]");
-  if (p.G < 1 || p.G > kGMax || p.G * p.V > kTileRows) return set_error("sgcn_rowgemm: need G <= 5 and G*V <= 128");
+  if (p.V != 25 && p.V != 33) return set_error("sgcn_rowgemm: num_point must be 25 (NTU) or 33 (MediaPipe)");
+  if (p.G != 128 / p.V) return set_error("sgcn_rowgemm: G must be 128 / num_point whole (n,t) groups per tile");
   const bool concat = pro == PRO_PLAIN && p.k0 > 0 && (p.K == 192 || p.K == 384);   // [g | x] input-gradient GEMM
   if (p.K != 64 && p.K != 128 && p.K != 256 && !concat) return set_error("sgcn_rowgemm: K must be 64, 128 or 256");
   if (p.N != 64 && p.N != 128 && p.N != 256) return set_error("sgcn_rowgemm: N must be 64, 128 or 256");
   if (p.groups < 0) return set_error("sgcn_rowgemm: negative group count");
   if (!p.in0 || !p.out || !p.wimg) return set_error("sgcn_rowgemm: null tensor");
   cudaStream_t s = (cudaStream_t)stream;
-  // warp-specialised kernels (fused_gemm.cuh, spatial_bwd.cu) cover the skeletons of the reference's configs;
-  // other joint counts in [25, 40] keep the generic kernel of this file
-  const bool fast = p.V == 25 || p.V == 33;
   if (pro == PRO_SPATIAL && epi == EPI_ROT_RAW) {
     if (!p.pro_a || !p.stats) return set_error("spatial fwd: null mask / stats");
-    if (fast) return spatial_fwd_launch(p, 0, s);
-    return launch_nch<PRO_SPATIAL, EPI_ROT_RAW>(p, s);
+    return spatial_fwd_launch(p, 0, s);
   }
   if (pro == PRO_SPATIAL && epi == EPI_ROT_FUSED) {
     if (!p.pro_a || !p.epi_a || !p.epi_b) return set_error("spatial fwd (fused): null table");
-    if (fast) return spatial_fwd_launch(p, 1, s);
-    return launch_nch<PRO_SPATIAL, EPI_ROT_FUSED>(p, s);
+    return spatial_fwd_launch(p, 1, s);
   }
   if (pro == PRO_LERP && epi == EPI_LINEAR) {
     if (!p.pro_a || !p.pro_b || !p.pro_c || p.T < 1) return set_error("temporal fwd: null table / bad T");
-    if (fast && p.K == p.N) return temporal_gemm_launch(p, 1, s);
-    return launch_nch<PRO_LERP, EPI_LINEAR>(p, s);
+    if (p.K != p.N) return set_error("temporal fwd: the 1x1 convolution of Shift_tcn has in == out channels");
+    return temporal_gemm_launch(p, 1, s);
   }
   if (pro == PRO_PLAIN && epi == EPI_LINEAR) {
     if (p.k0 > 0 && (!p.in1 || p.k0 % 64 != 0 || p.k0 >= p.K)) return set_error("plain GEMM: bad two-source split");
-    if (fast) return temporal_gemm_launch(p, 0, s);
-    if (p.k0 > 0 || p.in0_gs > 1 || p.out_gs > 1 || p.accum) return set_error("plain GEMM: strided / two-source form needs num_point 25 or 33");
-    return launch_nch<PRO_PLAIN, EPI_LINEAR>(p, s);
+    return temporal_gemm_launch(p, 0, s);
   }
   if (pro == PRO_DY && epi == EPI_SPATIAL_BWD) {
     if (!p.in1 || !p.pro_a || !p.pro_b || !p.pro_c || !p.epi_a || !p.xin || !p.red0)
       return set_error("spatial bwd: null tensor / table");
-    if (fast) return spatial_bwd_launch(p, s);
-    return launch_nch<PRO_DY, EPI_SPATIAL_BWD>(p, s);
+    return spatial_bwd_launch(p, s);
   }
   return set_error("sgcn_rowgemm: unsupported prologue/epilogue combination");
 }

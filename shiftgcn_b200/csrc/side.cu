@@ -57,9 +57,13 @@ __global__ void __launch_bounds__(kThreads) fold_kernel(const SgcnSideFold p) {
     if (var_r < 0.0) var_r = 0.0;
     if (tid == 0 && p.running_mean) {
       const double unbiased = var_r * (p.rows / (p.rows > 1.0 ? p.rows - 1.0 : 1.0));
-      p.running_mean[d] = (float)((1.0 - p.momentum) * (double)p.running_mean[d]) + (float)(p.momentum * mean_r);
-      p.running_var[d] = (float)((1.0 - p.momentum) * (double)p.running_var[d]) + (float)(p.momentum * unbiased);
-      if (d == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
+      // momentum < 0 = nn.BatchNorm(momentum=None): cumulative average, counter already incremented by the caller
+      const bool cma = p.momentum < 0.0;
+      const double mom = !cma ? p.momentum
+                              : ((p.num_batches_tracked && *p.num_batches_tracked > 0) ? 1.0 / (double)*p.num_batches_tracked : 0.0);
+      p.running_mean[d] = (float)((1.0 - mom) * (double)p.running_mean[d]) + (float)(mom * mean_r);
+      p.running_var[d] = (float)((1.0 - mom) * (double)p.running_var[d]) + (float)(mom * unbiased);
+      if (!cma && d == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
     }
     if (d == 0)
       for (int c = tid; c < C; c += kThreads) p.sx[c] = p.sx_sums[2 * c];

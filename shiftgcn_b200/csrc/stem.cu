@@ -463,14 +463,14 @@ extern "C" int sgcn_stem_bwd(const SgcnStem* p, int mode, void* stream) {
     if (!p->al || !p->be || !p->ga || !p->a2 || !p->b2 || !p->c2 || !p->dw_raw || !p->dmask_raw || !p->dx)
       return set_error("sgcn_stem_bwd(apply): null pointer");
     const size_t smem = (size_t)2 * stem::kGB * p->V * stem::D * sizeof(float);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};         // one bit per device (the attribute is per device)
+    if (needs_configure(configured)) {
       const int cap = 2 * stem::kGB * 39 * stem::D * (int)sizeof(float);
       cudaError_t e = cudaFuncSetAttribute(stem::stem_bwd_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(stem::stem_bwd_apply_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
       if (e != cudaSuccess) return set_cuda_error("stem_bwd_apply smem attribute", e);
-      configured = true;
+      mark_configured(configured);
     }
     if (l.jp <= 2) stem::stem_bwd_apply_kernel<2><<<grid, threads, smem, (cudaStream_t)stream>>>(*p, per, rev);
     else stem::stem_bwd_apply_kernel<3><<<grid, threads, smem, (cudaStream_t)stream>>>(*p, per, rev);

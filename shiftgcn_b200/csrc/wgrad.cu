@@ -480,15 +480,15 @@ static int launch_wgrad_cc(const SgcnWgrad& p, cudaStream_t s) {
   if (geo.nstages < 1 || geo.G != G) return set_error("sgcn_wgrad: operand stage does not fit in shared memory");
   const size_t smem = 1024 + (size_t)geo.nstages * geo.stage + 64;
   auto kern = wgrad_kernel<MODE, V, CA, CB>;
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
+  static std::atomic<unsigned long long> configured{0};           // one bit per device; smem is fixed per instantiation
+  if (needs_configure(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error("wgrad smem attribute", e);
-    configured = smem;
+    mark_configured(configured);
   }
   const long long ntiles = (p.groups + G - 1) / G;
   if (ntiles == 0) return 0;
-  long long grid = num_sms();
+  long long grid = tile_ctas();
   if (grid > ntiles) grid = ntiles;
   kern<<<(unsigned)grid, kWgThreads, smem, s>>>(p, geo, next_direction());
   return check_launch("wgrad_kernel");

@@ -11,12 +11,24 @@ and its per-parameter SGD groups (main.py:301-322):
     single-GPU large-batch semantics (SURVEY.md App. E-7 documents how DataParallel differs: it sums the
     already-constrained per-replica +-0.01 values);
   * SGD with momentum / Nesterov and the reference's decay rules: 1e-4 everywhere (BN and biases included),
-    1e-3 for ``Linear_weight``, 0 for ``Feature_Mask`` (main.py:307-317), applied as a handful of flat tensor ops.
+    1e-3 for ``Linear_weight``, 0 for ``Feature_Mask`` (main.py:307-317): scale, K5, decay and the momentum update
+    are ONE kernel over the flat buffers (``sgcn_sgd_epilogue``);
+  * the learning rate lives in device memory (``set_lr`` / ``reference_lr`` = main.py:342-351), so the captured CUDA
+    graph of a whole step follows the warm-up / step-decay schedule without re-capture.
 
 The batch is sharded by the caller (each rank feeds its own samples); there is no collective on the data path.
 """
 import torch
 import torch.distributed as dist
+
+from . import ops
+
+
+def reference_lr(epoch, base_lr=0.1, warm_up_epoch=0, step=(60, 80, 100)):
+    """``Processor.adjust_learning_rate`` (main.py:342-351): linear warm-up, then x0.1 at every epoch in ``step``"""
+    if epoch < warm_up_epoch:
+        return base_lr * (epoch + 1) / warm_up_epoch
+    return base_lr * (0.1 ** sum(1 for s in step if epoch >= s))
 
 
 def reference_weight_decay(name):
@@ -69,6 +81,13 @@ class FlatSGDTrainer:
             self.grad_views.append(self.flat_grad[off:off + sz].view_as(p.data))
             p.grad = None
             self.weight_decay[off:off + sz] = wd_fn(n)
+        # element i of the parameter buffer is a ypos entry whose reduced raw sum sits at flat_grad[n_param + ypos_src[i]]
+        self.ypos_src = torch.full((self.n_param,), -1, device=dev, dtype=torch.int32)
+        for g_off, raw_off, cnt, _ in self.ypos_slices:
+            self.ypos_src[g_off:g_off + cnt] = torch.arange(raw_off - self.n_param, raw_off - self.n_param + cnt,
+                                                            device=dev, dtype=torch.int32)
+        # [lr, momentum, gradient scale] in device memory: the captured graph reads them at replay time
+        self.hyper = torch.tensor([lr, momentum, 1.0], device=dev, dtype=torch.float32)
         self.steps = 0
         if self.world > 1:                           # replicas start from rank 0's weights and buffers
             dist.broadcast(self.flat_param, 0, group=self.group)
@@ -100,34 +119,54 @@ class FlatSGDTrainer:
         torch._foreach_copy_([self.flat_grad[raw_off:raw_off + cnt] for _, raw_off, cnt, _ in self.ypos_slices],
                              [shift._raw_ypos_grad.reshape(-1) for *_, shift in self.ypos_slices])
 
+    def set_lr(self, lr):
+        """takes effect on the next step, eager or replayed (the value is read from device memory)"""
+        self.lr = float(lr)
+        self.hyper[0:1].fill_(self.lr)
+
+    def adjust_learning_rate(self, epoch, base_lr=0.1, warm_up_epoch=0, step=(60, 80, 100)):
+        """the reference's schedule (main.py:342-351) applied to this trainer; returns the learning rate"""
+        lr = reference_lr(epoch, base_lr, warm_up_epoch, step)
+        self.set_lr(lr)
+        return lr
+
     def reduce_gradients(self):
-        """one collective for everything, then the K5 constraint on the reduced raw sums"""
-        have_raw = all(getattr(s, "_raw_ypos_grad", None) is not None for *_, s in self.ypos_slices)
-        if have_raw:
+        """one collective for gradients and raw shift-position sums alike"""
+        self._have_raw = all(getattr(s, "_raw_ypos_grad", None) is not None for *_, s in self.ypos_slices)
+        if self._have_raw and self.ypos_slices:
             self._collect_raw()
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG if self.flat_grad.is_cuda else dist.ReduceOp.SUM,
                             group=self.group)
             if not self.flat_grad.is_cuda:           # gloo has no AVG
                 self.flat_grad.div_(self.world)
-        if have_raw:                                 # K5 on the whole raw tail at once, then scatter to the ypos slots
-            raw = self.flat_grad[self.n_param:]
-            g = torch.where(raw != 0, torch.sign(raw) * 0.01, torch.full_like(raw, 0.0001))
-            torch._foreach_copy_([self.flat_grad[g_off:g_off + cnt] for g_off, _, cnt, _ in self.ypos_slices],
-                                 [g[raw_off - self.n_param:raw_off - self.n_param + cnt] for _, raw_off, cnt, _ in self.ypos_slices])
 
     def step(self):
-        """torch.optim.SGD semantics (momentum buffer initialised with the first gradient, optional Nesterov)"""
-        g = self.flat_grad[:self.n_param]
-        d = torch.addcmul(g, self.weight_decay, self.flat_param)
-        if self.momentum != 0:
-            if self.steps == 0:
-                self.momentum_buf.copy_(d)
-            else:
-                self.momentum_buf.mul_(self.momentum).add_(d)
-            d = d.add(self.momentum_buf, alpha=self.momentum) if self.nesterov else self.momentum_buf
-        self.flat_param.add_(d, alpha=-self.lr)
+        """K5 on the reduced raw sums, weight decay, SGD momentum / Nesterov (torch.optim.SGD semantics: the momentum
+        buffer starts as the first gradient, which a zero-initialised buffer reproduces)."""
+        have_raw = getattr(self, "_have_raw", False) and bool(self.ypos_slices)
+        if self.flat_param.is_cuda:
+            ops.sgd_epilogue(self.flat_param, self.flat_grad, self.momentum_buf, self.weight_decay,
+                             self.ypos_src if have_raw else None, self.hyper, self.n_param, self.nesterov)
+        else:
+            self._step_host(have_raw)
         self.steps += 1
+
+    def _step_host(self, have_raw):
+        """The same arithmetic with tensor ops for CPU tensors: used ONLY by the gloo tests of the multi-process logic
+        (tests/test_dp.py); CUDA buffers always take the kernel above."""
+        g = self.flat_grad[:self.n_param]
+        if have_raw:
+            raw = self.flat_grad[self.n_param:]
+            k5 = torch.where(raw != 0, torch.sign(raw) * 0.01, torch.full_like(raw, 0.0001))
+            sel = self.ypos_src >= 0
+            g[sel] = k5[self.ypos_src[sel].long()]
+        lr, mom = float(self.hyper[0]), float(self.hyper[1])
+        d = torch.addcmul(g, self.weight_decay, self.flat_param)
+        if mom != 0:
+            self.momentum_buf.mul_(mom).add_(d)
+            d = d.add(self.momentum_buf, alpha=mom) if self.nesterov else self.momentum_buf
+        self.flat_param.add_(d, alpha=-lr)
 
     def train_step(self, x, label, loss_fn=torch.nn.functional.cross_entropy):
         """forward + backward + all-reduce + SGD on this rank's shard; returns the (local) loss tensor"""
@@ -151,7 +190,7 @@ class FlatSGDTrainer:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(max(warmup, 1)):              # also initialises the momentum buffer (steps == 0 branch)
+            for _ in range(max(warmup, 1)):
                 self.train_step(self._static_x, self._static_y, loss_fn)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()

@@ -20,21 +20,47 @@ Kernel schedule of one identity unit in training (a = one activation tensor pass
             g_x = spatial backward-data (+ both residuals)    5a      sgcn_rowgemm  DY / SPATIAL_BWD
             dW                                                3a      sgcn_wgrad  SPATIAL
 """
+import threading
+
 import torch
 
 from . import ops
 
 BN_EPS = 1e-5
-# Function.forward always runs with grad mode off, and needs_input_grad ignores torch.no_grad(): the modules record the
-# caller's grad mode here right before .apply so that inference takes the fully fused (nothing saved) kernels
-GRAD_MODE = True
 PREMASK = True      # chained units hand each other ReLU-masked gradients (see _links); False = every unit masks for itself
+
+# Function.forward always runs with grad mode off, and needs_input_grad ignores torch.no_grad(): the modules record the
+# caller's grad mode right before .apply so that inference takes the fully fused (nothing saved) kernels.  Per host
+# thread: nn.DataParallel (the reference's multi-GPU mode, main.py:294-299) runs one replica per thread.
+_state = threading.local()
+
+
+def set_grad_mode(enabled):
+    _state.grad_mode = bool(enabled)
+
+
+def grad_mode():
+    return getattr(_state, "grad_mode", True)
+
+
+def bn_training(bn):
+    """does this BatchNorm normalise with batch statistics?  Each BatchNorm decides for itself, exactly like
+    nn.BatchNorm.forward: a frozen bn (``bn.eval()`` inside a training model) keeps its running statistics."""
+    return bool(bn.training or not bn.track_running_stats or bn.running_mean is None)
 
 
 def _bn_args(bn):
-    """(gamma, beta, running_mean, running_var, nbt, momentum) of a torch BatchNorm module"""
-    mom = 0.1 if bn.momentum is None else bn.momentum
-    return bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, mom
+    """(gamma, beta, running_mean, running_var, nbt, momentum) of a torch BatchNorm module.  momentum=None (cumulative
+    moving average) is passed as -1 with num_batches_tracked incremented HERE: the finalize kernels then use the factor
+    1 / num_batches_tracked (include/shiftgcn_b200.h:sgcn_bn_fwd_finalize)."""
+    track = bn.track_running_stats and bn.running_mean is not None
+    rmean, rvar, nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if track else (None, None, None)
+    mom = bn.momentum
+    if mom is None:
+        mom = -1.0
+        if track and bn.training:
+            nbt.add_(1)
+    return bn.weight, bn.bias, rmean, rvar, nbt, mom
 
 
 class Workspace:
@@ -65,7 +91,7 @@ class Workspace:
 
 
 # ================================================================================================ spatial unit
-def spatial_forward(x, res, W, bias, mask, bn, training, ws, fuse_eval, h_stats=None):
+def spatial_forward(x, res, W, bias, mask, bn, ws, fuse_eval, h_stats=None):
     """x: (n,T,V,C) rows; res: None (identity, needs C == D) or (n,T,V,D) rows already normalised.
 
     Returns (h, saved) where saved holds what the backward needs (None in the fused eval path).
@@ -76,6 +102,7 @@ def spatial_forward(x, res, W, bias, mask, bn, training, ws, fuse_eval, h_stats=
     dev = x.device
     mm, mm_rot = ops.mask_prepare(mask.reshape(V, C))
     wimg = ops.weight_image(W, 1, D, D, C)                         # B[n=d][k=c] = W[c][d]
+    training = bn_training(bn)
     gamma, beta, rmean, rvar, nbt, mom = _bn_args(bn)
     resid = x if res is None else res
     if fuse_eval:
@@ -137,7 +164,7 @@ def spatial_backward(saved, gh, W, mask, gamma, vd_sums_ready, ws, unit_res=None
 
 
 # ================================================================================================ first spatial unit
-def stem_forward(x, W, bias, mask, bn, Wd, bd, bn2, training, ws):
+def stem_forward(x, W, bias, mask, bn, Wd, bd, bn2, ws):
     """l1.gcn1 = Shift_gcn(3, 64) with its conv + BN `down` branch (model/shift_gcn.py:82-86,121-142); x: (n,T,V,3)."""
     n, T, V, C = x.shape
     D = W.shape[1]
@@ -148,15 +175,18 @@ def stem_forward(x, W, bias, mask, bn, Wd, bd, bn2, training, ws):
     common = dict(groups=R, V=V, D=D, x=x, maskmul=mm, W=W, bias=bias.reshape(D), Wd=Wd2, bd=bd)
     g1, b1, rm1, rv1, nbt1, mom1 = _bn_args(bn)
     g2, b2, rm2, rv2, nbt2, mom2 = _bn_args(bn2)
-    s_vd = s_r = None
-    if training:
-        s_vd, s_r = ws.get("stem_vd", 2 * V * D, dev), ws.get("stem_r", 2 * D, dev)
+    tr1, tr2 = bn_training(bn), bn_training(bn2)
+    s_vd, s_r = ws.get("stem_vd", 2 * V * D, dev), ws.get("stem_r", 2 * D, dev)
+    if tr1 or tr2:
         ops.stem_fwd(0, stats_vd=s_vd, stats_r=s_r, **common)
-    mean1, invstd1, sc1, sh1 = ops.bn_fwd_finalize(s_vd, g1, b1, rm1, rv1, nbt1, V * D, R, mom1, bn.eps, training)
-    mean2, invstd2, sc2, sh2 = ops.bn_fwd_finalize(s_r, g2, b2, rm2, rv2, nbt2, D, R * V, mom2, bn2.eps, training)
+    mean1, invstd1, sc1, sh1 = ops.bn_fwd_finalize(s_vd if tr1 else None, g1, b1, rm1, rv1, nbt1, V * D, R, mom1, bn.eps, tr1)
+    mean2, invstd2, sc2, sh2 = ops.bn_fwd_finalize(s_r if tr2 else None, g2, b2, rm2, rv2, nbt2, D, R * V, mom2, bn2.eps, tr2)
+    if tr1 != tr2:                 # the statistics kernel fills both buffers; the frozen BatchNorm does not consume its own
+        (s_r if tr1 else s_vd).zero_()
     h = torch.empty((n, T, V, D), device=dev, dtype=torch.float32)
     ops.stem_fwd(1, sc1=sc1, sh1=sh1, sc2=sc2, sh2=sh2, h=h, **common)
-    saved = dict(x=x, h=h, mm=mm, mean1=mean1, invstd1=invstd1, mean2=mean2, invstd2=invstd2, training=training)
+    saved = dict(x=x, h=h, mm=mm, mean1=mean1, invstd1=invstd1, mean2=mean2, invstd2=invstd2, training1=tr1,
+                 training2=tr2)
     return h, saved
 
 
@@ -166,13 +196,12 @@ def stem_backward(saved, g, W, bias, mask, gamma1, Wd, bd, gamma2, ws):
     D = W.shape[1]
     R = n * T
     dev = x.device
-    training = saved["training"]
     common = dict(groups=R, V=V, D=D, x=x, maskmul=mm, W=W, bias=bias.reshape(D), Wd=Wd.reshape(D, C), bd=bd, g=g, h=h)
     vd, rs = ws.get("stem_vd_bwd", 2 * V * D, dev), ws.get("stem_r_bwd", 2 * D, dev)
     ops.stem_bwd(0, mean1=saved["mean1"], invstd1=saved["invstd1"], mean2=saved["mean2"], invstd2=saved["invstd2"],
                  vd_sums=vd, r_sums=rs, **common)
-    f1 = ops.bn1d_bwd_finalize(vd, gamma1, saved["mean1"], saved["invstd1"], V, D, R, training)
-    f2 = ops.bn1d_bwd_finalize(rs, gamma2, saved["mean2"], saved["invstd2"], 1, D, R * V, training)
+    f1 = ops.bn1d_bwd_finalize(vd, gamma1, saved["mean1"], saved["invstd1"], V, D, R, saved["training1"])
+    f2 = ops.bn1d_bwd_finalize(rs, gamma2, saved["mean2"], saved["invstd2"], 1, D, R * V, saved["training2"])
     dw_raw, dm_raw = ws.get("stem_dw", 8 * D, dev), ws.get("stem_dmask", V * C, dev)
     dx = torch.empty_like(x)
     ops.stem_bwd(1, al=f1["alpha"], be=f1["beta"], ga=f1["gamma"], a2=f2["alpha"], b2=f2["beta"], c2=f2["gamma"],
@@ -185,7 +214,7 @@ def stem_backward(saved, g, W, bias, mask, gamma1, Wd, bd, gamma2, ws):
 
 
 # ================================================================================================ conv + BN side branches
-def side_forward(x, Wd, bd, bn, training, ws, gs=1):
+def side_forward(x, Wd, bd, bn, ws, gs=1):
     """BatchNorm2d(Conv2d_1x1(x)) on rows (`down` of Shift_gcn, model/shift_gcn.py:82-86; `tcn` residual, :31-45).
 
     x: (rows, C) with rows a multiple of V*... (any row count that is a multiple of the tile group size is fine: the
@@ -201,6 +230,7 @@ def side_forward(x, Wd, bd, bn, training, ws, gs=1):
     rows = n * T * V
     D = Wd.shape[0]
     dev = x.device
+    training = bn_training(bn)
     gamma, beta, rmean, rvar, nbt, mom = _bn_args(bn)
     Wd2 = Wd.detach().reshape(D, C)
     saved = dict(x=x, training=training, gs=gs)
@@ -214,9 +244,8 @@ def side_forward(x, Wd, bd, bn, training, ws, gs=1):
         XX = torch.zeros((C, C), device=dev, dtype=torch.float32)
         ops.wgrad(ops.WG_PLAIN, a_src=x, b_src=x, dw=XX, groups=n * T, V=V, CA=C, CB=C, a_gs=gs, b_gs=gs)
         counter = ws.get_int("side_counter", 1, dev)
-    track = bn.track_running_stats and rmean is not None
-    f = ops.side_fold(Wd2, None if bd is None else bd.detach(), gamma.detach(), beta.detach(), rmean if track else None,
-                      rvar if track else None, nbt if (track and training) else None, rows, bn.eps, mom, training,
+    f = ops.side_fold(Wd2, None if bd is None else bd.detach(), gamma.detach(), beta.detach(), rmean, rvar,
+                      nbt if training else None, rows, bn.eps, mom, training,
                       sx_sums=st, XX=XX, counter=counter)
     if training:
         saved.update(sx=f["sx"], XX=XX)
@@ -264,17 +293,22 @@ def side_backward(saved, G, sg, Wd, bd, gamma, ws, accum_into=None):
 
 
 # ================================================================================================ temporal unit
-def temporal_forward(h, res, relu, bn, ypos_in, Wt, bt, ypos_out, bn2, stride, training, ws, h_stats_ready):
+def temporal_forward(h, res, relu, bn, ypos_in, Wt, bt, ypos_out, bn2, stride, ws, h_stats_ready):
     """h: (n,T,V,C) rows -> y: (n,T/stride,V,C) rows = [relu](bn2(Shift_s(relu(conv(Shift_1(bn(h)))))) + res)"""
     n, T, V, C = h.shape
     To = T // stride
     dev = h.device
+    if res is not None and tuple(res.shape) != (n, To, V, C):
+        # e.g. a stride-2 conv residual of an odd-length sequence has ceil(T/2) frames: the reference fails on the add
+        raise RuntimeError(f"temporal unit: residual of shape {tuple(res.shape)} does not match the output "
+                           f"{(n, To, V, C)} (rows layout)")
+    tr_a, tr_b = bn_training(bn), bn_training(bn2)
     ga, ba, rma, rva, nbta, moma = _bn_args(bn)
     stats_a = ws.get("bn_a", 2 * C, dev)
-    if training and not h_stats_ready:
+    if tr_a and not h_stats_ready:
         ops.channel_stats(h, stats_a, n * T * V, C)
-    mean_a, invstd_a, scale_a, shift_a = ops.bn_fwd_finalize(stats_a if training else None, ga, ba, rma, rva, nbta, C,
-                                                              n * T * V, moma, bn.eps, training)
+    mean_a, invstd_a, scale_a, shift_a = ops.bn_fwd_finalize(stats_a if tr_a else None, ga, ba, rma, rva, nbta, C,
+                                                              n * T * V, moma, bn.eps, tr_a)
     wimg = ops.weight_image(Wt, C, 1, C, C)                        # B[n=co][k=ci] = Wt[co][ci]
     ypos_in_eff = ypos_in.detach().contiguous()
     q = torch.empty((n, T, V, C), device=dev, dtype=torch.float32)
@@ -283,15 +317,15 @@ def temporal_forward(h, res, relu, bn, ypos_in, Wt, bt, ypos_out, bn2, stride, t
     ypos_out_eff = (ypos_out.detach() + 0.5) if stride != 1 else ypos_out.detach().contiguous()   # cuda/shift.py:14-19
     gb, bb, rmb, rvb, nbtb, momb = _bn_args(bn2)
     stats_b = ws.get("bn_b", 2 * C, dev)
-    if training:
+    if tr_b:
         ops.tshift_fwd(0, q=q, ypos_eff=ypos_out_eff, n_samples=n, T_in=T, T_out=To, V=V, C=C, stride=stride,
                        stats=stats_b)
-    mean_b, invstd_b, scale_b, shift_b = ops.bn_fwd_finalize(stats_b if training else None, gb, bb, rmb, rvb, nbtb, C,
-                                                              n * To * V, momb, bn2.eps, training)
+    mean_b, invstd_b, scale_b, shift_b = ops.bn_fwd_finalize(stats_b if tr_b else None, gb, bb, rmb, rvb, nbtb, C,
+                                                              n * To * V, momb, bn2.eps, tr_b)
     y = torch.empty((n, To, V, C), device=dev, dtype=torch.float32)
     ops.tshift_fwd(1, q=q, ypos_eff=ypos_out_eff, n_samples=n, T_in=T, T_out=To, V=V, C=C, stride=stride, res=res,
                    out=y, scale=scale_b, shift=shift_b, relu=relu)
-    saved = dict(h=h, q=q, y=y, relu=relu, stride=stride, training=training, ypos_in_eff=ypos_in_eff,
+    saved = dict(h=h, q=q, y=y, relu=relu, stride=stride, training_a=tr_a, training_b=tr_b, ypos_in_eff=ypos_in_eff,
                  ypos_out_eff=ypos_out_eff, mean_a=mean_a, invstd_a=invstd_a, scale_a=scale_a, shift_a=shift_a,
                  mean_b=mean_b, invstd_b=invstd_b)
     return y, saved
@@ -309,13 +343,12 @@ def temporal_backward(saved, gy, gamma_a, Wt, gamma_b, ws, spatial_saved=None, s
     stride = saved["stride"]
     To = T // stride
     dev = h.device
-    training = saved["training"]
     relu = 1 if (saved["relu"] and not gy_masked) else 0   # a pre-masked g_y needs no look at y (1a less per pass)
     sums5 = ws.get("tshift_bwd", 5 * C, dev)
     common = dict(q=q, gy=gy, y=y if relu else None, relu=relu, ypos_eff=saved["ypos_out_eff"], mean=saved["mean_b"],
                   invstd=saved["invstd_b"], n_samples=n, T_in=T, T_out=To, V=V, C=C, stride=stride)
     ops.tshift_bwd(0, sums=sums5, **common)
-    fb = ops.tshift_bwd_finalize(sums5, gamma_b, saved["invstd_b"], C, n * To * V, n, training, input_shift=False,
+    fb = ops.tshift_bwd_finalize(sums5, gamma_b, saved["invstd_b"], C, n * To * V, n, saved["training_b"], input_shift=False,
                                  want_raw=want_raw)
     dpre = torch.empty((n, T, V, C), device=dev, dtype=torch.float32)
     dbias_acc = ws.get("dbt", C, dev)
@@ -337,7 +370,7 @@ def temporal_backward(saved, gy, gamma_a, Wt, gamma_b, ws, spatial_saved=None, s
                            mean=saved["mean_a"], invstd=saved["invstd_a"], scale=saved["scale_a"], shift=saved["shift_a"],
                            sums=sums3, gate=gate, n_samples=n, T=T, V=V, C=C)
     ops.tshift_in_bwd(0, sums=sums3, gate=gate, **common_in)
-    fa = ops.tshift_bwd_finalize(sums3, gamma_a, saved["invstd_a"], C, n * T * V, n, training, input_shift=True)
+    fa = ops.tshift_bwd_finalize(sums3, gamma_a, saved["invstd_a"], C, n * T * V, n, saved["training_a"], input_shift=True)
     gh = torch.empty((n, T, V, C), device=dev, dtype=torch.float32)
     pos = ws.get("tshift_in_pos", C, dev)
     if spatial_saved is not None:
@@ -416,10 +449,9 @@ class SpatialFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, res, W, bias, mask, gamma, beta, module):
-        training = module.training
-        need_grad = GRAD_MODE and any(ctx.needs_input_grad)
-        h, saved = spatial_forward(x, res, W, bias, mask, module.bn, training, module._ws,
-                                   fuse_eval=(not training and not need_grad))
+        need_grad = grad_mode() and any(ctx.needs_input_grad)
+        h, saved = spatial_forward(x, res, W, bias, mask, module.bn, module._ws,
+                                   fuse_eval=(not bn_training(module.bn) and not need_grad))
         ctx.module = module
         if saved is not None:
             saved["identity_res"] = res is None
@@ -442,7 +474,7 @@ class StemSpatialFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, bias, mask, g1, b1, Wd, bd, g2, b2, module):
-        h, saved = stem_forward(x, W, bias, mask, module.bn, Wd, bd, module.down[1], module.training, module._ws)
+        h, saved = stem_forward(x, W, bias, mask, module.bn, Wd, bd, module.down[1], module._ws)
         ctx.module = module
         _stash(ctx, s=saved, p=dict(W=W, bias=bias, mask=mask, g1=g1, Wd=Wd, bd=bd, g2=g2))
         return h
@@ -463,7 +495,7 @@ class SideBranchFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, Wd, bd, gamma, beta, bn, owner, hint_attr):
-        out, saved = side_forward(x, Wd, bd, bn, bn.training, owner._ws)
+        out, saved = side_forward(x, Wd, bd, bn, owner._ws)
         ctx.owner, ctx.hint_attr = owner, hint_attr
         _stash(ctx, s=saved, p=dict(Wd=Wd, bd=bd, gamma=gamma))
         return out
@@ -491,7 +523,7 @@ class TemporalFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, res, ga, ba, xpos_in, ypos_in, Wt, bt, xpos_out, ypos_out, gb, bb, module, relu):
         y, saved = temporal_forward(h, res, relu, module.bn, ypos_in, Wt.reshape(Wt.shape[0], Wt.shape[1]), bt,
-                                    ypos_out, module.bn2, module.shift_out.stride, module.training, module._ws, False)
+                                    ypos_out, module.bn2, module.shift_out.stride, module._ws, False)
         ctx.module = module
         ctx.has_res = res is not None
         _links(ctx, module, produces_gx=False)
@@ -525,14 +557,14 @@ class UnitFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W, bias, mask, g1, b1, ga, ba, xpos_in, ypos_in, Wt, bt, xpos_out, ypos_out, gb, bb, unit):
         gcn, tcn = unit.gcn1, unit.tcn1
-        training = unit.training
         n, T, V, C = x.shape
-        need_grad = GRAD_MODE and any(ctx.needs_input_grad)
-        h_stats = tcn._ws.get("bn_a", 2 * C, x.device) if training else None
-        h, s_saved = spatial_forward(x, None, W, bias, mask, gcn.bn, training, gcn._ws,
-                                     fuse_eval=(not training and not need_grad), h_stats=h_stats)
-        y, t_saved = temporal_forward(h, x, 1, tcn.bn, ypos_in, Wt.reshape(C, C), bt, ypos_out, tcn.bn2, 1, training,
-                                      tcn._ws, h_stats_ready=training)
+        need_grad = grad_mode() and any(ctx.needs_input_grad)
+        fuse_eval = not bn_training(gcn.bn) and not need_grad
+        # the BatchNorm2d statistics of h come out of the kernel that writes h (not in the fully fused eval kernel)
+        h_stats = tcn._ws.get("bn_a", 2 * C, x.device) if (bn_training(tcn.bn) and not fuse_eval) else None
+        h, s_saved = spatial_forward(x, None, W, bias, mask, gcn.bn, gcn._ws, fuse_eval=fuse_eval, h_stats=h_stats)
+        y, t_saved = temporal_forward(h, x, 1, tcn.bn, ypos_in, Wt.reshape(C, C), bt, ypos_out, tcn.bn2, 1,
+                                      tcn._ws, h_stats_ready=h_stats is not None)
         ctx.unit = unit
         _links(ctx, unit)
         if s_saved is not None:
@@ -568,17 +600,16 @@ class ConvUnitFn(torch.autograd.Function):
     def forward(ctx, x, W, bias, mask, g1, b1, Wd, bd, gd, bdn, ga, ba, xpos_in, ypos_in, Wt, bt, xpos_out, ypos_out, gb,
                 bb, Wr, br, gr, brn, unit):
         gcn, tcn = unit.gcn1, unit.tcn1
-        training = unit.training
         stride = tcn.shift_out.stride
         D = W.shape[1]
-        need_grad = GRAD_MODE and any(ctx.needs_input_grad)
-        res_d, sd_saved = side_forward(x, Wd, bd, gcn.down[1], training, gcn._ws)
-        h_stats = tcn._ws.get("bn_a", 2 * D, x.device) if training else None
-        h, s_saved = spatial_forward(x, res_d, W, bias, mask, gcn.bn, training, gcn._ws,
-                                     fuse_eval=(not training and not need_grad), h_stats=h_stats)
-        res_r, sr_saved = side_forward(x, Wr, br, unit.residual.bn, training, tcn._ws, gs=stride)   # strided in place
+        need_grad = grad_mode() and any(ctx.needs_input_grad)
+        fuse_eval = not bn_training(gcn.bn) and not need_grad
+        res_d, sd_saved = side_forward(x, Wd, bd, gcn.down[1], gcn._ws)
+        h_stats = tcn._ws.get("bn_a", 2 * D, x.device) if (bn_training(tcn.bn) and not fuse_eval) else None
+        h, s_saved = spatial_forward(x, res_d, W, bias, mask, gcn.bn, gcn._ws, fuse_eval=fuse_eval, h_stats=h_stats)
+        res_r, sr_saved = side_forward(x, Wr, br, unit.residual.bn, tcn._ws, gs=stride)   # strided in place
         y, t_saved = temporal_forward(h, res_r, 1, tcn.bn, ypos_in, Wt.reshape(D, D), bt, ypos_out, tcn.bn2, stride,
-                                      training, tcn._ws, h_stats_ready=training)
+                                      tcn._ws, h_stats_ready=h_stats is not None)
         ctx.unit = unit
         _links(ctx, unit)
         if s_saved is not None:

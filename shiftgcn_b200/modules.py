@@ -112,6 +112,7 @@ class Shift_tcn(nn.Module):
         nn.init.kaiming_normal_(self.temporal_linear.weight, mode='fan_out')
         self._ws = FN.Workspace()
         self._xpos_ok = None
+        self._xpos_gen = None
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._xpos_ok = None
@@ -123,11 +124,19 @@ class Shift_tcn(nn.Module):
             return False
         if x.shape[2] // self.shift_out.stride < 1:
             return False
-        if self._xpos_ok is None:      # one host sync, repeated only after load_state_dict
+        # one host sync, repeated only after a load_state_dict into this module, an ancestor or the Shift modules
+        # themselves.  Editing xpos in place to a non-negligible value is not noticed (call reset_xpos_check()): the
+        # reference initialises it to U(-1e-8, 1e-8) and gives it a zero gradient (shift_cuda_kernel.cu:371-395).
+        gen = (self.shift_in._load_generation, self.shift_out._load_generation)
+        if self._xpos_ok is None or self._xpos_gen != gen:
             with torch.no_grad():
                 m = torch.maximum(self.shift_in.xpos.abs().max(), self.shift_out.xpos.abs().max())
                 self._xpos_ok = bool(m.item() <= XPOS_LIMIT)
+            self._xpos_gen = gen
         return self._xpos_ok
+
+    def reset_xpos_check(self):
+        self._xpos_ok = None
 
     def _args(self):
         return (self.bn.weight, self.bn.bias, self.shift_in.xpos, self.shift_in.ypos, self.temporal_linear.weight,
@@ -204,28 +213,19 @@ class Shift_gcn(nn.Module):
             res = FN.SideBranchFn.apply(x_rows, conv.weight, conv.bias, bn.weight, bn.bias, bn, self, "_down_sg")
         else:
             res = to_rows(self.down(x0))
-        FN.GRAD_MODE = torch.is_grad_enabled()
+        FN.set_grad_mode(torch.is_grad_enabled())
         return FN.SpatialFn.apply(x_rows, res, *self._args(), self)
-
-    def _forward_general(self, x0):
-        """Unfused path for shapes neither the tensor-core kernels (64 / 128 / 256 channels) nor the stem kernels
-        (3 -> 64, the model's first layer) cover: the same arithmetic with library ops on CUDA tensors."""
-        n, c, t, v = x0.shape
-        rows = x0.permute(0, 2, 3, 1).reshape(n * t, v * c)
-        xs = torch.index_select(rows, 1, self.shift_in).view(n * t, v, c)     # backward = index_add_ (atomics), not the
-        xm = xs * (torch.tanh(self.Feature_Mask) + 1)                         # sort-based index_put of `rows[:, idx]`
-        y = torch.matmul(xm, self.Linear_weight) + self.Linear_bias
-        z = torch.index_select(y.reshape(n * t, -1), 1, self.shift_out)
-        z = self.bn(z).view(n, t, v, self.out_channels)
-        res = self.down(x0).permute(0, 2, 3, 1)
-        return from_rows(F.relu(z + res).contiguous())
 
     def forward(self, x0):
         _require_cuda(x0, "Shift_gcn")
         if self.stem_supported(x0):
             return from_rows(self.forward_stem_rows(to_rows(x0)))
         if not self.fused_supported(x0):
-            return self._forward_general(x0)
+            # no second (library-op) implementation: the sm_100a kernels are the only path of this package
+            raise RuntimeError(
+                f"Shift_gcn({self.in_channels}, {self.out_channels}, num_point={self.num_point}) on input "
+                f"{tuple(x0.shape)}: shiftgcn_b200 has kernels for 64 / 128 / 256 channels (and the 3 -> 64 first layer) "
+                "on the 25-joint (NTU) and 33-landmark (MediaPipe) skeletons only")
         return from_rows(self.forward_rows(to_rows(x0), x0))
 
 
@@ -256,14 +256,14 @@ class TCN_GCN_unit(nn.Module):
         _require_cuda(x, "TCN_GCN_unit")
         gcn, tcn1 = self.gcn1, self.tcn1
         if self._res_mode == "identity" and gcn.fused_supported(x) and tcn1.fused_supported(x):
-            FN.GRAD_MODE = torch.is_grad_enabled()
+            FN.set_grad_mode(torch.is_grad_enabled())
             y = FN.UnitFn.apply(to_rows(x), *gcn._args(), *tcn1._args(), self)
             return from_rows(y)
         if (self._res_mode == "conv" and isinstance(gcn.down, nn.Sequential) and gcn.fused_supported(x)
                 and side_supported(gcn.down[0], x.shape[3]) and side_supported(self.residual.conv, x.shape[3])
                 and x.shape[2] % self.residual.conv.stride[0] == 0 and self._tcn_fused_for(x)):
             d, r = gcn.down, self.residual
-            FN.GRAD_MODE = torch.is_grad_enabled()
+            FN.set_grad_mode(torch.is_grad_enabled())
             y = FN.ConvUnitFn.apply(to_rows(x), *gcn._args(), d[0].weight, d[0].bias, d[1].weight, d[1].bias,
                                     *tcn1._args(), r.conv.weight, r.conv.bias, r.bn.weight, r.bn.bias, self)
             return from_rows(y)
@@ -315,10 +315,15 @@ class Model(nn.Module):
         # the result is already channels-last, i.e. the logical (N*M, C, T, V) tensor the units consume without a copy.
         x = x.permute(0, 2, 4, 3, 1).reshape(N * T, M * V * C)
         bn = self.data_bn
-        x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, self.training or not bn.track_running_stats,
-                         0.1 if bn.momentum is None else bn.momentum, bn.eps)
-        if self.training and bn.track_running_stats:
+        track = bn.track_running_stats and bn.running_mean is not None
+        if bn.training and track:
             bn.num_batches_tracked += 1
+        if bn.momentum is not None:
+            factor = bn.momentum
+        else:                        # cumulative moving average (nn.BatchNorm semantics for momentum=None)
+            factor = 1.0 / float(bn.num_batches_tracked) if (bn.training and track) else 0.0
+        x = F.batch_norm(x, bn.running_mean if track else None, bn.running_var if track else None, bn.weight, bn.bias,
+                         FN.bn_training(bn), factor, bn.eps)
         x = x.view(N, T, M, V, C).permute(0, 2, 1, 3, 4).reshape(N * M, T, V, C).permute(0, 3, 1, 2)
         return self._trunk(x, N, M)
 

@@ -2,9 +2,11 @@
 
 PyTorch is plumbing only: it owns device memory and the current stream.  Every function validates device /
 dtype / contiguity (the checks the reference does with AT_ASSERTM, shift_cuda.cpp:15-17, plus the ones it
-omits), launches on ``torch.cuda.current_stream()`` and never synchronises.
+omits), launches on the current stream of the tensors' device and never synchronises.
 """
+import contextlib
 import ctypes
+import threading
 
 import torch
 
@@ -20,8 +22,28 @@ LAUNCHES = 0          # kernels of this library enqueued so far (bench.py report
 PROFILE = None        # when a list: (name, start_event, end_event, algorithmic_bytes) per C-ABI call
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+class _StreamArg:
+    """placeholder in an argument list: replaced by the current stream of the device the op's tensors live on"""
+
+
+_STREAM = _StreamArg()
+_tls = threading.local()          # device of the tensors seen by _p() since the last C-ABI call of this thread
+_NULL_CTX = contextlib.nullcontext()
+
+
+def _call(name, fn, *args):
+    """One C-ABI call on the device of its tensors: every pointer handed out by _p()/_d() since the previous call must
+    live on ONE device (checked there); the call runs with that device current and on ITS current stream, whatever the
+    caller's current device is (the reference extension launches on the legacy default stream of the current device and
+    is only correct when that happens to be the tensors' device, shift_cuda_kernel.cu:414)."""
+    dev = getattr(_tls, "dev", None)
+    _tls.dev = None
+    if dev is None:
+        dev = torch.cuda.current_device()
+    ctx = _NULL_CTX if dev == torch.cuda.current_device() else torch.cuda.device(dev)
+    with ctx:
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(fn(*[stream if a is _STREAM else a for a in args]), name)
 
 
 def _launch(name, nkernels, algo_bytes, fn, *args):
@@ -29,17 +51,26 @@ def _launch(name, nkernels, algo_bytes, fn, *args):
     global LAUNCHES
     LAUNCHES += nkernels
     if PROFILE is None:
-        _lib.check(fn(*args), name)
+        _call(name, fn, *args)
         return
+    dev = getattr(_tls, "dev", None)
+    stream = torch.cuda.current_stream(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    _lib.check(fn(*args), name)
-    e1.record()
+    e0.record(stream)
+    _call(name, fn, *args)
+    e1.record(stream)
     PROFILE.append((name, e0, e1, algo_bytes))
 
 
 def _nbytes(*tensors):
-    return sum(t.numel() * t.element_size() for t in tensors if t is not None)
+    """bytes of the distinct tensors (an identity unit passes the same tensor as input and residual: count it once)"""
+    seen, total = set(), 0
+    for t in tensors:
+        if t is None or t.data_ptr() in seen:
+            continue
+        seen.add(t.data_ptr())
+        total += t.numel() * t.element_size()
+    return total
 
 
 def _count(n=1):
@@ -48,15 +79,23 @@ def _count(n=1):
 
 
 def _p(t, dtype=torch.float32, name="tensor"):
-    """device pointer of a contiguous CUDA tensor (None -> NULL)"""
+    """device pointer of a contiguous CUDA tensor (None -> NULL); all pointers of one call must share a device"""
     if t is None:
         return None
+    cur = getattr(_tls, "dev", None)
+    bad = None
     if not t.is_cuda:
-        raise RuntimeError(f"{name} must be a CUDA tensor")
-    if t.dtype != dtype:
-        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
-    if not t.is_contiguous():
-        raise RuntimeError(f"{name} must be contiguous")
+        bad = f"{name} must be a CUDA tensor"
+    elif t.dtype != dtype:
+        bad = f"{name} must be {dtype}, got {t.dtype}"
+    elif not t.is_contiguous():
+        bad = f"{name} must be contiguous"
+    elif cur is not None and cur != t.device.index:
+        bad = f"{name} is on cuda:{t.device.index} but the other tensors of this call are on cuda:{cur}"
+    if bad is not None:
+        _tls.dev = None                       # the call is abandoned: do not leak its device into the next one
+        raise RuntimeError(bad)
+    _tls.dev = t.device.index
     return ctypes.c_void_p(t.data_ptr())
 
 
@@ -74,14 +113,20 @@ def set_traversal(snake):
     return bool(_lib.load().sgcn_set_traversal(1 if snake else 0))
 
 
+def set_max_ctas(n):
+    """Cap the grid of the persistent tile kernels (include/shiftgcn_b200.h:sgcn_set_max_ctas; 0 = one CTA per SM).
+    Parity tests use it to put many tiles on every CTA at small sizes.  Returns the previous cap."""
+    return int(_lib.load().sgcn_set_max_ctas(int(n)))
+
+
 def restart_traversal():
     """restart the snake alternation (top of every step: all steps and a captured graph see the same tile orders)"""
     _lib.load().sgcn_set_traversal(_lib.traversal_mode())
 
 
 def groups_per_tile(V):
-    if V < 25 or V > 40:
-        raise RuntimeError(f"shiftgcn_b200 fused kernels support 25 <= num_point <= 40, got {V}")
+    if V not in (25, 33):
+        raise RuntimeError(f"shiftgcn_b200 fused kernels exist for num_point 25 (NTU) and 33 (MediaPipe), got {V}")
     return 128 // V
 
 
@@ -90,8 +135,7 @@ def selftest_umma(a, b, mode, K, N, M2=128):
     lib = _lib.load()
     rows = 128
     d = torch.empty(rows, N, device=a.device, dtype=torch.float32)
-    with torch.cuda.device(a.device):
-        _lib.check(lib.sgcn_selftest_umma(_p(a), _p(b), _p(d), mode, K, N, M2, _stream()), "selftest_umma")
+    _call("selftest_umma", lib.sgcn_selftest_umma, _p(a), _p(b), _p(d), mode, K, N, M2, _STREAM)
     return d
 
 
@@ -115,9 +159,8 @@ def shift_forward(inp, xpos, ypos, stride):
         raise RuntimeError("xpos / ypos must have one entry per channel")
     out = torch.empty((n, c, h // stride, w), device=inp.device, dtype=dt)
     _count(1)
-    with torch.cuda.device(inp.device):
-        _lib.check(fn(_p(inp, dt, "input"), _p(out, dt), _p(xpos, dt, "xpos"), _p(ypos, dt, "ypos"), n, c, h, w, stride,
-                      _stream()), "shift forward")
+    _call("shift forward", fn, _p(inp, dt, "input"), _p(out, dt), _p(xpos, dt, "xpos"), _p(ypos, dt, "ypos"), n, c, h, w,
+          stride, _STREAM)
     return out
 
 
@@ -142,10 +185,8 @@ def shift_backward(grad_output, inp, output, xpos, ypos, stride, return_raw=Fals
     raw = torch.empty(2, c, device=inp.device, dtype=dt) if return_raw else None
     scratch = torch.zeros(2, c, device=inp.device, dtype=torch.float64)
     _count(3)
-    with torch.cuda.device(inp.device):
-        _lib.check(fn(_p(grad_output, dt, "grad_output"), _p(inp, dt, "input"), _p(xpos, dt), _p(ypos, dt),
-                      _p(grad_input, dt), _p(gx, dt), _p(gy, dt), _p(raw, dt), _d(scratch), n, c, h, w, stride,
-                      _stream()), "shift backward")
+    _call("shift backward", fn, _p(grad_output, dt, "grad_output"), _p(inp, dt, "input"), _p(xpos, dt), _p(ypos, dt),
+          _p(grad_input, dt), _p(gx, dt), _p(gy, dt), _p(raw, dt), _d(scratch), n, c, h, w, stride, _STREAM)
     if return_raw:
         return [grad_input, gx, gy], raw
     return [grad_input, gx, gy]
@@ -157,7 +198,7 @@ def weight_image(src, ld_n, ld_k, N, K):
     _count()
     lib = _lib.load()
     img = torch.empty(N * K, device=src.device, dtype=torch.float32)
-    _lib.check(lib.sgcn_prep_weight_image(_p(src, name="weight"), ld_n, ld_k, N, K, _p(img), _stream()), "weight image")
+    _call("weight image", lib.sgcn_prep_weight_image, _p(src, name="weight"), ld_n, ld_k, N, K, _p(img), _STREAM)
     return img
 
 
@@ -167,8 +208,7 @@ def mask_prepare(mask):
     lib = _lib.load()
     V, C = mask.shape
     out = torch.empty(2, V, C, device=mask.device, dtype=torch.float32)
-    _lib.check(lib.sgcn_mask_prepare_rot(_p(mask, name="Feature_Mask"), _p(out[0]), _p(out[1]), V, C, _stream()),
-               "mask prepare")
+    _call("mask prepare", lib.sgcn_mask_prepare_rot, _p(mask, name="Feature_Mask"), _p(out[0]), _p(out[1]), V, C, _STREAM)
     return out[0], out[1]
 
 
@@ -176,7 +216,7 @@ def mask_grad_finalize(raw, mask):
     _count()
     lib = _lib.load()
     dm = torch.empty_like(mask)
-    _lib.check(lib.sgcn_mask_grad_finalize(_d(raw), _p(mask), _p(dm), mask.numel(), _stream()), "mask grad")
+    _call("mask grad", lib.sgcn_mask_grad_finalize, _d(raw), _p(mask), _p(dm), mask.numel(), _STREAM)
     return dm
 
 
@@ -184,7 +224,7 @@ def reduce_export(src, scale=1.0):
     _count()
     lib = _lib.load()
     dst = torch.empty(src.shape, device=src.device, dtype=torch.float32)
-    _lib.check(lib.sgcn_reduce_export(_d(src), _p(dst), src.numel(), float(scale), _stream()), "reduce export")
+    _call("reduce export", lib.sgcn_reduce_export, _d(src), _p(dst), src.numel(), float(scale), _STREAM)
     return dst
 
 
@@ -194,10 +234,9 @@ def bn_fwd_finalize(stats, gamma, beta, running_mean, running_var, nbt, features
     lib = _lib.load()
     dev = gamma.device if gamma is not None else running_mean.device
     out = torch.empty(4, features, device=dev, dtype=torch.float32)
-    _lib.check(lib.sgcn_bn_fwd_finalize(
-        _d(stats), _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(nbt, torch.int64),
+    _call("bn forward finalize", lib.sgcn_bn_fwd_finalize, _d(stats), _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(nbt, torch.int64),
         _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), features, float(count), float(momentum), float(eps),
-        1 if training else 0, _stream()), "bn forward finalize")
+        1 if training else 0, _STREAM)
     return out[0], out[1], out[2], out[3]
 
 
@@ -207,9 +246,9 @@ def tshift_bwd_finalize(sums, gamma, invstd, C, count, n_batch, training, input_
     lib = _lib.load()
     out = torch.empty(8, C, device=gamma.device, dtype=torch.float32)
     fn = lib.sgcn_tshift_in_bwd_finalize if input_shift else lib.sgcn_tshift_bwd_finalize
-    _lib.check(fn(_d(sums), _p(gamma), _p(invstd), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), _p(out[4]),
+    _call("tshift backward finalize", fn, _d(sums), _p(gamma), _p(invstd), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), _p(out[4]),
                   _p(out[5]), _p(out[6]), _p(out[7]) if want_raw else None, C, float(count), float(n_batch),
-                  1 if training else 0, _stream()), "tshift backward finalize")
+                  1 if training else 0, _STREAM)
     return dict(dgamma=out[0], dbeta=out[1], k1=out[2], m1=out[3], m2=out[4], gx=out[5], gy=out[6], raw=out[7])
 
 
@@ -219,9 +258,9 @@ def bn1d_bwd_finalize(vd_sums, gamma, mean, invstd, V, D, count, training):
     lib = _lib.load()
     out = torch.empty(5, V * D, device=gamma.device, dtype=torch.float32)
     dbias = torch.empty(D, device=gamma.device, dtype=torch.float32)
-    _lib.check(lib.sgcn_bn1d_bwd_finalize(_d(vd_sums), _p(gamma), _p(mean), _p(invstd), _p(out[0]), _p(out[1]),
+    _call("bn1d backward finalize", lib.sgcn_bn1d_bwd_finalize, _d(vd_sums), _p(gamma), _p(mean), _p(invstd), _p(out[0]), _p(out[1]),
                                           _p(out[2]), _p(out[3]), _p(out[4]), _p(dbias), V, D, float(count),
-                                          1 if training else 0, _stream()), "bn1d backward finalize")
+                                          1 if training else 0, _STREAM)
     return dict(dgamma=out[0], dbeta=out[1], alpha=out[2], beta=out[3], gamma=out[4], dbias=dbias)
 
 
@@ -237,7 +276,7 @@ def rowgemm(pro, epi, *, in0, out, wimg, groups, V, K, N, T=1, in1=None, pro_a=N
                     in1_gs=int(in1_gs), out_gs=int(out_gs), accum=int(accum))
     name = "rowgemm[%s/%s]" % (("spatial", "lerp", "plain", "dy")[pro], ("rot_raw", "rot_fused", "linear", "spatial_bwd")[epi])
     nbytes = int(groups) * V * 4 * (K + N * (2 if accum else 1)) if pro == PRO_PLAIN else _nbytes(in0, in1, out, res, res2, res2m, xin)
-    _launch(name, 1, nbytes, lib.sgcn_rowgemm, ctypes.byref(p), pro, epi, _stream())
+    _launch(name, 1, nbytes, lib.sgcn_rowgemm, ctypes.byref(p), pro, epi, _STREAM)
 
 
 def wgrad(mode, *, a_src, b_src, dw, groups, V, CA, CB, T=1, a_tab0=None, b_src2=None, b_tab0=None, b_tab1=None,
@@ -248,7 +287,7 @@ def wgrad(mode, *, a_src, b_src, dw, groups, V, CA, CB, T=1, a_tab0=None, b_src2
                   T=int(T), CA=CA, CB=CB, a_gs=int(a_gs), b_gs=int(b_gs))
     nbytes = int(groups) * V * 4 * (CA + CB) if mode == WG_PLAIN else _nbytes(a_src, b_src, b_src2)
     _launch("wgrad[%s]" % ("spatial", "temporal", "plain")[mode], 1, nbytes, lib.sgcn_wgrad,
-            ctypes.byref(p), mode, _stream())
+            ctypes.byref(p), mode, _STREAM)
 
 
 # ------------------------------------------------------------------------------------------------ first spatial unit
@@ -268,7 +307,7 @@ def stem_fwd(mode, *, groups, V, D, **t):
     lib = _lib.load()
     p = _stem_params(groups, V, D, **t)
     _launch("stem_fwd[%s]" % ("stats", "apply")[mode], 1, _nbytes(t.get("x"), t.get("h") if mode == 1 else None),
-            lib.sgcn_stem_fwd, ctypes.byref(p), mode, _stream())
+            lib.sgcn_stem_fwd, ctypes.byref(p), mode, _STREAM)
 
 
 def stem_bwd(mode, *, groups, V, D, **t):
@@ -276,14 +315,14 @@ def stem_bwd(mode, *, groups, V, D, **t):
     lib = _lib.load()
     p = _stem_params(groups, V, D, **t)
     _launch("stem_bwd[%s]" % ("stats", "apply")[mode], 1, _nbytes(t.get("x"), t.get("g"), t.get("h"), t.get("dx")),
-            lib.sgcn_stem_bwd, ctypes.byref(p), mode, _stream())
+            lib.sgcn_stem_bwd, ctypes.byref(p), mode, _STREAM)
 
 
 # ------------------------------------------------------------------------------------------------ SIMT kernels
 def bn_res_relu_fwd(z, res, h, scale, shift, stats_out, rows, V, D, relu=1):
     lib = _lib.load()
     _launch("bn_res_relu_fwd", 1, _nbytes(z, res, h), lib.sgcn_bn_res_relu_fwd, _p(z), _p(res), _p(h), _p(scale),
-            _p(shift), _d(stats_out), int(rows), V, D, int(relu), _stream())
+            _p(shift), _d(stats_out), int(rows), V, D, int(relu), _STREAM)
 
 
 def tshift_fwd(mode, *, q, ypos_eff, n_samples, T_in, T_out, V, C, stride, res=None, out=None, scale=None, shift=None,
@@ -293,7 +332,7 @@ def tshift_fwd(mode, *, q, ypos_eff, n_samples, T_in, T_out, V, C, stride, res=N
                    stats=_d(stats), n_samples=int(n_samples), T_in=T_in, T_out=T_out, V=V, C=C, stride=stride,
                    relu=int(relu))
     _launch("tshift_fwd[%s]" % ("stats", "apply")[mode], 1, _nbytes(q, res, out), lib.sgcn_tshift_fwd, ctypes.byref(p),
-            mode, _stream())
+            mode, _STREAM)
 
 
 def tshift_bwd(mode, *, q, gy, ypos_eff, mean, invstd, n_samples, T_in, T_out, V, C, stride, y=None, relu=0, k1=None,
@@ -303,7 +342,7 @@ def tshift_bwd(mode, *, q, gy, ypos_eff, mean, invstd, n_samples, T_in, T_out, V
                       m1=_p(m1), m2=_p(m2), sums=_d(sums), dpre=_p(dpre), dbias=_d(dbias), n_samples=int(n_samples),
                       T_in=T_in, T_out=T_out, V=V, C=C, stride=stride, relu=int(relu))
     _launch("tshift_bwd[%s]" % ("stats", "apply")[mode], 1, _nbytes(q, gy, y, dpre), lib.sgcn_tshift_bwd,
-            ctypes.byref(p), mode, _stream())
+            ctypes.byref(p), mode, _STREAM)
 
 
 def tshift_in_bwd(mode, *, dp, h, ypos_eff, mean, invstd, n_samples, T, V, C, scale=None, shift=None, k1=None, m1=None,
@@ -316,7 +355,7 @@ def tshift_in_bwd(mode, *, dp, h, ypos_eff, mean, invstd, n_samples, T, V, C, sc
                         gate=_p(gate, torch.int32, "gate"), n_samples=int(n_samples), T=T, V=V, C=C, relu_h=int(relu_h))
     # a gated statistics pass normally returns at once (its sums came from tshift_in_bwd_sums): no algorithmic bytes
     _launch("tshift_in_bwd[%s]" % ("stats", "apply")[mode] + ("(gated)" if gate is not None else ""), 1,
-            0 if gate is not None else _nbytes(dp, h, z, gh), lib.sgcn_tshift_in_bwd, ctypes.byref(p), mode, _stream())
+            0 if gate is not None else _nbytes(dp, h, z, gh), lib.sgcn_tshift_in_bwd, ctypes.byref(p), mode, _STREAM)
 
 
 def tshift_in_bwd_sums(*, dp, ypos_eff, Wt, dWt, dbt, mean, invstd, scale, shift, sums, gate, n_samples, T, V, C):
@@ -325,7 +364,7 @@ def tshift_in_bwd_sums(*, dp, ypos_eff, Wt, dWt, dbt, mean, invstd, scale, shift
     p = SgcnTShiftInSums(dp=_p(dp), ypos_eff=_p(ypos_eff), Wt=_p(Wt, name="Wt"), dWt=_p(dWt, name="dWt"), dbt=_p(dbt),
                          mean=_p(mean), invstd=_p(invstd), scale=_p(scale), shift=_p(shift), sums=_d(sums),
                          gate=_p(gate, torch.int32, "gate"), n_samples=int(n_samples), T=T, V=V, C=C)
-    _launch("tshift_in_bwd[sums]", 3, 0, lib.sgcn_tshift_in_bwd_sums, ctypes.byref(p), _stream())
+    _launch("tshift_in_bwd[sums]", 3, 0, lib.sgcn_tshift_in_bwd_sums, ctypes.byref(p), _STREAM)
 
 
 def shift_pos_finalize(pos_sums, C, n_batch, want_raw=False):
@@ -333,33 +372,33 @@ def shift_pos_finalize(pos_sums, C, n_batch, want_raw=False):
     _count()
     lib = _lib.load()
     out = torch.empty(3, C, device=pos_sums.device, dtype=torch.float32)
-    _lib.check(lib.sgcn_shift_pos_finalize(_d(pos_sums), _p(out[0]), _p(out[1]), _p(out[2]) if want_raw else None, C,
-                                           float(n_batch), _stream()), "shift position finalize")
+    _call("shift position finalize", lib.sgcn_shift_pos_finalize, _d(pos_sums), _p(out[0]), _p(out[1]), _p(out[2]) if want_raw else None, C,
+                                           float(n_batch), _STREAM)
     return out[0], out[1], (out[2] if want_raw else None)
 
 
 def channel_stats(x, stats, rows, C):
     lib = _lib.load()
-    _launch("channel_stats", 1, _nbytes(x), lib.sgcn_channel_stats, _p(x), _d(stats), int(rows), C, _stream())
+    _launch("channel_stats", 1, _nbytes(x), lib.sgcn_channel_stats, _p(x), _d(stats), int(rows), C, _STREAM)
 
 
 def channel_stats_groups(x, stats, groups, V, C, gs):
     """channel sums over `groups` frames of V rows, frame g being frame g*gs of x"""
     lib = _lib.load()
     _launch("channel_stats", 1, int(groups) * V * C * 4, lib.sgcn_channel_stats_groups, _p(x), _d(stats), int(groups), V, C,
-            int(gs), _stream())
+            int(gs), _STREAM)
 
 
 def relu_bn1d_bwd_stats(g, h, z, zmean, zinvstd, gh, vd_sums, groups, V, C):
     lib = _lib.load()
     _launch("relu_bn1d_bwd_stats", 1, _nbytes(g, h, z, gh), lib.sgcn_relu_bn1d_bwd_stats, _p(g), _p(h), _p(z), _p(zmean),
-            _p(zinvstd), _p(gh), _d(vd_sums), int(groups), V, C, _stream())
+            _p(zinvstd), _p(gh), _d(vd_sums), int(groups), V, C, _STREAM)
 
 
 def relu_mask_grad(g, y):
     lib = _lib.load()
     out = torch.empty_like(g)
-    _launch("relu_mask_grad", 1, _nbytes(g, y, out), lib.sgcn_relu_mask_grad, _p(g), _p(y), _p(out), g.numel(), _stream())
+    _launch("relu_mask_grad", 1, _nbytes(g, y, out), lib.sgcn_relu_mask_grad, _p(g), _p(y), _p(out), g.numel(), _STREAM)
     return out
 
 
@@ -382,7 +421,7 @@ def input_stream(joint, parent=None, motion=False, rows=False, scale=None, shift
         return out
     _launch("input_stream", 1, _nbytes(joint, out), lib.sgcn_input_stream, _p(joint, name="joint"), _p(out),
             _p(parent, torch.int32, "parent"), _p(scale), _p(shift), N, C, T, V, M, 1 if motion else 0, 1 if rows else 0,
-            _stream())
+            _STREAM)
     return out
 
 
@@ -403,7 +442,7 @@ def side_fold(Wd, bd, gamma, beta, running_mean, running_var, nbt, rows, eps, mo
                      num_batches_tracked=_p(nbt, torch.int64), Wf=_p(Wf), bf=_p(bf), mean_r=_d(stat[0]), invstd=_d(stat[1]),
                      sx=_d(sx), counter=_p(counter, torch.int32), rows=float(rows), eps=float(eps),
                      momentum=float(momentum), C=C, D=D, training=1 if training else 0)
-    _lib.check(lib.sgcn_side_fold(ctypes.byref(p), _stream()), "side fold")
+    _call("side fold", lib.sgcn_side_fold, ctypes.byref(p), _STREAM)
     return dict(Wf=Wf, bf=bf, mean_r=stat[0], invstd=stat[1], sx=sx)
 
 
@@ -422,7 +461,7 @@ def side_bwd(P, sg, Wd, bd, gamma, invstd, mean_r, rows, training, sx=None, XX=N
                     gamma=_p(gamma), invstd=_d(invstd), mean_r=_d(mean_r), dgamma=_p(vec[0]), dbeta=_p(vec[1]),
                     dWd=_p(dWd), dbd=_p(vec[2]), Wcat=_p(Wcat), kvec=_p(kvec), coef=_d(coef), rows=float(rows), C=C, D=D,
                     training=1 if training else 0)
-    _lib.check(lib.sgcn_side_bwd(ctypes.byref(p), _stream()), "side backward")
+    _call("side backward", lib.sgcn_side_bwd, ctypes.byref(p), _STREAM)
     return dict(dgamma=vec[0], dbeta=vec[1], dWd=dWd, dbd=vec[2], Wcat=Wcat, kvec=kvec)
 
 
@@ -433,5 +472,15 @@ def bcast_rows(g, rows_per_n, scale):
     out = torch.empty((n, rows_per_n, C), device=g.device, dtype=torch.float32)
     if out.numel():
         _launch("bcast_rows", 1, _nbytes(out), lib.sgcn_bcast_rows, _p(g, name="g"), _p(out), n, int(rows_per_n), C,
-                ctypes.c_float(scale), _stream())
+                ctypes.c_float(scale), _STREAM)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ optimizer step
+def sgd_epilogue(param, grad, momentum_buf, weight_decay, ypos_src, hyper, n_param, nesterov):
+    """scale -> K5 on the reduced raw position sums -> weight decay -> SGD momentum / Nesterov, one kernel over the flat
+    buffers (include/shiftgcn_b200.h:sgcn_sgd_epilogue); hyper = device tensor [lr, momentum, gradient scale]"""
+    lib = _lib.load()
+    _launch("sgd_epilogue", 1, 0, lib.sgcn_sgd_epilogue, _p(param, name="flat_param"), _p(grad, name="flat_grad"),
+            _p(momentum_buf, name="momentum_buf"), _p(weight_decay, name="weight_decay"),
+            _p(ypos_src, torch.int32, "ypos_src"), _p(hyper, name="hyper"), int(n_param), 1 if nesterov else 0, _STREAM)

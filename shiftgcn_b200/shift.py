@@ -71,5 +71,11 @@ class Shift(nn.Module):
         self.xpos = nn.Parameter(torch.empty(channel, device=device).uniform_(-1e-8, 1e-8))
         self.ypos = nn.Parameter(torch.empty(channel, device=device).uniform_(-init_scale, init_scale))
 
+        self._load_generation = 0
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._load_generation += 1          # Shift_tcn re-validates its cached "xpos is 0" decision (modules.py)
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def forward(self, input):
         return ShiftFunction.apply(input, self.xpos, self.ypos, self.stride)

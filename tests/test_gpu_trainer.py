@@ -1,0 +1,160 @@
+"""The step after backward on the GPU: the fused scale -> K5 -> weight decay -> SGD kernel against
+torch.optim.SGD with the reference's parameter groups (main.py:301-322), the device-resident learning rate, and the
+CUDA-graph capture of a whole training step against the same steps run eagerly -- the path bench.py times."""
+import copy
+
+import pytest
+import torch
+
+from util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(device, V=25, M=2, num_class=60, seed=1):
+    from oracle import model_ref
+    from shiftgcn_b200.modules import Model
+    torch.manual_seed(seed)
+    graph = "graph.ntu_rgb_d.Graph" if V == 25 else "graph.mediapipe_pose.Graph"
+    mod = Model(num_class=num_class, num_point=V, num_person=M, graph=graph, graph_args=dict(labeling_mode="spatial"))
+    model_ref.fill_module_(mod)
+    return mod.to(device).train()
+
+
+def test_sgd_epilogue_kernel_matches_torch_sgd(cuda_device):
+    """three steps of the one-kernel update == torch.optim.SGD(momentum 0.9, nesterov) with per-group weight decay,
+    and the K5 constraint is applied to the raw position sums behind the gradients"""
+    from shiftgcn_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    n, n_raw = 5000, 96
+    param = torch.randn(n, generator=g).to(cuda_device)
+    wd = torch.zeros(n, device=cuda_device)
+    wd[:2000], wd[2000:3500], wd[3500:] = 1e-4, 1e-3, 0.0
+    ysrc = torch.full((n,), -1, dtype=torch.int32, device=cuda_device)
+    ysrc[4000:4000 + n_raw] = torch.arange(n_raw, dtype=torch.int32, device=cuda_device)
+    hyper = torch.tensor([0.1, 0.9, 0.5], device=cuda_device)      # lr, momentum, gradient scale (world 2, summed)
+    mbuf = torch.zeros(n, device=cuda_device)
+    ref_p = [param[:2000].clone().requires_grad_(True), param[2000:3500].clone().requires_grad_(True),
+             param[3500:].clone().requires_grad_(True)]
+    opt = torch.optim.SGD([dict(params=[ref_p[0]], weight_decay=1e-4), dict(params=[ref_p[1]], weight_decay=1e-3),
+                           dict(params=[ref_p[2]], weight_decay=0.0)], lr=0.1, momentum=0.9, nesterov=True)
+    for step in range(3):
+        grad = torch.randn(n + n_raw, generator=g).to(cuda_device)
+        grad[n + 5] = 0.0                                            # exact zero -> 1e-4
+        want_g = grad[:n] * 0.5
+        raw = grad[n:]
+        want_g[4000:4000 + n_raw] = torch.where(raw != 0, torch.sign(raw) * 0.01, torch.full_like(raw, 1e-4))
+        for p, (a, b) in zip(ref_p, ((0, 2000), (2000, 3500), (3500, n))):
+            p.grad = want_g[a:b].clone()
+        if step == 2:
+            hyper[0:1].fill_(0.01)                                   # schedule change between steps: no re-capture needed
+            for grp in opt.param_groups:
+                grp["lr"] = 0.01
+        opt.step()
+        ops.sgd_epilogue(param, grad, mbuf, wd, ysrc, hyper, n, True)
+        assert torch.allclose(grad[:n], want_g, rtol=0, atol=0)
+        got = param
+        want = torch.cat([p.detach() for p in ref_p])
+        assert (got - want).abs().max().item() < 2e-6 * want.abs().max().item(), f"step {step}"
+
+
+def test_graph_replay_equals_eager_steps(cuda_device):
+    """FlatSGDTrainer.capture / replay (what bench.py times) follows the same trajectory as eager train_step calls"""
+    from shiftgcn_b200.dp import FlatSGDTrainer
+    base = _model(cuda_device)
+    g = torch.Generator().manual_seed(9)
+    xs = [torch.randn(4, 3, 32, 25, 2, generator=g).to(cuda_device) for _ in range(3)]
+    ys = [torch.randint(0, 60, (4,), generator=g).to(cuda_device) for _ in range(3)]
+    m_eager, m_graph = copy.deepcopy(base), copy.deepcopy(base)
+    t_eager = FlatSGDTrainer(m_eager, lr=0.05)
+    t_graph = FlatSGDTrainer(m_graph, lr=0.05)
+    init = t_eager.flat_param.clone()
+    # capture() runs `warmup` real steps on its example batch first: give the eager trainer the same ones
+    t_graph.capture(xs[0], ys[0], warmup=1)
+    t_eager.train_step(xs[0], ys[0])
+    losses = []
+    for x, y in zip(xs, ys):
+        le = t_eager.train_step(x, y)
+        lg = t_graph.replay(x, y)
+        losses.append((le.item(), lg.item()))
+    torch.cuda.synchronize()
+    for le, lg in losses:
+        assert abs(le - lg) < 5e-3 * max(1.0, abs(le)), losses
+    pos = torch.zeros_like(init, dtype=torch.bool)
+    for g_off, _, cnt, _ in t_eager.ypos_slices:
+        pos[g_off:g_off + cnt] = True
+    de, dg = t_eager.flat_param - init, t_graph.flat_param - init
+    assert de[~pos].abs().max().item() > 0
+    # same arithmetic; what differs is the order of the fp64 atomics and with it a few TF32 roundings
+    assert rel_l2(dg[~pos], de[~pos]) < 2e-2
+    # shift positions move by +-lr*0.01-sized steps whose SIGN comes from a reduced sum: identical except where that sum
+    # is at the noise level
+    same = ((de[pos] - dg[pos]).abs() < 1e-7).float().mean().item()
+    assert same > 0.9, same
+    for (k, a), (_, b) in zip(m_eager.named_buffers(), m_graph.named_buffers()):
+        if a.dtype.is_floating_point:
+            assert rel_l2(b, a) < 1e-3, k
+        else:
+            assert torch.equal(a, b), k
+
+
+def test_learning_rate_lives_on_the_device(cuda_device):
+    """set_lr() after capture changes what replay() does (the rate used to be baked into the graph)"""
+    from shiftgcn_b200.dp import FlatSGDTrainer, reference_lr
+    m = _model(cuda_device, V=33, M=1, num_class=2)
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(4, 3, 32, 33, 1, generator=g).to(cuda_device)
+    y = torch.randint(0, 2, (4,), generator=g).to(cuda_device)
+    t = FlatSGDTrainer(m, lr=0.1)
+    t.capture(x, y, warmup=1)
+    t.set_lr(0.0)
+    before = t.flat_param.clone()
+    t.replay(x, y)
+    torch.cuda.synchronize()
+    assert torch.equal(t.flat_param, before)                     # lr 0: parameters untouched, momentum still advances
+    t.adjust_learning_rate(epoch=0, base_lr=0.1, warm_up_epoch=5)
+    assert abs(t.lr - 0.02) < 1e-12 and abs(reference_lr(70, 0.1, 0, (60, 80)) - 0.01) < 1e-12
+    t.replay(x, y)
+    torch.cuda.synchronize()
+    assert (t.flat_param - before).abs().max().item() > 0
+
+
+def test_frozen_batchnorm_inside_training_unit(cuda_device):
+    """each BatchNorm decides for itself: bn.eval() inside a training unit keeps its running statistics"""
+    from oracle import model_ref
+    from shiftgcn_b200.modules import TCN_GCN_unit
+    from test_gpu_units import _compare
+    torch.manual_seed(1)
+    mod = TCN_GCN_unit(64, 64, None, stride=1, residual=True, num_point=25)
+    ref = model_ref.RefUnit(64, 64, None, stride=1, residual=True, num_point=25)
+    model_ref.fill_module_(mod), model_ref.fill_module_(ref)
+    g = torch.Generator().manual_seed(15)
+    x = torch.randn(2, 64, 14, 25, generator=g)
+    go = torch.randn(2, 64, 14, 25, generator=g)
+
+    class Frozen(torch.nn.Module):
+        """train() everywhere except the two frozen BatchNorms"""
+
+        def __init__(self, unit):
+            super().__init__()
+            self.unit = unit
+
+        def train(self, mode=True):
+            super().train(mode)
+            self.unit.gcn1.bn.eval()
+            self.unit.tcn1.bn2.eval()
+            return self
+
+        def forward(self, x):
+            return self.unit(x)
+
+    _compare(Frozen(mod), Frozen(ref), x, go, True, cuda_device)
+
+
+def test_strided_unit_odd_length_raises(cuda_device):
+    """a stride-2 unit on an odd number of frames: the conv residual has ceil(T/2) frames, the shifted branch T//2;
+    the reference fails on the add, this package raises instead of adding misaligned rows"""
+    from shiftgcn_b200.modules import TCN_GCN_unit
+    mod = TCN_GCN_unit(64, 128, None, stride=2, residual=True, num_point=25).to(cuda_device)
+    with pytest.raises(RuntimeError):
+        mod(torch.randn(2, 64, 13, 25, device=cuda_device))
