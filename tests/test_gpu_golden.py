@@ -41,7 +41,7 @@ def _check(mod, z, train, device):
         want = torch.from_numpy(z[key])
         if name.endswith("ypos"):
             raw = torch.from_numpy(z["raw/" + name]) if "raw/" + name in z.files else None
-            check_ypos_grad(name, p.grad, want, raw)
+            check_ypos_grad(name, p.grad, want, raw, decisive=5e-2, min_sure=0.3)   # exact oracle vs TF32 sums
         elif name.endswith("xpos"):
             assert torch.count_nonzero(p.grad).item() == 0
         else:

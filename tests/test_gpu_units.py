@@ -41,7 +41,13 @@ def _run_ref(ref, x, go, train, emulate):
         model_ref.TF32_EMULATION = False
 
 
-def _compare(mod, ref, x, go, train, device, check_input_grad=True):
+def _compare(mod, ref, x, go, train, device, check_input_grad=True, robust=False):
+    """robust=True (large tensors): gradients vs the TF32-emulating oracle are compared as vectors (L2 <= 1e-2) plus a
+    bound on the FRACTION of entries off by more than 2e-3 of the largest one, instead of entry-wise at 1e-3.  The
+    emulation is not bit-identical to the hardware (accumulation order), so among millions of pre-activations a few land
+    on the other side of a ReLU, and each such flip changes a handful of gradient entries by O(1): measured 1e-2 .. 0.3
+    in max-norm at the benchmark's sequence lengths with < 0.2 % of the entries affected, while a mishandled tile
+    (>= 1/480 of the rows wrong by O(1)) moves the L2 error to >= 4e-2."""
     mod = mod.to(device)
     mod.train(train)
     xc = x.to(device).requires_grad_(True)
@@ -53,7 +59,12 @@ def _compare(mod, ref, x, go, train, device, check_input_grad=True):
         assert out.shape == out_r.shape
         assert rel_err(out, out_r) < tol, f"output (emulate={emulate})"
         if check_input_grad:
-            if emulate:
+            if emulate and robust:
+                assert rel_l2(xc.grad, gx_r) < 1e-2, f"input grad l2 (emulate={emulate})"
+                d = (xc.grad.double().cpu() - gx_r).abs()
+                frac = (d > 2e-3 * gx_r.abs().max()).double().mean().item()
+                assert frac < 1e-2, f"input grad: {frac:.2e} of the entries differ (emulate={emulate})"
+            elif emulate:
                 assert rel_err(xc.grad, gx_r) < tol, f"input grad (emulate={emulate})"
             else:
                 assert rel_l2(xc.grad, gx_r) < TOL_TF32_GRAD, f"input grad (emulate={emulate})"
@@ -71,7 +82,10 @@ def _compare(mod, ref, x, go, train, device, check_input_grad=True):
                 continue
             # gradients that are analytically ~0 (bias before a train-mode BN) are compared absolutely
             floor = 1e-6 * max(go.abs().sum().item(), 1.0)
-            if emulate:
+            if emulate and robust:
+                err = (p.grad.double().cpu() - want).norm().item()
+                assert err < 1e-2 * want.norm().item() + floor, f"grad {name}: l2 err {err:.3e} (emulate={emulate})"
+            elif emulate:
                 scale = max(want.abs().max().item(), 1e-30)
                 err = (p.grad.double().cpu() - want).abs().max().item()
                 assert err < tol * scale + floor, f"grad {name}: err {err:.3e} scale {scale:.3e} (emulate={emulate})"

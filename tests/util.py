@@ -48,13 +48,14 @@ class raw_pos_log:
         return False
 
 
-def check_ypos_grad(name, got, want, raw, floor=1e-9):
-    """K5 output is +-0.01 by the SIGN of a reduced sum: only comparable where the sum is clearly non-zero."""
+def check_ypos_grad(name, got, want, raw, floor=1e-9, decisive=1e-3, min_sure=0.5):
+    """K5 output is +-0.01 by the SIGN of a reduced sum: only comparable where the sum is clearly non-zero
+    (|raw| > decisive * max|raw|; against the exact oracle the TF32 noise of the sums needs a wider margin)."""
     got = got.detach().double().cpu()
     want = want.detach().double().cpu()
     scale = raw.abs().max().item() if raw is not None else 0.0
-    sure = raw.abs() > max(1e-3 * scale, floor) if raw is not None else torch.ones_like(want, dtype=torch.bool)
-    assert sure.float().mean().item() > 0.5, f"{name}: too few channels with a decisive sign"
+    sure = raw.abs() > max(decisive * scale, floor) if raw is not None else torch.ones_like(want, dtype=torch.bool)
+    assert sure.float().mean().item() > min_sure, f"{name}: too few channels with a decisive sign"
     assert torch.equal(got[sure], want[sure].to(got.dtype)) or (got[sure] - want[sure]).abs().max().item() < 1e-9, \
         f"{name}: K5-constrained gradient differs on channels with decisive raw sums"
     assert set(np.round(got.abs().numpy(), 6).tolist()) <= {0.01, 0.0001}, f"{name}: values outside {{0.01, 1e-4}}"
