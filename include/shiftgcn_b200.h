@@ -151,7 +151,13 @@ typedef struct SgcnRowGemm {
   int in0_gs, in1_gs;  /* frame stride of the input rows: group g reads group g*gs (strided 1x1 convolution)       */
   int out_gs;          /* frame stride of the output rows (transposed strided convolution)                         */
   int accum;           /* out += result instead of out = result                                                    */
+  /* contraction precision: SGCN_PREC_TF32 (operands rounded to TF32, the default) or SGCN_PREC_FP32 (3xTF32: both
+   * operands split into a TF32 head and a TF32 tail, D = Ah*Bh + Al*Bh + Ah*Bl with fp32 accumulation -- fp32-accurate,
+   * ~3x the tensor-core work; wimg must then come from sgcn_prep_weight_image_split)                              */
+  int prec;
 } SgcnRowGemm;
+
+enum { SGCN_PREC_TF32 = 0, SGCN_PREC_FP32 = 1 };
 
 enum { SGCN_PRO_SPATIAL = 0, SGCN_PRO_LERP = 1, SGCN_PRO_PLAIN = 2, SGCN_PRO_DY = 3 };
 enum { SGCN_EPI_ROT_RAW = 0, SGCN_EPI_ROT_FUSED = 1, SGCN_EPI_LINEAR = 2, SGCN_EPI_SPATIAL_BWD = 3 };
@@ -172,6 +178,7 @@ typedef struct SgcnWgrad {
   int CA, CB;
   int a_gs;             /* PLAIN: row group g of A is group g*a_gs of a_src (strided 1x1 convolution), 0 or 1 = dense  */
   int b_gs;             /* PLAIN: the same for B / b_src                                                           */
+  int prec;             /* SGCN_PREC_TF32 / SGCN_PREC_FP32 (3xTF32 split of BOTH activation operands)               */
 } SgcnWgrad;
 
 /* PLAIN: dW[a, b] = sum_rows a_src[row, a] * b_src[row, b] with both operands copied as they are (Gram matrices and
@@ -374,6 +381,10 @@ int sgcn_mask_grad_finalize(double* raw, const float* mask, float* dmask, int n,
 
 /* canonical (SWIZZLE_128B, TF32-rounded) image of B[n][k] = src[n*ld_n + k*ld_k], chunked by 64 k */
 int sgcn_prep_weight_image(const float* src, long long ld_n, long long ld_k, int N, int K, float* image, void* stream);
+/* fp32-accurate mode: two canonical images back to back, image[0 .. N*K) = TF32 head of the weights, image[N*K .. 2*N*K) =
+ * TF32 tail (weight - head); consumed by sgcn_rowgemm with prec = SGCN_PREC_FP32 */
+int sgcn_prep_weight_image_split(const float* src, long long ld_n, long long ld_k, int N, int K, float* image,
+                                 void* stream);
 
 /* double -> float copy of a reduction buffer (+ clear) */
 int sgcn_reduce_export(double* src, float* dst, int n, double scale, void* stream);

@@ -16,12 +16,13 @@ class SgcnRowGemm(ctypes.Structure):
     _fields_ = [(n, _vp) for n in ("in0", "in1", "out", "wimg", "pro_a", "pro_b", "pro_c", "bias", "epi_a", "epi_b",
                                    "res", "res2", "res2m", "xin", "stats", "red0")] + \
                [("groups", _ll), ("V", _i), ("G", _i), ("T", _i), ("K", _i), ("N", _i), ("relu", _i), ("k0", _i),
-                ("in0_gs", _i), ("in1_gs", _i), ("out_gs", _i), ("accum", _i)]
+                ("in0_gs", _i), ("in1_gs", _i), ("out_gs", _i), ("accum", _i), ("prec", _i)]
 
 
 class SgcnWgrad(ctypes.Structure):
     _fields_ = [(n, _vp) for n in ("a_src", "a_tab0", "b_src", "b_src2", "b_tab0", "b_tab1", "b_tab2", "dw")] + \
-               [("groups", _ll), ("V", _i), ("G", _i), ("T", _i), ("CA", _i), ("CB", _i), ("a_gs", _i), ("b_gs", _i)]
+               [("groups", _ll), ("V", _i), ("G", _i), ("T", _i), ("CA", _i), ("CB", _i), ("a_gs", _i), ("b_gs", _i),
+                ("prec", _i)]
 
 
 class SgcnTShift(ctypes.Structure):
@@ -104,6 +105,7 @@ SIGNATURES = {
     "sgcn_mask_prepare_rot": [_vp, _vp, _vp, _i, _i, _vp],
     "sgcn_mask_grad_finalize": [_vp, _vp, _vp, _i, _vp],
     "sgcn_prep_weight_image": [_vp, _ll, _ll, _i, _i, _vp, _vp],
+    "sgcn_prep_weight_image_split": [_vp, _ll, _ll, _i, _i, _vp, _vp],
     "sgcn_reduce_export": [_vp, _vp, _i, _d, _vp],
     "sgcn_sgd_epilogue": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp],
 }

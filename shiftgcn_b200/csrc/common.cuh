@@ -59,6 +59,15 @@ __device__ __forceinline__ float to_tf32(float x) {  // round-to-nearest (ties a
 // TF32 ulp to the magnitude is round-to-nearest (ties away) in ONE integer instruction (cvt.rna.tf32 expands to four).
 __device__ __forceinline__ float tf32_half_ulp(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
+// 3xTF32 ("fp32-accurate") operand split: v = hi + lo with hi = TF32-rounded v (exactly representable, low 13 mantissa
+// bits zero) and lo = v - hi (exact in fp32), itself pre-rounded for the tensor core.  A contraction then runs as
+// Ah*Bh + Al*Bh + Ah*Bl: the products of two 11-bit mantissas are exact in the fp32 accumulator and the dropped Al*Bl
+// term is ~2^-22 relative.
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+  lo = tf32_half_ulp(v - hi);
+}
+
 // ------------------------------------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

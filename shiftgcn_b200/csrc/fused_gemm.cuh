@@ -79,15 +79,22 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <int PRO, int EPI, int V, int K, int N>
+// P3 = fp32-accurate mode (3xTF32, SgcnRowGemm::prec): every operand stage holds the TF32 head of the chunk followed by
+// its TF32 tail, the weight image is {head image, tail image} (sgcn_prep_weight_image_split) and the issuer runs three
+// MMA groups per 32-channel block: Ah*Wh, Al*Wh, Ah*Wl.
+template <int PRO, int EPI, int V, int K, int N, bool P3 = false>
 struct Cfg {
   static constexpr int G = 128 / V;
   static constexpr int KC = K / 64, NCH = N / 64;
-  // weights: resident image, or 32-channel blocks streamed through a two-stage ring (the temporal-shift variant
-  // gives shared memory to its wider raw tiles instead)
-  static constexpr bool kWRes = (K * N * 4) <= (PRO == PRO_LERP ? 32768 : 65536);
+  static constexpr int kImgBytes = K * N * 4;                      // one canonical weight image
+  static constexpr int kOpBytes = (P3 ? 2 : 1) * kChunkBytes;      // one operand stage
+  // weights: resident image(s), or 32-channel blocks streamed through a ring (the temporal-shift variant gives shared
+  // memory to its wider raw tiles instead)
+  static constexpr bool kWRes = ((P3 ? 2 : 1) * kImgBytes) <= (PRO == PRO_LERP ? 32768 : 65536);
   static constexpr int kWStage = N * 128;                          // one streamed 32-channel weight block
-  static constexpr int kWBytes = kWRes ? K * N * 4 : 2 * kWStage;
+  static constexpr int kWB = P3 ? 4 : 2;                           // streamed blocks per chunk: (head, tail) x two halves
+  static constexpr int kWRing = (P3 && PRO == PRO_LERP && N >= 256) ? 1 : 2;   // ring depth of the streamed blocks
+  static constexpr int kWBytes = kWRes ? (P3 ? 2 : 1) * kImgBytes : kWRing * kWStage;
   // lane <-> channel work split: a warp owns (joint, 32-channel half) pairs k * 12 + warp, k < kJ
   static constexpr int kPairs = 2 * V;
   static constexpr int kJ = (kPairs + kBldWarps - 1) / kBldWarps;  // kBldWarps == kEpiWarps
@@ -99,26 +106,28 @@ struct Cfg {
   static constexpr int kStBytes = EPI == EPI_LINEAR ? 128 * 32 * 4 : kChunkBytes;   // epilogue staging tile
   // HBM latency x bandwidth needs >= 64 KiB of loads in flight per SM: spend what is left on input stages
   static constexpr int kAvail = 232448 - 1600 - kWBytes - kStBytes;
-  static constexpr int kRaw2 = PRO == PRO_PLAIN ? 0 : (kAvail - 2 * kChunkBytes) / kRawBytes;
-  static constexpr int kRaw1 = PRO == PRO_PLAIN ? 0 : (kAvail - kChunkBytes) / kRawBytes;
-  static constexpr int kOpStages = PRO == PRO_PLAIN ? (kAvail / kChunkBytes < 4 ? kAvail / kChunkBytes : 4) : (kRaw2 >= 3 ? 2 : 1);
+  static constexpr int kRaw2 = PRO == PRO_PLAIN ? 0 : (kAvail - 2 * kOpBytes) / kRawBytes;
+  static constexpr int kRaw1 = PRO == PRO_PLAIN ? 0 : (kAvail - kOpBytes) / kRawBytes;
+  static constexpr int kOpStages = PRO == PRO_PLAIN ? (kAvail / kOpBytes < 4 ? kAvail / kOpBytes : 4) : (kRaw2 >= 3 ? 2 : 1);
   static constexpr int kRawStages = PRO == PRO_PLAIN ? 0 : ((kOpStages == 2 ? kRaw2 : kRaw1) < 4 ? (kOpStages == 2 ? kRaw2 : kRaw1) : 4);
-  static constexpr size_t kSmem = 1024 + kWBytes + kOpStages * kChunkBytes + kStBytes + kRawStages * kRawBytes + 64;
+  static constexpr size_t kSmem = 1024 + kWBytes + kOpStages * kOpBytes + kStBytes + kRawStages * kRawBytes + 64;
   static_assert(PRO == PRO_PLAIN || kRawStages >= 2, "need at least two raw stages");
+  static_assert(kOpStages >= (PRO == PRO_PLAIN ? 2 : 1), "need operand stages");
   static_assert(kSmem <= 232448 - 512, "shared memory budget");
 };
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int PRO, int EPI, int V, int K, int N>
+template <int PRO, int EPI, int V, int K, int N, bool P3>
 __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGemm p, const int rev) {
-  using C = Cfg<PRO, EPI, V, K, N>;
+  using C = Cfg<PRO, EPI, V, K, N, P3>;
+  constexpr int kOpBytes = C::kOpBytes;
   constexpr int G = C::G, KC = C::KC, NCH = C::NCH, OS = C::kOpStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr int RS = C::kRawStages;
   const uint32_t sW = smem0;
   const uint32_t sOp = sW + C::kWBytes;
-  const uint32_t sSt = sOp + OS * kChunkBytes;
+  const uint32_t sSt = sOp + OS * kOpBytes;
   const uint32_t sRaw = sSt + C::kStBytes;
   __shared__ uint64_t op_full[4], op_free[4], acc_full[2], acc_free[2], w_full[2], w_free[2];
   __shared__ uint32_t tmem_base_s;
@@ -181,24 +190,37 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
           const int s = q % OS;
           mbar_wait(&op_full[s], (uint32_t)((q / OS) & 1));
           tc_fence_after();
-          const uint32_t a_lo = dlo | ((sOp + (uint32_t)s * kChunkBytes) >> 4);
+          const uint32_t a_lo = dlo | ((sOp + (uint32_t)s * kOpBytes) >> 4);      // head half of the stage
+          const uint32_t a_tail = a_lo + (uint32_t)(kChunkBytes >> 4);                // tail half (P3)
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk) {
-            uint32_t w0;
-            if (C::kWRes) {
-              w0 = sW + (uint32_t)(kc * 2 + blk) * (uint32_t)C::kWStage;
-            } else {
-              const int h = 2 * q + blk;                            // streamed 32-channel weight block
-              mbar_wait(&w_full[h & 1], (uint32_t)((h >> 1) & 1));
-              tc_fence_after();
-              w0 = sW + (uint32_t)(h & 1) * (uint32_t)C::kWStage;
-            }
-            const uint32_t b_lo = dlo | (w0 >> 4);
+            // weight block (head image; in P3 mode followed by the same block of the tail image)
 #pragma unroll
-            for (int sub = 0; sub < 4; ++sub)
-              umma_tf32(acc, ((uint64_t)dhi << 32) | (a_lo + (uint32_t)(blk * (kBlockBytes >> 4) + sub * 2)),
-                        ((uint64_t)dhi << 32) | (b_lo + (uint32_t)(sub * 2)), idesc, (kc | blk | sub) ? 1u : 0u);
-            if (!C::kWRes) tc_commit(&w_free[blk]);
+            for (int part = 0; part < (P3 ? 2 : 1); ++part) {
+              uint32_t w0;
+              int slot = 0;
+              if (C::kWRes) {
+                w0 = sW + (uint32_t)(part * C::kImgBytes) + (uint32_t)(kc * 2 + blk) * (uint32_t)C::kWStage;
+              } else {
+                const int h = C::kWB * q + (P3 ? 2 * blk + part : blk);   // streamed 32-channel weight block
+                slot = h % C::kWRing;
+                mbar_wait(&w_full[slot], (uint32_t)((h / C::kWRing) & 1));
+                tc_fence_after();
+                w0 = sW + (uint32_t)slot * (uint32_t)C::kWStage;
+              }
+              const uint32_t b_lo = dlo | (w0 >> 4);
+#pragma unroll
+              for (int sub = 0; sub < 4; ++sub)
+                umma_tf32(acc, ((uint64_t)dhi << 32) | (a_lo + (uint32_t)(blk * (kBlockBytes >> 4) + sub * 2)),
+                          ((uint64_t)dhi << 32) | (b_lo + (uint32_t)(sub * 2)), idesc, (kc | blk | sub | part) ? 1u : 0u);
+              if (P3 && part == 0) {                                 // tail of the activations against the weight heads
+#pragma unroll
+                for (int sub = 0; sub < 4; ++sub)
+                  umma_tf32(acc, ((uint64_t)dhi << 32) | (a_tail + (uint32_t)(blk * (kBlockBytes >> 4) + sub * 2)),
+                            ((uint64_t)dhi << 32) | (b_lo + (uint32_t)(sub * 2)), idesc, 1u);
+              }
+              if (!C::kWRes) tc_commit(&w_free[slot]);
+            }
           }
           tc_commit(&op_free[s]);
         }
@@ -206,13 +228,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
       }
     } else if (warp == kLoadWarp && lane == 0 && !C::kWRes) {
       // ================================================================================ weight loader (TMA ring)
-      const int total_blocks = 2 * total_chunks;
+      const int total_blocks = C::kWB * total_chunks;
       for (int h = 0; h < total_blocks; ++h) {
-        const int s = h & 1;
-        if (h >= 2) mbar_wait(&w_free[s], (uint32_t)(((h >> 1) - 1) & 1));
+        const int s = h % C::kWRing;
+        if (h >= C::kWRing) mbar_wait(&w_free[s], (uint32_t)(((h / C::kWRing) - 1) & 1));
+        const int kc = (h / C::kWB) % KC, j = h % C::kWB;            // P3: j = 2 * half + part, else j = half
+        const size_t src = P3 ? (size_t)(j & 1) * C::kImgBytes + (size_t)(kc * 2 + (j >> 1)) * C::kWStage
+                              : (size_t)(kc * 2 + j) * C::kWStage;
         mbar_expect_tx(&w_full[s], C::kWStage);
-        bulk_load(sW + (uint32_t)s * (uint32_t)C::kWStage, (const uint8_t*)p.wimg + (size_t)(h % (2 * KC)) * C::kWStage,
-                  C::kWStage, &w_full[s]);
+        bulk_load(sW + (uint32_t)s * (uint32_t)C::kWStage, (const uint8_t*)p.wimg + src, C::kWStage, &w_full[s]);
       }
     }
     __syncwarp();
@@ -235,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         const int ti = q / KC, kc = q - ti * KC;
         const long long g0 = tile_of(ti) * G;
         const int nrow = (int)((p.groups - g0) < G ? (p.groups - g0) : G) * V;
-        const uint32_t dst = sOp + (uint32_t)(q % OS) * kChunkBytes + dst0;
+        const uint32_t dst = sOp + (uint32_t)(q % OS) * kOpBytes + dst0;
         if (simple) {
           const float* src = p.in0 + ((size_t)g0 * V + prow) * K + kc * 64 + pc4 * 4;
 #pragma unroll
@@ -268,6 +292,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         }
         cp_async_commit();
         cp_wait<OS - 1>();
+        if constexpr (P3) {
+          // split this thread's OWN pieces of chunk q (its cp.async copies have completed) into TF32 head (in place)
+          // and tail (second half of the stage)
+          const int ti = q / KC;
+          const long long g0 = tile_of(ti) * G;
+          const int nrow = (int)((p.groups - g0) < G ? (p.groups - g0) : G) * V;
+          const uint32_t dst = sOp + (uint32_t)(q % OS) * kOpBytes + dst0;
+#pragma unroll
+          for (int i = 0; i < kPieces; ++i)
+            if (prow + 24 * i < nrow) {
+              const float4 v = lds128(dst + (uint32_t)i * 3072u);
+              float4 hi, lo;
+              split_tf32(v.x, hi.x, lo.x), split_tf32(v.y, hi.y, lo.y), split_tf32(v.z, hi.z, lo.z), split_tf32(v.w, hi.w, lo.w);
+              sts128(dst + (uint32_t)i * 3072u, hi);
+              sts128(dst + (uint32_t)i * 3072u + (uint32_t)kChunkBytes, lo);
+            }
+        }
         fence_proxy_async();
         mbar_arrive(&op_full[q % OS]);
       }
@@ -335,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         const int os = q % OS;
         if (q >= OS) mbar_wait(&op_free[os], (uint32_t)(((q / OS) - 1) & 1));
         const uint32_t raw = sRaw + (uint32_t)(q % RS) * C::kRawBytes + (uint32_t)lane * 4u;
-        const uint32_t ob = opb + (uint32_t)os * kChunkBytes;
+        const uint32_t ob = opb + (uint32_t)os * kOpBytes;
 
         // Operand row r = g*V + v (128-byte pitch, 16-byte chunk XOR-ed with (r & 7)), 32-channel half, channel lane:
         //   address = ob + half*16K + r*128 + (((lane >> 2) ^ r) & 7) * 16 + (lane & 3) * 4
@@ -343,7 +384,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         // beyond a partial last tile are written too (their operand rows and outputs are never used).
         const uint32_t lqs = lq << 4;
         auto put = [&](uint32_t base, uint32_t v16, int g, float val) {
-          sts32(base + ((lqs ^ (v16 + (uint32_t)(g * V * 16))) & 0x70u) + (uint32_t)(g * V * 128), tf32_half_ulp(val));
+          const uint32_t addr = base + ((lqs ^ (v16 + (uint32_t)(g * V * 16))) & 0x70u) + (uint32_t)(g * V * 128);
+          if constexpr (P3) {
+            float hi, lo;
+            split_tf32(val, hi, lo);
+            sts32(addr, hi);
+            sts32(addr + (uint32_t)kChunkBytes, lo);
+          } else {
+            sts32(addr, tf32_half_ulp(val));
+          }
         };
         if constexpr (PRO == PRO_SPATIAL) {
           // xm[(g,u), c] = x[g, (u+c) % V, c] * maskmul[u, c]
@@ -611,10 +660,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-template <int PRO, int EPI, int V, int K, int N>
-static int launch(const SgcnRowGemm& p, cudaStream_t s) {
-  using C = Cfg<PRO, EPI, V, K, N>;
-  auto kern = fused_gemm_kernel<PRO, EPI, V, K, N>;
+template <int PRO, int EPI, int V, int K, int N, bool P3>
+static int launch_p(const SgcnRowGemm& p, cudaStream_t s) {
+  using C = Cfg<PRO, EPI, V, K, N, P3>;
+  auto kern = fused_gemm_kernel<PRO, EPI, V, K, N, P3>;
   static std::atomic<unsigned long long> configured{0};           // one bit per device (the attribute is per device)
   if (needs_configure(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem);
@@ -627,6 +676,13 @@ static int launch(const SgcnRowGemm& p, cudaStream_t s) {
   if (grid > ntiles) grid = ntiles;
   kern<<<(unsigned)grid, kThreads, C::kSmem, s>>>(p, next_direction());
   return check_launch("fused_gemm_kernel");
+}
+
+template <int PRO, int EPI, int V, int K, int N>
+static int launch(const SgcnRowGemm& p, cudaStream_t s) {
+  if (p.prec == SGCN_PREC_FP32) return launch_p<PRO, EPI, V, K, N, true>(p, s);
+  if (p.prec != SGCN_PREC_TF32) return set_error("sgcn_rowgemm: unknown precision");
+  return launch_p<PRO, EPI, V, K, N, false>(p, s);
 }
 
 }  // namespace fg

@@ -163,6 +163,18 @@ __global__ void prep_weight_image_kernel(const float* __restrict__ src, long lon
   *(float*)((uint8_t*)image + off) = to_tf32(src[(size_t)n * ld_n + (size_t)k * ld_k]);
 }
 
+__global__ void prep_weight_image_split_kernel(const float* __restrict__ src, long long ld_n, long long ld_k, int N, int K,
+                                               float* __restrict__ image) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const int n = i / K, k = i - n * K;
+  const size_t off = (size_t)(k >> 6) * N * 256 + (size_t)((k >> 5) & 1) * N * 128 + canon_off(n, k & 31);
+  const float w = src[(size_t)n * ld_n + (size_t)k * ld_k];
+  const float hi = to_tf32(w);
+  *(float*)((uint8_t*)image + off) = hi;
+  *(float*)((uint8_t*)image + (size_t)N * K * 4 + off) = to_tf32(w - hi);
+}
+
 __global__ void reduce_export_kernel(double* __restrict__ src, float* __restrict__ dst, int n, double scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -254,6 +266,14 @@ extern "C" int sgcn_prep_weight_image(const float* src, long long ld_n, long lon
   if (N % 8 != 0 || K % 64 != 0) return set_error("sgcn_prep_weight_image: need N % 8 == 0 and K % 64 == 0");
   prep_weight_image_kernel<<<(N * K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src, ld_n, ld_k, N, K, image);
   return check_launch("prep_weight_image_kernel");
+}
+
+extern "C" int sgcn_prep_weight_image_split(const float* src, long long ld_n, long long ld_k, int N, int K, float* image,
+                                            void* stream) {
+  if (!src || !image) return set_error("sgcn_prep_weight_image_split: null pointer");
+  if (N % 8 != 0 || K % 64 != 0) return set_error("sgcn_prep_weight_image_split: need N % 8 == 0 and K % 64 == 0");
+  prep_weight_image_split_kernel<<<(N * K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src, ld_n, ld_k, N, K, image);
+  return check_launch("prep_weight_image_split_kernel");
 }
 
 extern "C" int sgcn_reduce_export(double* src, float* dst, int n, double scale, void* stream) {

@@ -53,27 +53,35 @@ __device__ __forceinline__ uint32_t stage_off(uint32_t row, uint32_t c4, uint32_
   return row * 256u + ((c4 ^ (row & 15u)) << 4) + (j << 2);
 }
 
-template <int V, int K, int N>
+// P3 = fp32-accurate mode (3xTF32, SgcnRowGemm::prec): operand chunks hold {TF32 head, TF32 tail}, the weight image is
+// {head image, tail image} and every chunk runs Ah*Wh, Al*Wh, Ah*Wl.
+template <int V, int K, int N, bool P3 = false>
 struct Cfg {
   static constexpr int G = 128 / V;
   static constexpr int KC = K / 64, NCH = N / 64;
-  static constexpr bool kWRes = (K * N * 4) <= 65536;
-  static constexpr int kWBytes = kWRes ? K * N * 4 : N * 256;
+  static constexpr int kImgBytes = K * N * 4;
+  static constexpr int kOpBytes = (P3 ? 2 : 1) * kChunkBytes;
+  static constexpr bool kWRes = ((P3 ? 2 : 1) * kImgBytes) <= 65536;
+  static constexpr int kWChunk = N * 256;                          // one streamed [N x 64] weight chunk
+  static constexpr int kWLoads = P3 ? 2 : 1;                       // streamed loads per operand chunk (head, tail)
+  static constexpr int kWBytes = kWRes ? (P3 ? 2 : 1) * kImgBytes : kWChunk;
   static constexpr int kSlots = V * 16;                            // (joint, 4-channel group) slots of a 64-wide chunk
   static constexpr int kEpiRounds = (kSlots + kEpiThreads - 1) / kEpiThreads;
   static constexpr int kBldRounds = (kSlots + kBldThreads - 1) / kBldThreads;
-  static constexpr size_t kSmem = 1024 + kWBytes + 3 * kChunkBytes + 64;
+  static constexpr size_t kSmem = 1024 + kWBytes + 2 * kOpBytes + kChunkBytes + 64;
+  static_assert(kSmem <= 232448 - 512, "shared memory budget");
 };
 
-template <int V, int K, int N>
+template <int V, int K, int N, bool P3>
 __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowGemm p, const int rev) {
-  using C = Cfg<V, K, N>;
+  using C = Cfg<V, K, N, P3>;
+  constexpr int kOpBytes = C::kOpBytes;
   constexpr int G = C::G, KC = C::KC, NCH = C::NCH;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
   uint8_t* sOp = sW + C::kWBytes;                                  // 2 operand chunks
-  uint8_t* sSt = sOp + 2 * kChunkBytes;                            // epilogue staging
+  uint8_t* sSt = sOp + 2 * kOpBytes;                               // epilogue staging
   __shared__ uint64_t op_full[2], op_free[2], acc_full[2], acc_free[2], w_full, w_free;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -110,10 +118,16 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(128, N, 0, 0);
       const long long total_chunks = my_tiles * KC;
-      if (!C::kWRes && total_chunks > 0) {
+      // streamed weights: ONE [N x 64] buffer, (re)loaded kWLoads times per operand chunk -- load L = kWLoads * q + part
+      // is chunk kc of the head (part 0) or tail (part 1) image; it is requested as soon as the MMAs that read load
+      // L - 1 have completed
+      const long long total_loads = C::kWLoads * total_chunks;
+      auto load_w = [&](long long L) {
+        const int kc = (int)((L / C::kWLoads) % KC), part = (int)(L % C::kWLoads);
         mbar_expect_tx(&w_full, C::kWBytes);
-        bulk_load(sW, p.wimg, C::kWBytes, &w_full);
-      }
+        bulk_load(sW, (const uint8_t*)p.wimg + (size_t)part * C::kImgBytes + (size_t)kc * C::kWChunk, C::kWBytes, &w_full);
+      };
+      if (!C::kWRes && total_chunks > 0) load_w(0);
       long long q = 0;
       for (long long ti = 0; ti < my_tiles; ++ti) {
         const int buf = (int)(ti & 1);
@@ -123,26 +137,39 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
         for (int kc = 0; kc < KC; ++kc, ++q) {
           const int s = (int)(q & 1);
           mbar_wait(&op_full[s], (uint32_t)((q >> 1) & 1));
-          if (!C::kWRes) mbar_wait(&w_full, (uint32_t)(q & 1));
           tc_fence_after();
-          const uint32_t a0 = smem_u32(sOp) + (uint32_t)s * kChunkBytes;
-          const uint32_t w0 = smem_u32(sW) + (C::kWRes ? (uint32_t)kc * (uint32_t)N * 256u : 0u);
+          const uint32_t a0 = smem_u32(sOp) + (uint32_t)s * kOpBytes;
 #pragma unroll
-          for (int k8 = 0; k8 < 8; ++k8) {
-            const uint32_t blk = k8 >> 2, sub = k8 & 3;
-            umma_tf32(acc, umma_desc(a0 + blk * kBlockBytes + sub * 32, 16, 1024),
-                      umma_desc(w0 + blk * (uint32_t)N * 128u + sub * 32, 16, 1024), idesc, (kc | k8) ? 1u : 0u);
-          }
-          tc_commit(&op_free[s]);
-          if (!C::kWRes) {
-            tc_commit(&w_free);
-            if (q + 1 < total_chunks) {                   // single weight buffer: reload once these MMAs have read it
-              mbar_wait(&w_free, (uint32_t)(q & 1));
-              const int kn = (kc + 1) % KC;
-              mbar_expect_tx(&w_full, C::kWBytes);
-              bulk_load(sW, (const uint8_t*)p.wimg + (size_t)kn * C::kWBytes, C::kWBytes, &w_full);
+          for (int part = 0; part < (P3 ? 2 : 1); ++part) {
+            const long long L = C::kWLoads * q + part;
+            if (!C::kWRes) {
+              mbar_wait(&w_full, (uint32_t)(L & 1));
+              tc_fence_after();
+            }
+            const uint32_t w0 = smem_u32(sW) + (C::kWRes ? (uint32_t)(part * C::kImgBytes) + (uint32_t)kc * (uint32_t)C::kWChunk : 0u);
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8) {
+              const uint32_t blk = k8 >> 2, sub = k8 & 3;
+              umma_tf32(acc, umma_desc(a0 + blk * kBlockBytes + sub * 32, 16, 1024),
+                        umma_desc(w0 + blk * (uint32_t)N * 128u + sub * 32, 16, 1024), idesc, (kc | k8 | part) ? 1u : 0u);
+            }
+            if (P3 && part == 0) {                                  // tail of the activations against the weight heads
+#pragma unroll
+              for (int k8 = 0; k8 < 8; ++k8) {
+                const uint32_t blk = k8 >> 2, sub = k8 & 3;
+                umma_tf32(acc, umma_desc(a0 + kChunkBytes + blk * kBlockBytes + sub * 32, 16, 1024),
+                          umma_desc(w0 + blk * (uint32_t)N * 128u + sub * 32, 16, 1024), idesc, 1u);
+              }
+            }
+            if (!C::kWRes) {
+              tc_commit(&w_free);
+              if (L + 1 < total_loads) {                            // single weight buffer: reload once these MMAs have read it
+                mbar_wait(&w_free, (uint32_t)(L & 1));
+                load_w(L + 1);
+              }
             }
           }
+          tc_commit(&op_free[s]);
         }
         tc_commit(&acc_full[buf]);
       }
@@ -160,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
       for (int kc = 0; kc < KC; ++kc, ++q) {
         const int s = (int)(q & 1);
         if (q >= 2) mbar_wait(&op_free[s], (uint32_t)(((q >> 1) - 1) & 1));
-        uint8_t* op = sOp + (size_t)s * kChunkBytes;
+        uint8_t* op = sOp + (size_t)s * kOpBytes;
 #pragma unroll
         for (int rd = 0; rd < C::kBldRounds; ++rd) {
           const int slot = bt + rd * kBldThreads;
@@ -191,8 +218,15 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
                   int u = u0 - j;
                   if (u < 0) u += V;
                   const uint32_t row = (uint32_t)(g * V + u);
-                  *(float*)(op + blk_off + (row >> 3) * 1024u + (row & 7u) * 128u + ((cc ^ (row & 7u)) << 4) + j * 4) =
-                      tf32_half_ulp(dz[j]);
+                  float* dst = (float*)(op + blk_off + (row >> 3) * 1024u + (row & 7u) * 128u + ((cc ^ (row & 7u)) << 4) + j * 4);
+                  if constexpr (P3) {
+                    float hi, lo;
+                    split_tf32(dz[j], hi, lo);
+                    *dst = hi;
+                    *(float*)((uint8_t*)dst + kChunkBytes) = lo;
+                  } else {
+                    *dst = tf32_half_ulp(dz[j]);
+                  }
                 }
               }
           }
@@ -329,10 +363,10 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-template <int V, int K, int N>
-static int launch(const SgcnRowGemm& p, cudaStream_t s) {
-  using C = Cfg<V, K, N>;
-  auto kern = spatial_bwd_kernel<V, K, N>;
+template <int V, int K, int N, bool P3>
+static int launch_p(const SgcnRowGemm& p, cudaStream_t s) {
+  using C = Cfg<V, K, N, P3>;
+  auto kern = spatial_bwd_kernel<V, K, N, P3>;
   static std::atomic<unsigned long long> configured{0};           // one bit per device (the attribute is per device)
   if (needs_configure(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem);
@@ -345,6 +379,13 @@ static int launch(const SgcnRowGemm& p, cudaStream_t s) {
   if (grid > ntiles) grid = ntiles;
   kern<<<(unsigned)grid, kThreads, C::kSmem, s>>>(p, next_direction());
   return check_launch("spatial_bwd_kernel");
+}
+
+template <int V, int K, int N>
+static int launch(const SgcnRowGemm& p, cudaStream_t s) {
+  if (p.prec == SGCN_PREC_FP32) return launch_p<V, K, N, true>(p, s);
+  if (p.prec != SGCN_PREC_TF32) return set_error("sgcn_rowgemm: unknown precision");
+  return launch_p<V, K, N, false>(p, s);
 }
 
 template <int V>

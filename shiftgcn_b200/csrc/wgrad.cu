@@ -47,15 +47,16 @@ struct WgGeom {
 
 __host__ __device__ constexpr int wg_vp(int V) { return ((V + 7) / 8) * 8; }
 
-// largest tile (G in {4,3,2,1}) that leaves room for three stages (two for the widest layers)
-__host__ __device__ inline WgGeom wg_geom(int CA, int CB, int V) {
+// largest tile (G in {4,3,2,1}) that leaves room for three stages (two for the widest layers).  mult = 2 in the
+// fp32-accurate mode (3xTF32, SgcnWgrad::prec): a stage then holds the TF32 heads of A and B followed by their tails.
+__host__ __device__ inline WgGeom wg_geom(int CA, int CB, int V, int mult) {
   WgGeom g;
   const int cands[4] = {4, 3, 2, 1};
   for (int i = 0; i < 4; ++i) {
     g.G = cands[i];
     g.KR = g.G * wg_vp(V);
     g.blk = g.KR * 128;
-    g.stage = ((CA + CB) / 32) * g.blk;
+    g.stage = mult * ((CA + CB) / 32) * g.blk;
     g.nstages = kWgSmemBudget / g.stage;
     if (g.nstages > kWgMaxGroups) g.nstages = kWgMaxGroups;
     if (g.KR <= 128 && g.nstages >= (g.G == 1 ? 1 : 3)) break;
@@ -71,11 +72,11 @@ __device__ __forceinline__ void sts_tf32(uint32_t saddr, float v) { sts32(saddr,
 // Tile row order: row(g, v) = g * VP + v.  The contraction runs over rows, so any order works as long as A and B
 // agree; this one makes the swizzle phase (row & 3) of every row a builder thread writes equal to (warp & 3),
 // i.e. all shared-memory offsets are "per-thread constant + compile-time immediate".
-__host__ __device__ constexpr int wg_pick_g(int CA, int CB, int V) {   // same rule as wg_geom, usable as a template argument
+__host__ __device__ constexpr int wg_pick_g(int CA, int CB, int V, int mult) {   // same rule as wg_geom, usable as a template argument
   for (int i = 0; i < 4; ++i) {
     const int G = 4 - i;
     const int KR = G * wg_vp(V);
-    const int stage = ((CA + CB) / 32) * KR * 128;
+    const int stage = mult * ((CA + CB) / 32) * KR * 128;
     int ns = kWgSmemBudget / stage;
     if (ns > kWgMaxGroups) ns = kWgMaxGroups;
     if (KR <= 128 && ns >= (G == 1 ? 1 : 3)) return G;
@@ -83,9 +84,9 @@ __host__ __device__ constexpr int wg_pick_g(int CA, int CB, int V) {   // same r
   return 1;
 }
 
-template <int MODE, int V, int CA, int CB>
+template <int MODE, int V, int CA, int CB, bool P3>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p, const WgGeom geo, const int rev) {
-  constexpr int G = wg_pick_g(CA, CB, V);
+  constexpr int G = wg_pick_g(CA, CB, V, P3 ? 2 : 1);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -96,7 +97,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
   constexpr uint32_t ablocks = CA / 32, bblocks = CB / 32;
   constexpr int mblocks = (CA + 127) / 128;
   const int NG = geo.nstages;
-  const uint32_t stage_bytes = (ablocks + bblocks) * BLK;
+  constexpr uint32_t kTail = (ablocks + bblocks) * BLK;     // P3: byte offset from a head element to its tail
+  const uint32_t stage_bytes = (P3 ? 2u : 1u) * kTail;
+  // store one operand element: TF32-rounded, or (P3) its TF32 head plus the tail kTail bytes further on
+  auto put = [&](uint32_t saddr, float v) {
+    if constexpr (P3) {
+      float hi, lo;
+      split_tf32(v, hi, lo);
+      sts32(saddr, hi);
+      sts32(saddr + kTail, lo);
+    } else {
+      sts32(saddr, tf32_half_ulp(v));
+    }
+  };
 
   __shared__ uint64_t bar_full[kWgMaxGroups], bar_free[kWgMaxGroups], bar_done;
   __shared__ uint32_t tmem_base_s;
@@ -139,9 +152,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
         const uint32_t sb = sa + ablocks * (uint32_t)BLK;
         for (int mb = 0; mb < mblocks; ++mb)
 #pragma unroll
-          for (int ks = 0; ks < KR / 8; ++ks)
-            umma_tf32(tmem_base + (uint32_t)(mb * CB), umma_desc(sa + (uint32_t)mb * 4u * BLK + ks * 1024, BLK, 512, 1),
-                      umma_desc(sb + ks * 1024, BLK, 512, 1), idesc, (j | ks) ? 1u : 0u);
+          for (int ks = 0; ks < KR / 8; ++ks) {
+            const uint64_t da = umma_desc(sa + (uint32_t)mb * 4u * BLK + ks * 1024, BLK, 512, 1);
+            const uint64_t db = umma_desc(sb + ks * 1024, BLK, 512, 1);
+            umma_tf32(tmem_base + (uint32_t)(mb * CB), da, db, idesc, (j | ks) ? 1u : 0u);
+            if constexpr (P3) {                               // + A_tail^T B_head + A_head^T B_tail
+              umma_tf32(tmem_base + (uint32_t)(mb * CB), umma_desc(sa + kTail + (uint32_t)mb * 4u * BLK + ks * 1024, BLK, 512, 1),
+                        db, idesc, 1u);
+              umma_tf32(tmem_base + (uint32_t)(mb * CB), da, umma_desc(sb + kTail + ks * 1024, BLK, 512, 1), idesc, 1u);
+            }
+          }
         tc_commit(&bar_free[s]);
       }
       tc_commit(&bar_done);
@@ -190,6 +210,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
           cp_async_commit();
         }
       };
+      // P3: once this thread's cp.async copies have landed it splits ITS OWN 16-byte pieces of a raw-copied operand
+      // (blocks at `base`, `C` channels wide, group stride `gs`) into TF32 heads (in place) and tails
+      auto split_own = [&](uint8_t* base, int C, long long gs) {
+        (void)gs;
+        const int ppr = C >> 2;
+        const int k = gt & (ppr - 1);
+        const uint32_t kk = (uint32_t)k & 7u;
+        const uint32_t poff = ((uint32_t)k >> 3) * BLK + ((kk & 1u) << 4);
+        const int rstep = kWgGroupThreads / ppr;
+        for (int q = gt / ppr; q < ng * V; q += rstep) {
+          const int g = q / V, v = q - g * V;
+          const uint32_t r = (uint32_t)(g * VP + v);
+          float4* ptr = (float4*)(base + poff + r * 128u + ((((kk >> 1) ^ (r & 3u))) << 5));
+          const float4 x = *ptr;
+          float4 hi, lo;
+          split_tf32(x.x, hi.x, lo.x), split_tf32(x.y, hi.y, lo.y), split_tf32(x.z, hi.z, lo.z), split_tf32(x.w, hi.w, lo.w);
+          *ptr = hi;
+          *(float4*)((uint8_t*)ptr + kTail) = lo;
+        }
+      };
       auto stage_ready = [&]() {                             // TEMPORAL: called in front of the first store of a tile
         if (a_pending) {
           if (use > 0) mbar_wait(&bar_free[grp], (uint32_t)((use - 1) & 1));
@@ -215,6 +255,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
         }
         cp_async_commit();
         cp_async_wait_all();
+        if constexpr (P3) {
+          split_own(sA, CA, 1);
+          split_own(sBp, CB, 1);
+        }
       } else if (MODE == WG_TEMPORAL) {
         // ---- B = p[(g,v), c] = (1-f) U(t+y1) + f U(t+y1+1),  U = sa*h + sb inside the sample, 0 outside
         const int t0 = (int)(g0 % T);                        // frame of the tile's first group
@@ -265,7 +309,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
                       const float* row = p.b_src + ((size_t)(g0 - t0) * V + (w + 8 * sl)) * CB + c;   // frame 0 of the sample
                       const float u0 = (unsigned)ta < (unsigned)T ? fmaf(sa, __ldg(row + (size_t)ta * V * CB), sb[b]) : 0.f;
                       const float u1 = (unsigned)tb < (unsigned)T ? fmaf(sa, __ldg(row + (size_t)tb * V * CB), sb[b]) : 0.f;
-                      sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(f, u1, (1.f - f) * u0));
+                      put(dst + (g * VP + 8 * sl) * 128, fmaf(f, u1, (1.f - f) * u0));
                     }
                 continue;
               }
@@ -274,7 +318,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
                 if (w + 8 * sl < V) {
 #pragma unroll
                   for (int g = 0; g < G; ++g)
-                    sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(a0[b], L[b][sl][g], fmaf(a1[b], L[b][sl][g + 1], sb[b])));
+                    put(dst + (g * VP + 8 * sl) * 128, fmaf(a0[b], L[b][sl][g], fmaf(a1[b], L[b][sl][g + 1], sb[b])));
                 }
             }
           }
@@ -319,7 +363,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
                   for (int k = 0; k <= G; ++k) U[k] = ok[k] ? fmaf(sa[b], L[b][sl][k], sb[b]) : 0.f;
 #pragma unroll
                   for (int g = 0; g < G; ++g)
-                    if (g < ng) sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(f[b], U[g + 1], f0 * U[g]));
+                    if (g < ng) put(dst + (g * VP + 8 * sl) * 128, fmaf(f[b], U[g + 1], f0 * U[g]));
                 }
             } else {
 #pragma unroll
@@ -332,13 +376,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
                       if (t >= T) t -= T;
                       const float u0 = ((unsigned)(t + y1[b]) < (unsigned)T) ? fmaf(sa[b], L[b][sl][g], sb[b]) : 0.f;
                       const float u1 = ((unsigned)(t + y1[b] + 1) < (unsigned)T) ? fmaf(sa[b], L[b][sl][g + 1], sb[b]) : 0.f;
-                      sts_tf32(dst + (g * VP + 8 * sl) * 128, fmaf(f[b], u1, f0 * u0));
+                      put(dst + (g * VP + 8 * sl) * 128, fmaf(f[b], u1, f0 * u0));
                     }
                 }
             }
           }
         }
         cp_async_wait_all();
+        if constexpr (P3) split_own(sA, CA, 1);
       } else {
         auto build_spatial = [&](auto full_tag) {
           constexpr bool kFull = decltype(full_tag)::value;   // full tile: compile-time offsets, no predicates
@@ -348,7 +393,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
         // the BASE32B swizzle spreads over all 32 banks.
         // ---- A = xm[(g,u), c] = x[g, (u+c) % V, c] * maskmul[u, c]          (model/shift_gcn.py:127-129)
         //      loaded as x[g, sv, c] -> row u = (sv - c) mod V;  a_tab0[sv, c] = maskmul[(sv - c) mod V, c]
-        constexpr int NB = G >= 4 ? 1 : (G >= 2 ? 2 : 4);   // 32-channel blocks per batch: ~16 independent loads in flight
+        constexpr int NB0 = G >= 4 ? 1 : (G >= 2 ? 2 : 4);  // 32-channel blocks per batch: ~16 independent loads in flight
+        constexpr int NB = NB0 < (int)ablocks ? NB0 : (int)ablocks;   // (never more blocks than A has: CA = 64 with G = 1)
         constexpr int NBB = G >= 4 ? 1 : 2;
         for (uint32_t blk0 = 0; blk0 < ablocks; blk0 += NB) {
           float val[NB][KV][G], mm[NB][KV];
@@ -379,7 +425,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
               if (w + 8 * sl < V) {
 #pragma unroll
                 for (int g = 0; g < G; ++g)
-                  if (kFull || g < ng) sts_tf32(dst + off[b][sl] + g * VP * 128, val[b][sl][g] * mm[b][sl]);
+                  if (kFull || g < ng) put(dst + off[b][sl] + g * VP * 128, val[b][sl][g] * mm[b][sl]);
               }
           }
         }
@@ -426,7 +472,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
 #pragma unroll
                   for (int g = 0; g < G; ++g)
                     if (kFull || g < ng)
-                      sts_tf32(dst + off[b][i] + g * VP * 128, fmaf(al[b][i], gv[b][i][g], fmaf(be[b][i], zv[b][i][g], ga[b][i])));
+                      put(dst + off[b][i] + g * VP * 128, fmaf(al[b][i], gv[b][i][g], fmaf(be[b][i], zv[b][i][g], ga[b][i])));
                 }
               }
             }
@@ -437,7 +483,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
         else build_spatial(std::false_type{});
       }
       if (ng < G) {   // partial last tile: rows of missing groups may hold an earlier tile
-        const int nblk = (int)(ablocks + bblocks);
+        const int nblk = (int)((P3 ? 2 : 1) * (ablocks + bblocks));
         for (int r = ng * VP + w; r < KR; r += 8)
           for (int blk = 0; blk < nblk; ++blk) *(float*)(sA + (size_t)blk * BLK + r * 128 + lane * 4) = 0.f;
       }
@@ -473,13 +519,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-template <int MODE, int V, int CA, int CB>
-static int launch_wgrad_cc(const SgcnWgrad& p, cudaStream_t s) {
-  const WgGeom geo = wg_geom(CA, CB, V);
-  constexpr int G = wg_pick_g(CA, CB, V);
+template <int MODE, int V, int CA, int CB, bool P3>
+static int launch_wgrad_p(const SgcnWgrad& p, cudaStream_t s) {
+  const WgGeom geo = wg_geom(CA, CB, V, P3 ? 2 : 1);
+  constexpr int G = wg_pick_g(CA, CB, V, P3 ? 2 : 1);
   if (geo.nstages < 1 || geo.G != G) return set_error("sgcn_wgrad: operand stage does not fit in shared memory");
   const size_t smem = 1024 + (size_t)geo.nstages * geo.stage + 64;
-  auto kern = wgrad_kernel<MODE, V, CA, CB>;
+  auto kern = wgrad_kernel<MODE, V, CA, CB, P3>;
   static std::atomic<unsigned long long> configured{0};           // one bit per device; smem is fixed per instantiation
   if (needs_configure(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -492,6 +538,13 @@ static int launch_wgrad_cc(const SgcnWgrad& p, cudaStream_t s) {
   if (grid > ntiles) grid = ntiles;
   kern<<<(unsigned)grid, kWgThreads, smem, s>>>(p, geo, next_direction());
   return check_launch("wgrad_kernel");
+}
+
+template <int MODE, int V, int CA, int CB>
+static int launch_wgrad_cc(const SgcnWgrad& p, cudaStream_t s) {
+  if (p.prec == SGCN_PREC_FP32) return launch_wgrad_p<MODE, V, CA, CB, true>(p, s);
+  if (p.prec != SGCN_PREC_TF32) return set_error("sgcn_wgrad: unknown precision");
+  return launch_wgrad_p<MODE, V, CA, CB, false>(p, s);
 }
 
 template <int MODE, int V>

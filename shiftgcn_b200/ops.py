@@ -6,6 +6,7 @@ omits), launches on the current stream of the tensors' device and never synchron
 """
 import contextlib
 import ctypes
+import os
 import threading
 
 import torch
@@ -16,6 +17,45 @@ from ._lib import SgcnRowGemm, SgcnSideBwd, SgcnSideFold, SgcnStem, SgcnTShift, 
 PRO_SPATIAL, PRO_LERP, PRO_PLAIN, PRO_DY = 0, 1, 2, 3
 EPI_ROT_RAW, EPI_ROT_FUSED, EPI_LINEAR, EPI_SPATIAL_BWD = 0, 1, 2, 3
 WG_SPATIAL, WG_TEMPORAL, WG_PLAIN = 0, 1, 2
+
+
+PREC_TF32, PREC_FP32 = 0, 1
+_PRECISION_NAMES = {"tf32": PREC_TF32, "fp32": PREC_FP32}
+# Contraction precision of the tensor-core kernels (process-wide; SGCN_PRECISION sets the start value):
+#   "tf32"  operands rounded to TF32 (10-bit mantissa), fp32 accumulation -- the fast default (<= 1e-2 contract)
+#   "fp32"  3xTF32: both operands split into TF32 head + tail, three MMA groups per block -- fp32-accurate
+#           (<= 1e-5 contract; the reference's einsum is a true fp32 contraction, model/shift_gcn.py:131)
+_precision = _PRECISION_NAMES.get(os.environ.get("SGCN_PRECISION", "tf32").lower(), PREC_TF32)
+
+
+def set_precision(mode):
+    """"tf32" (default) or "fp32" (3xTF32 operand split, fp32-accurate); returns the previous mode's name.  Forward and
+    backward of a step should run under the same mode."""
+    global _precision
+    if mode not in _PRECISION_NAMES:
+        raise ValueError(f"precision must be one of {sorted(_PRECISION_NAMES)}, got {mode!r}")
+    prev = get_precision()
+    _precision = _PRECISION_NAMES[mode]
+    return prev
+
+
+def get_precision():
+    return "fp32" if _precision == PREC_FP32 else "tf32"
+
+
+class precision:
+    """``with ops.precision("fp32"): ...`` -- scoped precision of the tensor-core contractions"""
+
+    def __init__(self, mode):
+        self.mode, self.prev = mode, None
+
+    def __enter__(self):
+        self.prev = set_precision(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        set_precision(self.prev)
+        return False
 
 
 LAUNCHES = 0          # kernels of this library enqueued so far (bench.py reports the per-step count)
@@ -194,9 +234,14 @@ def shift_backward(grad_output, inp, output, xpos, ypos, stride, return_raw=Fals
 
 # ------------------------------------------------------------------------------------------------ small helpers
 def weight_image(src, ld_n, ld_k, N, K):
-    """canonical TF32 image of B[n][k] = src.flatten()[n*ld_n + k*ld_k]"""
+    """canonical TF32 image of B[n][k] = src.flatten()[n*ld_n + k*ld_k]; in "fp32" precision the head image followed
+    by the tail image (what sgcn_rowgemm expects under SGCN_PREC_FP32)"""
     _count()
     lib = _lib.load()
+    if _precision == PREC_FP32:
+        img = torch.empty(2 * N * K, device=src.device, dtype=torch.float32)
+        _call("weight image (split)", lib.sgcn_prep_weight_image_split, _p(src, name="weight"), ld_n, ld_k, N, K, _p(img), _STREAM)
+        return img
     img = torch.empty(N * K, device=src.device, dtype=torch.float32)
     _call("weight image", lib.sgcn_prep_weight_image, _p(src, name="weight"), ld_n, ld_k, N, K, _p(img), _STREAM)
     return img
@@ -273,7 +318,9 @@ def rowgemm(pro, epi, *, in0, out, wimg, groups, V, K, N, T=1, in1=None, pro_a=N
                     pro_b=_p(pro_b), pro_c=_p(pro_c), bias=_p(bias), epi_a=_p(epi_a), epi_b=_p(epi_b), res=_p(res),
                     res2=_p(res2), res2m=_p(res2m), xin=_p(xin), stats=_d(stats), red0=_d(red0), groups=int(groups),
                     V=V, G=groups_per_tile(V), T=int(T), K=K, N=N, relu=int(relu), k0=int(k0), in0_gs=int(in0_gs),
-                    in1_gs=int(in1_gs), out_gs=int(out_gs), accum=int(accum))
+                    in1_gs=int(in1_gs), out_gs=int(out_gs), accum=int(accum), prec=_precision)
+    if wimg.numel() != (2 if _precision == PREC_FP32 else 1) * K * N:
+        raise RuntimeError("rowgemm: the weight image was prepared under a different precision mode")
     name = "rowgemm[%s/%s]" % (("spatial", "lerp", "plain", "dy")[pro], ("rot_raw", "rot_fused", "linear", "spatial_bwd")[epi])
     nbytes = int(groups) * V * 4 * (K + N * (2 if accum else 1)) if pro == PRO_PLAIN else _nbytes(in0, in1, out, res, res2, res2m, xin)
     _launch(name, 1, nbytes, lib.sgcn_rowgemm, ctypes.byref(p), pro, epi, _STREAM)
@@ -284,7 +331,7 @@ def wgrad(mode, *, a_src, b_src, dw, groups, V, CA, CB, T=1, a_tab0=None, b_src2
     lib = _lib.load()
     p = SgcnWgrad(a_src=_p(a_src), a_tab0=_p(a_tab0), b_src=_p(b_src), b_src2=_p(b_src2), b_tab0=_p(b_tab0),
                   b_tab1=_p(b_tab1), b_tab2=_p(b_tab2), dw=_p(dw), groups=int(groups), V=V, G=groups_per_tile(V),
-                  T=int(T), CA=CA, CB=CB, a_gs=int(a_gs), b_gs=int(b_gs))
+                  T=int(T), CA=CA, CB=CB, a_gs=int(a_gs), b_gs=int(b_gs), prec=_precision)
     nbytes = int(groups) * V * 4 * (CA + CB) if mode == WG_PLAIN else _nbytes(a_src, b_src, b_src2)
     _launch("wgrad[%s]" % ("spatial", "temporal", "plain")[mode], 1, nbytes, lib.sgcn_wgrad,
             ctypes.byref(p), mode, _STREAM)
