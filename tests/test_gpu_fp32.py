@@ -4,6 +4,12 @@ asks for fp32 results within 1e-5 relative error; the default TF32 mode is held 
 unit type runs forward + backward under ``ops.precision("fp32")``:
   outputs, BatchNorm buffers      <= 1e-5 of the largest reference entry
   input / parameter gradients     <= 5e-5 (a backward pass chains 3-5 contractions and fp32 reductions over n*T*V rows)
+
+The gradient bounds hold only while every ReLU takes the same branch in fp32 and in the fp64 oracle.  A pre-activation
+that lies within fp32 rounding (~1e-6 of the tensor maximum) of zero flips its mask and changes a few thousand gradient
+entries by O(10 %) -- about one such element per 1-2 million ReLU inputs.  The seeds below are draws without such an
+element (tools/diag_unit_bwd.py locates the offending entry when a new draw has one: with seed 54 the 256-channel
+multi-tile case differs from the oracle in exactly ONE element of the conv-output gradient, (n,t,v,c) = (0,46,12,56)).
 """
 import copy
 
@@ -119,7 +125,7 @@ def test_tcn_gcn_unit_fp32_many_tiles_per_cta(cuda_device, C, D, V, n, T, stride
     mod = TCN_GCN_unit(C, D, None, stride=stride, residual=True, num_point=V)
     ref = model_ref.RefUnit(C, D, None, stride=stride, residual=True, num_point=V)
     fill_pair(mod, ref)
-    g = torch.Generator().manual_seed(54)
+    g = torch.Generator().manual_seed(53)             # see the module docstring: seed 54 draws a ReLU input at the kink
     x = torch.randn(n, C, T, V, generator=g)
     go = torch.randn(n, D, T // stride, V, generator=g)
     prev = ops.set_max_ctas(3)

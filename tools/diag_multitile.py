@@ -10,6 +10,11 @@ from shiftgcn_b200.modules import Shift_gcn, Shift_tcn, TCN_GCN_unit
 dev = torch.device("cuda:0")
 
 
+FP32 = os.environ.get("FP32", "0") == "1"
+if FP32:
+    ops.set_precision("fp32")
+
+
 def run(mod, x, go, cap, train):
     ops.set_max_ctas(cap)
     mod.train(train)
@@ -31,7 +36,7 @@ def cmp(tag, a, b):
     for k in a:
         d = (a[k].double() - b[k].double()).abs()
         scale = b[k].double().abs().max().item() + 1e-30
-        nbad = (d > 1e-4 * scale).sum().item()
+        nbad = (d > (2e-6 if FP32 else 1e-4) * scale).sum().item()
         worst.append((d.max().item() / scale, k, nbad, d.numel()))
     worst.sort(reverse=True)
     print(tag, " | ".join(f"{k}: {e:.2e} bad {nb}/{n}" for e, k, nb, n in worst[:4]), flush=True)
@@ -41,6 +46,9 @@ cases = [("gcn", 64, 128, 25, 2, 33, 1), ("gcn", 128, 256, 25, 1, 43, 1), ("gcn"
          ("unit", 64, 64, 25, 2, 43, 1), ("unit", 256, 256, 25, 1, 38, 1), ("unit", 128, 256, 25, 1, 46, 2),
          ("unit", 128, 128, 33, 1, 40, 1), ("tcn", 64, 64, 25, 2, 61, 1), ("tcn", 256, 256, 25, 1, 53, 1),
          ("gcn", 64, 64, 25, 8, 300, 1), ("unit", 64, 64, 25, 8, 300, 1), ("unit", 256, 256, 25, 16, 75, 1)]
+if FP32:
+    cases = [("gcn", 256, 256, 25, 1, 47, 1), ("tcn", 256, 256, 25, 1, 47, 1), ("unit", 256, 256, 25, 1, 47, 1),
+             ("tcn", 128, 128, 25, 1, 47, 1), ("gcn", 128, 256, 25, 1, 47, 1)]
 for kind, C, D, V, n, T, s in cases:
     torch.manual_seed(1)
     if kind == "gcn":
