@@ -90,6 +90,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// Wait of a MANY-thread role (builder / epilogue warps) on a hand-over that is usually not there yet: spinning on
+// try_wait costs three issue slots per probe on the sub-partition the working warps share, so back off with nanosleep
+// between probes.  The single MMA-issuing lane keeps the tight loop above (its latency is on the critical path).
+#ifndef SGCN_WAIT_NS
+#define SGCN_WAIT_NS 0
+#endif
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+#if SGCN_WAIT_NS > 0
+  const uint32_t addr = smem_u32(bar);
+  while (!mbar_try(addr, parity)) __nanosleep(SGCN_WAIT_NS);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------ cp.async
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");

@@ -103,7 +103,11 @@ struct Cfg {
   static constexpr int kWin = PRO == PRO_LERP ? (K == 64 ? 3 : 2) : 0;   // distinct floor(ypos) values the raw tile covers
   static constexpr int kRawRows = (G + kWin) * V;
   static constexpr int kRawBytes = PRO == PRO_PLAIN ? 0 : kRawRows * 256;
-  static constexpr int kStBytes = EPI == EPI_LINEAR ? 128 * 32 * 4 : kChunkBytes;   // epilogue staging tile
+  // epilogue staging tile.  ROT_*: [128 rows x 64 channels] with a row pitch of 68 floats -- "thread = row" 128-bit
+  // stores are conflict free (8 consecutive rows cover the eight 16-byte bank groups) and the rotated "lane = channel"
+  // reads need no swizzle arithmetic: bank = (4*row + channel) % 32, at most 2-way conflicts where the rotation wraps
+  static constexpr int kStPitch = 272;
+  static constexpr int kStBytes = EPI == EPI_LINEAR ? 128 * 32 * 4 : 128 * kStPitch;
   // HBM latency x bandwidth needs >= 64 KiB of loads in flight per SM: spend what is left on input stages
   static constexpr int kAvail = 232448 - 1600 - kWBytes - kStBytes;
   static constexpr int kRaw2 = PRO == PRO_PLAIN ? 0 : (kAvail - 2 * kOpBytes) / kRawBytes;
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
       for (int q = 0; q < total_chunks; ++q) {
         const int qn = q + OS - 1;                                 // refill the stage chunk q-1 has just left
         if (qn < total_chunks) {
-          if (q >= 1) mbar_wait(&op_free[(q - 1) % OS], (uint32_t)(((q - 1) / OS) & 1));
+          if (q >= 1) mbar_wait_relaxed(&op_free[(q - 1) % OS], (uint32_t)(((q - 1) / OS) & 1));
           issue(qn);
         }
         cp_async_commit();
@@ -369,12 +373,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         const int ti = q / KC, kc = q - ti * KC;
         const long long g0 = tile_of(ti) * G;
         const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
+        // the per-(joint, channel) / per-channel tables of this chunk are requested BEFORE the wait for its raw rows:
+        // loaded right in front of their use, every (joint, half) pair paid a full global-load latency (ncu: 28 % of
+        // the builder warps' stall samples sat on the first multiply of each pair)
+        const int tc = kc * 64 + (bw & 1) * 32 + lane;             // pairs k*12 + bw keep the parity of bw
+        float tab[PRO == PRO_SPATIAL ? C::kJ : 3];
+        if constexpr (PRO == PRO_SPATIAL) {
+#pragma unroll
+          for (int k = 0; k < C::kJ; ++k) tab[k] = __ldg(p.pro_a + min((k * kBldWarps + bw) >> 1, V - 1) * K + tc);
+        } else {
+          tab[0] = __ldg(p.pro_c + tc), tab[1] = __ldg(p.pro_a + tc), tab[2] = __ldg(p.pro_b + tc);
+        }
         cp_wait<RS - 2>();
         bld_sync();
         if (q + RS - 1 < total_chunks) issue(q + RS - 1);
         cp_async_commit();
         const int os = q % OS;
-        if (q >= OS) mbar_wait(&op_free[os], (uint32_t)(((q / OS) - 1) & 1));
+        if (q >= OS) mbar_wait_relaxed(&op_free[os], (uint32_t)(((q / OS) - 1) & 1));
         const uint32_t raw = sRaw + (uint32_t)(q % RS) * C::kRawBytes + (uint32_t)lane * 4u;
         const uint32_t ob = opb + (uint32_t)os * kOpBytes;
 
@@ -396,9 +411,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         };
         if constexpr (PRO == PRO_SPATIAL) {
           // xm[(g,u), c] = x[g, (u+c) % V, c] * maskmul[u, c]
-          const int half = bw & 1;                                 // pairs k*12 + bw keep the parity of bw
-          const int c = kc * 64 + half * 32 + lane, cm = c % V;
-          const float* mrow = p.pro_a + c;
+          const int half = bw & 1;
+          const int c = tc, cm = c % V;
           const uint32_t rbh = raw + (uint32_t)(half * 128), obh = ob + (uint32_t)(half * kBlockBytes);
 #pragma unroll
           for (int k = 0; k < C::kJ; ++k) {
@@ -406,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
             if (u < V) {
               int sv = u + cm;
               if (sv >= V) sv -= V;
-              const float mm = __ldg(mrow + u * K);
+              const float mm = tab[k];
               const uint32_t rb = rbh + (uint32_t)sv * 256u;
               float s[G];
 #pragma unroll
@@ -421,9 +435,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
           const int T = p.T;
           const int t0 = p.groups < (1ll << 31) ? (int)((unsigned)g0 % (unsigned)T) : (int)(g0 % T);
           const bool interior = ng == G && t0 + lerp_lo >= 0 && t0 + G - 1 + lerp_lo + C::kWin < T && t0 + G <= T;
-          const int half = bw & 1;                                 // pairs k*12 + bw keep the parity of bw
-          const int c = kc * 64 + half * 32 + lane;
-          const float ypos = __ldg(p.pro_c + c), sa = __ldg(p.pro_a + c), sb = __ldg(p.pro_b + c);
+          const int half = bw & 1;
+          const int c = tc;
+          const float ypos = tab[0], sa = tab[1], sb = tab[2];
           const float fl = floorf(ypos);
           const int y1 = (int)fl, idx = y1 - lerp_lo;
           const float f = ypos - fl, a1 = sa * f, a0 = sa - a1;
@@ -479,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
     float s1[NACC], s2[NACC];
 #pragma unroll
     for (int a = 0; a < NACC; ++a) s1[a] = 0.f, s2[a] = 0.f;
-    const uint32_t stb = sSt + (uint32_t)(lane & 3) * 4u;
+    const uint32_t stb = sSt + (uint32_t)(((warp & 1) * 32 + lane) * 4);   // this lane's channel column of the staging tile
 
     for (int ti = 0; ti < my_tiles; ++ti) {
       const long long g0 = tile_of(ti) * G;
@@ -493,21 +507,27 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
       // front of their use, where every (joint, half) pair paid a full global-load latency.
       constexpr int kPF = EPI == EPI_ROT_FUSED ? C::kJ : 1;
       float scp[kPF], shp[kPF], rvp[kPF][G];
-      auto prefetch = [&](int nc) {
-        const int d = nc * 64 + (wv & 1) * 32 + lane;
+      auto prefetch_t = [&](int nc, auto full_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;          // full tile: one pointer per pair + immediate offsets
+        const int d = nc * 64 + (wv & 1) * 32 + lane;              // (25 separate 64-bit pointers spilled to local memory)
+        const float* rbase = res + row0 * N + d;
 #pragma unroll
         for (int k = 0; k < kPF; ++k) {
-          const int v = min((k * kEpiWarps + wv) >> 1, V - 1);
-          scp[k] = __ldg(p.epi_a + v * N + d);
-          shp[k] = __ldg(p.epi_b + v * N + d);
-          const float* rptr = res + row0 * N + d + v * N;
+          const int o = min((k * kEpiWarps + wv) >> 1, V - 1) * N + d;
+          scp[k] = __ldg(p.epi_a + o);
+          shp[k] = __ldg(p.epi_b + o);
+          const float* rptr = rbase + (o - d);
 #pragma unroll
-          for (int g = 0; g < G; ++g) rvp[k][g] = __ldg(rptr + min(g, ng - 1) * V * N);
+          for (int g = 0; g < G; ++g) rvp[k][g] = __ldg(rptr + (kFull ? g : min(g, ng - 1)) * V * N);
         }
+      };
+      auto prefetch = [&](int nc) {
+        if (ng == G) prefetch_t(nc, std::true_type{});
+        else prefetch_t(nc, std::false_type{});
       };
       if constexpr (EPI == EPI_ROT_FUSED) prefetch(0);
       if (warp < 8) {    // only the TMEM readers (who gate acc_free) wait for the accumulator, see spatial_bwd.cu
-        mbar_wait(&acc_full[buf], (uint32_t)((ti >> 1) & 1));
+        mbar_wait_relaxed(&acc_full[buf], (uint32_t)((ti >> 1) & 1));
         tc_fence_after();
       }
       if constexpr (EPI == EPI_LINEAR) {
@@ -517,6 +537,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         const int nrow = ng * V;
 #pragma unroll
         for (int st = 0; st < 2 * NCH; ++st) {
+          const int d = st * 32 + lc * 4;                          // requested before the drain and its barrier
+          const float4 bias = p.bias ? ldg4(p.bias + d) : make_float4(0.f, 0.f, 0.f, 0.f);
           if (warp < 8) {   // TMEM -> staging: lane quarter (warp & 3), 16-column half (warp >> 2)
             const int qd = warp & 3, hf = warp >> 2;
             const uint32_t row = (uint32_t)(qd * 32 + lane);
@@ -531,8 +553,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
             }
           }
           epi_sync();
-          const int d = st * 32 + lc * 4;
-          const float4 bias = p.bias ? ldg4(p.bias + d) : make_float4(0.f, 0.f, 0.f, 0.f);
           const uint32_t sb = sSt + (uint32_t)lrow * 128u + ((((uint32_t)lc) ^ ((uint32_t)lrow & 7u)) << 4);
           if (p.out_gs <= 1 && !p.accum) {
             float* optr = p.out + (row0 + lrow) * N + d;
@@ -569,22 +589,26 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
       // ROT_RAW keeps per-chunk statistics in registers (compile-time indices: full unroll); ROT_FUSED has no such
       // arrays and, for four chunks, stays rolled so that only one chunk's prefetch is live (measured: 246 -> 178 us
       // at N = 256; two chunks are faster unrolled, 204 vs 246 us)
-      constexpr int kNcUnroll = (EPI == EPI_ROT_FUSED && NCH > 2) ? 1 : NCH;
+      constexpr int kNcUnroll = (EPI == EPI_ROT_FUSED && NCH > 1) ? 1 : NCH;
+      int nch_rt = NCH;                                            // ROT_FUSED: opaque trip count, the loop must stay
+      if constexpr (EPI == EPI_ROT_FUSED) asm volatile("" : "+r"(nch_rt));   // rolled even for two chunks (spills)
 #pragma unroll kNcUnroll
-      for (int nc = 0; nc < NCH; ++nc) {
+      for (int nc = 0; nc < (EPI == EPI_ROT_FUSED ? nch_rt : NCH); ++nc) {
         if constexpr (EPI == EPI_ROT_FUSED)
           if (nc > 0) prefetch(nc);
+        // requested in front of the drain and its barrier, used after them
+        const float bias = p.bias ? __ldg(p.bias + nc * 64 + (wv & 1) * 32 + lane) : 0.f;
         if (warp < 8) {   // TMEM -> staging: lane quarter (warp & 3), column half (warp >> 2)
           const int qd = warp & 3, hf = warp >> 2;
           const uint32_t row = (uint32_t)(qd * 32 + lane);
-          const uint32_t rb = sSt + row * 256u;
+          const uint32_t rb = sSt + row * (uint32_t)C::kStPitch + (uint32_t)(hf * 128);
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * N + nc * 64 + hf * 32 + h2 * 16), v);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              sts128(rb + ((((uint32_t)(hf * 8 + h2 * 4 + i)) ^ (row & 15u)) << 4), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+              sts128(rb + (uint32_t)((h2 * 4 + i) * 16), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
           }
           if (nc == NCH - 1) {                                     // last read of this accumulator buffer
             tc_fence_before();
@@ -594,12 +618,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         epi_sync();
         {
           // z[(g,v), d] = y[(g, (v-d) % V), d] + bias: lane <-> channel d, the warp owns (joint v, half) pairs.
-          // Staging row r = g*V + u (256-byte pitch, 16-byte chunk XOR-ed with (r & 15)):
-          //   address = stb + r*256 + ((chunk ^ r) & 15) * 16,   chunk = half*8 + (lane >> 2)
+          // Staging row r = g*V + u: address = stb + r * kStPitch (per-pair base + compile-time group offset)
           const int half = wv & 1;                                 // pairs k*12 + warp keep the parity of the warp
           const int d = nc * 64 + half * 32 + lane, dm = d % V;
-          const float bias = p.bias ? __ldg(p.bias + d) : 0.f;
-          const uint32_t c4s = (uint32_t)(half * 8 + (lane >> 2)) << 4;
           float* obase = p.out + row0 * N + d;
           auto tile_pass = [&](auto full_tag) {
             constexpr bool kFull = decltype(full_tag)::value;
@@ -610,7 +631,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
                 int u = v - dm;
                 if (u < 0) u += V;
                 float* optr = obase + v * N;
-                const uint32_t sb = stb + (uint32_t)u * 256u, u16 = (uint32_t)u << 4;
+                const uint32_t sb = stb + (uint32_t)u * (uint32_t)C::kStPitch;
                 float sc = 0.f, sh = 0.f, rv[G];
                 if (EPI == EPI_ROT_FUSED) {
                   sc = scp[EPI == EPI_ROT_FUSED ? k : 0];
@@ -621,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
 #pragma unroll
                 for (int g = 0; g < G; ++g)
                   if (kFull || g < ng) {
-                    float z = lds32(sb + ((c4s ^ (u16 + (uint32_t)(g * V * 16))) & 0xF0u) + (uint32_t)(g * V * 256)) + bias;
+                    float z = lds32(sb + (uint32_t)(g * V * C::kStPitch)) + bias;
                     if (EPI == EPI_ROT_RAW) {
                       s1[nc * C::kJ + k] += z;
                       s2[nc * C::kJ + k] = fmaf(z, z, s2[nc * C::kJ + k]);

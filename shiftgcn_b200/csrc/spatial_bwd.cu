@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
       const size_t row0 = (size_t)g0 * V;
       for (int kc = 0; kc < KC; ++kc, ++q) {
         const int s = (int)(q & 1);
-        if (q >= 2) mbar_wait(&op_free[s], (uint32_t)(((q >> 1) - 1) & 1));
+        if (q >= 2) mbar_wait_relaxed(&op_free[s], (uint32_t)(((q >> 1) - 1) & 1));
         uint8_t* op = sOp + (size_t)s * kOpBytes;
 #pragma unroll
         for (int rd = 0; rd < C::kBldRounds; ++rd) {
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
       // issuer reuse the buffer, so the barrier can never run two phases ahead of a waiter (a warp that waited
       // without gating acc_free could miss a whole phase and spin forever).  Warps 8..12 are ordered by epi_sync.
       if (warp < 8) {
-        mbar_wait(&acc_full[buf], (uint32_t)((ti >> 1) & 1));
+        mbar_wait_relaxed(&acc_full[buf], (uint32_t)((ti >> 1) & 1));
         tc_fence_after();
       }
 #pragma unroll

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
       // loads is already in flight while the tensor core drains the stage.
       // TEMPORAL does the same with the register-staged B operand: its first batch of loads is issued, then the wait
       // and the cp.async copy of A (`stage_ready`).
-      if (MODE == WG_PLAIN && use > 0) mbar_wait(&bar_free[grp], (uint32_t)((use - 1) & 1));
+      if (MODE == WG_PLAIN && use > 0) mbar_wait_relaxed(&bar_free[grp], (uint32_t)((use - 1) & 1));
       bool a_pending = MODE == WG_TEMPORAL;
 
       auto issue_a = [&]() {
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
       };
       auto stage_ready = [&]() {                             // TEMPORAL: called in front of the first store of a tile
         if (a_pending) {
-          if (use > 0) mbar_wait(&bar_free[grp], (uint32_t)((use - 1) & 1));
+          if (use > 0) mbar_wait_relaxed(&bar_free[grp], (uint32_t)((use - 1) & 1));
           issue_a();
           a_pending = false;
         }
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
               for (int g = 0; g < G; ++g) val[b][sl][g] = __ldg(src + (kFull ? g : min(g, ng - 1)) * gstride + sv * CA);
             }
           }
-          if (blk0 == 0 && use > 0) mbar_wait(&bar_free[grp], (uint32_t)((use - 1) & 1));
+          if (blk0 == 0 && use > 0) mbar_wait_relaxed(&bar_free[grp], (uint32_t)((use - 1) & 1));
 #pragma unroll
           for (int b = 0; b < NB; ++b) {
             const uint32_t dst = sA32 + (blk0 + b) * (uint32_t)BLK + (((uint32_t)lane & 7u) << 2);
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
     // ================================================================ flush (warps 1..4): TMEM lane = A channel.
     // Transposed through shared memory so that the atomics of a warp hit 32 consecutive addresses.
     if (warp >= 1 && warp <= 4 && my_tiles > 0) {
-      mbar_wait(&bar_done, 0);          // every MMA has completed: the operand stages are free to be reused
+      mbar_wait_relaxed(&bar_done, 0);          // every MMA has completed: the operand stages are free to be reused
       tc_fence_after();
       const int q = warp & 3;                               // TMEM lane quarter this warp may read
       float* tr = (float*)smem + q * (32 * 33);
