@@ -75,6 +75,28 @@ int sgcn_shift_bwd_nchw_f64(const double* grad_out, const double* in, const doub
 int sgcn_input_stream(const float* joint, float* out, const int* parent, const float* scale, const float* shift,
                       long long N, int C, int T, int V, int M, int motion, int rows, void* stream);
 
+/* Sliding-window inference over one sequence (inference_pipeline.py:252-281 create_sliding_windows, :342-366
+ * run_ensemble_inference, :377-386 aggregate_per_frame).  seq [C, Ttot, V, M] stays on the device; window w is the
+ * frames start[w] .. start[w]+win-1, zero padded past Ttot; streams are derived from the PADDED window like
+ * sgcn_input_stream (same parent / motion / rows / scale / shift arguments).  out: [W, C, win, V, M] or rows
+ * [(W*M), win, V, C]. */
+int sgcn_window_stream(const float* seq, float* out, const int* start, const int* parent, const float* scale,
+                       const float* shift, long long W, int C, int Ttot, int win, int V, int M, int motion, int rows,
+                       void* stream);
+/* score[w] = softmax(logits[w, :])[cls] in fp64 (logits [W, num_class] fp32: the alpha-weighted ensemble sum);
+ * per_frame[f] = mean of score[w] over the windows with start[w] <= f < start[w] + real[w], 0 where none covers f
+ * (the reference divides by max(count, 1)).  score [W] and per_frame [total_frames] are fp64 device buffers.
+ * logits == NULL: score already holds the window scores, only the aggregation runs. */
+int sgcn_window_scores(const float* logits, const int* start, const int* real, double* score, double* per_frame, int W,
+                       int num_class, int cls, int total_frames, void* stream);
+
+/* Feeder augmentation on the device: feeders/tools.py:58-101 random_move for a batch [N, C, T, V, M] (C >= 2), in place.
+ * node: int[K+1] frame indices 0 = node[0] < ... < node[K] = T (the reference's `node`, move_time = K); vals: fp64
+ * [N, 4, K+1] = the angle (degrees), scale, x and y translation drawn at every node for every sample.  Between two nodes
+ * the parameters follow np.linspace exactly; the x / y channels of frame t become R(a_t) * s_t * (x, y) + (tx_t, ty_t). */
+int sgcn_random_move(float* data, const double* vals, const int* node, long long N, int C, int T, int V, int M, int K,
+                     void* stream);
+
 /* ---------------------------------------------------------------- first spatial unit (3 input channels) -- */
 /* l1.gcn1 = Shift_gcn(3, 64) (model/shift_gcn.py:178, 121-142) including its `down` branch (1x1 conv + BatchNorm2d,
  * :82-86).  z and the conv output are recomputed from x wherever needed; only h, g cross HBM at full size.

@@ -164,6 +164,51 @@ def main():
     rec["ntu/joint"], rec["ntu/bone"] = jn, bone
     rec["ntu/joint_motion"], rec["ntu/bone_motion"] = _motion(jn), _motion(bone)
     np.savez_compressed(os.path.join(OUT, "modalities.npz"), **rec)
+    # ---- 8. sliding windows and per-frame aggregation: the reference's own create_sliding_windows / aggregate_per_frame /
+    #         detect_fall_intervals (inference_pipeline.py:252-281, 377-424, executed from its source) on a short, an
+    #         exact and a ragged sequence
+    ref_windows, ref_aggregate, ref_detect = modalities.reference_window_functions()
+    rng = np.random.default_rng(11)
+    rec, det = {}, {}
+    for tag, T in (("short", 7), ("exact", 20), ("ragged", 23), ("one_over", 9)):
+        seq = rng.standard_normal((3, T, 33, 1)).astype(np.float32)
+        wins = ref_windows(seq, window_size=8, stride=4)
+        rec[f"{tag}/seq"] = seq
+        rec[f"{tag}/windows"] = np.stack([w[0] for w in wins])
+        rec[f"{tag}/meta"] = np.array([[w[1], w[2], w[3]] for w in wins], dtype=np.int64)
+        scores = rng.uniform(0, 1, len(wins))
+        results = [(float(s), w[1], w[2], w[3]) for s, w in zip(scores, wins)]
+        rec[f"{tag}/scores"] = scores
+        rec[f"{tag}/per_frame"] = ref_aggregate(results, T)
+        det[tag] = ref_detect(rec[f"{tag}/per_frame"], 0.5, 30.0)
+        # the four streams of the padded windows, from the reference's own derive_modalities
+        per_window = [ref_derive(w[0]) for w in wins]
+        for name in modalities.MODALITIES[1:]:
+            rec[f"{tag}/{name}"] = np.stack([d[name] for d in per_window])
+    np.savez_compressed(os.path.join(OUT, "windows.npz"), **rec)
+    with open(os.path.join(OUT, "windows_detections.json"), "w") as f:
+        json.dump(det, f, indent=1)
+    # ---- 9. feeder augmentation: the reference's own feeders/tools.py random_move (imported; it needs only numpy) on
+    #         seeded draws; the node values are recovered by replaying the same np.random calls with the same seed
+    import importlib.util
+    from . import feeder_tools
+    spec = importlib.util.spec_from_file_location("ref_feeder_tools", "/root/reference/feeders/tools.py")
+    ref_tools = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_tools)
+    rng = np.random.default_rng(13)
+    rec = {}
+    for tag, (T, V, M, move_time) in {"ntu": (20, 25, 2, [1]), "mp": (13, 33, 1, [1]), "two_seg": (17, 25, 2, [2])}.items():
+        x = rng.standard_normal((4, 3, T, V, M)).astype(np.float32)
+        outs, nodes, vals = [], None, []
+        for n in range(4):
+            np.random.seed(100 + n)
+            outs.append(ref_tools.random_move(x[n].copy(), move_time_candidate=move_time))
+            np.random.seed(100 + n)
+            nodes, v = feeder_tools.move_nodes(T, move_time[0])
+            vals.append(v)
+        rec[f"{tag}/x"], rec[f"{tag}/out"] = x, np.stack(outs)
+        rec[f"{tag}/node"], rec[f"{tag}/vals"] = nodes.astype(np.int32), np.stack(vals)
+    np.savez_compressed(os.path.join(OUT, "feeder.npz"), **rec)
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} files, {total / 1e6:.2f} MB -> {OUT}")
 

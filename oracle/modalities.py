@@ -68,6 +68,51 @@ def fall_scores(logits):
     return e[:, 1] / e.sum(axis=1)
 
 
+def sliding_windows(data, window_size=300, stride=150):
+    """inference_pipeline.py:252-281 -- (C, T, V, M) -> [(window, start, end, num_real)], short sequences and the last
+    ragged window zero padded; the loop stops after the first window that reaches the end of the sequence"""
+    C, T, V, M = data.shape
+    if T <= window_size:
+        padded = np.zeros((C, window_size, V, M), dtype=np.float32)
+        padded[:, :T] = data
+        return [(padded, 0, T, T)]
+    windows, start = [], 0
+    while start < T:
+        end = start + window_size
+        if end <= T:
+            windows.append((data[:, start:end].copy(), start, end, window_size))
+        else:
+            padded = np.zeros((C, window_size, V, M), dtype=np.float32)
+            padded[:, :T - start] = data[:, start:T]
+            windows.append((padded, start, T, T - start))
+        start += stride
+        if end >= T:
+            break
+    return windows
+
+
+def aggregate_per_frame(window_results, total_frames):
+    """inference_pipeline.py:377-386 -- per-frame mean of the window scores over the REAL frames of each window"""
+    score_sum = np.zeros(total_frames, dtype=np.float64)
+    score_count = np.zeros(total_frames, dtype=np.float64)
+    for fall_score, start, end, num_real in window_results:
+        score_sum[start:start + num_real] += fall_score
+        score_count[start:start + num_real] += 1.0
+    return score_sum / np.maximum(score_count, 1.0)
+
+
+# ------------------------------------------------------------------ the reference's own code (build container only)
+def reference_window_functions(root="/root/reference"):
+    """(create_sliding_windows, aggregate_per_frame, detect_fall_intervals) executed from the reference SOURCE with ast
+    (see reference_objects for why it cannot be imported); used by oracle/make_golden.py only"""
+    src = open(os.path.join(root, "inference_pipeline.py")).read()
+    want = ("create_sliding_windows", "aggregate_per_frame", "detect_fall_intervals", "_add_detection")
+    keep = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in want]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "inference_pipeline.py", "exec"), ns)
+    return ns["create_sliding_windows"], ns["aggregate_per_frame"], ns["detect_fall_intervals"]
+
+
 # ------------------------------------------------------------------ the reference's own code (build container only)
 def reference_objects(root="/root/reference"):
     """(derive_modalities function, BONE_PAIRS, NTU `paris` dict) taken from the reference SOURCE FILES with ast --

@@ -80,6 +80,9 @@ SIGNATURES = {
     "sgcn_shift_bwd_nchw_f32": [_vp] * 9 + [_ll, _i, _i, _i, _i, _vp],
     "sgcn_shift_bwd_nchw_f64": [_vp] * 9 + [_ll, _i, _i, _i, _i, _vp],
     "sgcn_input_stream": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp],
+    "sgcn_window_stream": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "sgcn_window_scores": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "sgcn_random_move": [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp],
     "sgcn_side_fold": [ctypes.POINTER(SgcnSideFold), _vp],
     "sgcn_side_bwd": [ctypes.POINTER(SgcnSideBwd), _vp],
     "sgcn_stem_fwd": [ctypes.POINTER(SgcnStem), _i, _vp],

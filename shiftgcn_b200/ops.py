@@ -472,6 +472,75 @@ def input_stream(joint, parent=None, motion=False, rows=False, scale=None, shift
     return out
 
 
+def window_stream(seq, start, window, parent=None, motion=False, rows=False, scale=None, shift=None):
+    """streams of the sliding windows of ONE sequence (C, Ttot, V, M) on the device (sgcn_window_stream): window w = frames
+    start[w] .. start[w]+window-1, zero padded past the end, modality derived from the padded window like the reference
+    (inference_pipeline.py:252-309).  start: int32 CUDA tensor [W].  Returns (W, C, window, V, M), or with rows=True the
+    row tensor (W*M, window, V, C)."""
+    lib = _lib.load()
+    if seq.dim() != 4:
+        raise RuntimeError("window_stream expects a sequence of shape (C, T, V, M)")
+    C, Ttot, V, M = seq.shape
+    if start.dtype != torch.int32 or start.dim() != 1:
+        raise RuntimeError("start must be a 1-D int32 tensor of window start frames")
+    if parent is not None and (parent.numel() != V or parent.dtype != torch.int32):
+        raise RuntimeError("parent must be an int32 tensor with one entry per joint")
+    if (scale is None) != (shift is None) or (scale is not None and (not rows or scale.numel() != M * V * C)):
+        raise RuntimeError("scale / shift come together, need rows=True and M*V*C entries each")
+    W = start.numel()
+    out = torch.empty((W * M, window, V, C) if rows else (W, C, window, V, M), device=seq.device, dtype=torch.float32)
+    if out.numel() == 0:
+        return out
+    _launch("window_stream", 1, _nbytes(seq, out), lib.sgcn_window_stream, _p(seq, name="seq"), _p(out),
+            _p(start, torch.int32, "start"), _p(parent, torch.int32, "parent"), _p(scale), _p(shift), W, C, Ttot, window, V,
+            M, 1 if motion else 0, 1 if rows else 0, _STREAM)
+    return out
+
+
+def window_scores(logits, start, real, total_frames, cls=1):
+    """(score [W] f64, per_frame [total_frames] f64): softmax(logits)[cls] per window and its per-frame average over the
+    windows covering each frame with real data (sgcn_window_scores; inference_pipeline.py:358-360, 377-386)."""
+    lib = _lib.load()
+    W, K = logits.shape
+    dev = logits.device
+    score = torch.empty(W, device=dev, dtype=torch.float64)
+    per_frame = torch.empty(total_frames, device=dev, dtype=torch.float64)
+    if W == 0 and total_frames == 0:
+        return score, per_frame
+    _launch("window_scores", 2, _nbytes(logits, per_frame), lib.sgcn_window_scores, _p(logits, name="logits"),
+            _p(start, torch.int32, "start"), _p(real, torch.int32, "real"), _d(score), _d(per_frame), W, K, cls, total_frames,
+            _STREAM)
+    return score, per_frame
+
+
+def random_move_(data, vals, node):
+    """in-place feeders/tools.py:58-101 random_move of a CUDA batch (N, C, T, V, M) (sgcn_random_move).
+    vals: fp64 CUDA (N, 4, K+1) node values (angle in degrees, scale, tx, ty); node: int32 CUDA [K+1] frame indices."""
+    lib = _lib.load()
+    if data.dim() != 5:
+        raise RuntimeError("random_move_ expects a batch of shape (N, C, T, V, M)")
+    N, C, T, V, M = data.shape
+    K = node.numel() - 1
+    if vals.shape != (N, 4, K + 1):
+        raise RuntimeError(f"vals must have shape {(N, 4, K + 1)}, got {tuple(vals.shape)}")
+    if N == 0:
+        return data
+    _launch("random_move", 1, _nbytes(data), lib.sgcn_random_move, _p(data, name="data"), _d(vals, "vals"),
+            _p(node, torch.int32, "node"), N, C, T, V, M, K, _STREAM)
+    return data
+
+
+def frame_aggregate(score, start, real, total_frames):
+    """per-frame mean of given window scores (fp64 [W]) -- the aggregation half of sgcn_window_scores"""
+    lib = _lib.load()
+    per_frame = torch.empty(total_frames, device=score.device, dtype=torch.float64)
+    if total_frames == 0:
+        return per_frame
+    _launch("window_scores", 1, _nbytes(score, per_frame), lib.sgcn_window_scores, None, _p(start, torch.int32, "start"),
+            _p(real, torch.int32, "real"), _d(score), _d(per_frame), score.numel(), 2, 1, total_frames, _STREAM)
+    return per_frame
+
+
 # ------------------------------------------------------------------------------------------------ conv + BN side branches
 def side_fold(Wd, bd, gamma, beta, running_mean, running_var, nbt, rows, eps, momentum, training, sx_sums=None, XX=None,
               counter=None):
