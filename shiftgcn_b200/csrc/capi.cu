@@ -105,3 +105,57 @@ extern "C" int sgcn_device_check(void) {
   }
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ TMA tensor maps
+#include <cudaTypedefs.h>
+
+#include "tensormap.h"
+
+namespace sgcn {
+
+static PFN_cuTensorMapEncodeTiled encode_fn() {
+  static std::atomic<void*> cached{nullptr};
+  void* fn = cached.load(std::memory_order_acquire);
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    cached.store(fn, std::memory_order_release);
+  }
+  return (PFN_cuTensorMapEncodeTiled)fn;
+}
+
+static int encode(CUtensorMap* m, int rank, const float* base, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box, CUtensorMapSwizzle sw) {
+  PFN_cuTensorMapEncodeTiled fn = encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled is not available from this driver");
+  if (((uintptr_t)base & 15u) != 0) return set_error("TMA source tensors must be 16-byte aligned");
+  const cuuint32_t ones[3] = {1, 1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, dims, strides, box, ones,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[96];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return set_error(buf);
+  }
+  return 0;
+}
+
+int make_rows_map(CUtensorMap* m, const float* base, long long rows, int pitch, int box_ch, int box_rows) {
+  const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_ch, (cuuint32_t)box_rows};
+  return encode(m, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+int make_groups_map_sw128(CUtensorMap* m, const float* base, long long groups, long long gs, int V, int pitch,
+                          int box_groups) {
+  const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)V, (cuuint64_t)groups};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)(gs > 0 ? gs : 1) * V * pitch * 4};
+  const cuuint32_t box[3] = {32, (cuuint32_t)V, (cuuint32_t)box_groups};
+  return encode(m, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace sgcn

@@ -6,8 +6,13 @@
 // per SM, persistent) processes tiles of G whole (n,t) groups (G*V <= 128 rows), so the joint shifts of the spatial
 // unit are permutations inside the tile.  Seven warpgroups, four roles (register budgets set with setmaxnreg):
 //
-//   builders   12 warps  stream raw [rows x 64 channel] chunks of the input into shared memory with 16-byte
-//                        cp.async (two chunks in flight, no registers involved), then run the prologue as a
+//   row loader 1 lane    TMA (cp.async.bulk.tensor, one tensor map per input): the raw [rows x 64 channel] box of every
+//                        chunk goes into a ring of dense shared-memory stages, several chunks ahead, with mbarrier
+//                        complete_tx; halo rows in front of the tensor and rows past a partial last tile arrive as
+//                        zeros.  PRO_PLAIN: the {32 channels, V, G} boxes land in the SWIZZLE_128B operand stage
+//                        directly and no thread touches the data before the tensor core does.
+//   builders   12 warps  wait for a raw stage (each warp on its own: no barrier between the builder warps), then run
+//                        the prologue as a
 //                        shared -> shared pass with lane <-> channel: whatever row a lane reads (joint shift:
 //                        row (u+c) % V, temporal shift: frame t + floor(ypos_c)), the bank is the channel, so the
 //                        gathers are conflict free; results go TF32-rounded into the K-major SWIZZLE_128B operand
@@ -31,6 +36,8 @@
 #include "capi_internal.h"
 #include "common.cuh"
 #include "rowgemm.h"
+#include "tensormap.h"
+#include <string.h>
 #include <type_traits>
 
 namespace sgcn {
@@ -41,7 +48,7 @@ enum { EPI_ROT_RAW = 0, EPI_ROT_FUSED = 1, EPI_LINEAR = 2 };
 
 constexpr int kEpiWarps = 12, kBldWarps = 12;
 constexpr int kEpiThreads = kEpiWarps * 32, kBldThreads = kBldWarps * 32;
-constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1;   // warps 12..15: MMA, W loader, two spares
+constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1, kRowWarp = kEpiWarps + 2;   // warps 12..15: MMA, W loader, row loader, spare
 constexpr int kBld0 = kEpiWarps + 4;                             // first builder warp
 constexpr int kThreads = (kEpiWarps + 4 + kBldWarps) * 32;       // 896
 constexpr int kChunkBytes = 128 * 64 * 4;                        // one [128 x 64] fp32 operand chunk / staging tile
@@ -122,7 +129,9 @@ struct Cfg {
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int PRO, int EPI, int V, int K, int N, bool P3>
-__global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGemm p, const int rev) {
+__global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGemm p, const int rev,
+                                                                 const __grid_constant__ CUtensorMap tm0,
+                                                                 const __grid_constant__ CUtensorMap tm1) {
   using C = Cfg<PRO, EPI, V, K, N, P3>;
   constexpr int kOpBytes = C::kOpBytes;
   constexpr int G = C::G, KC = C::KC, NCH = C::NCH, OS = C::kOpStages;
@@ -133,15 +142,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
   const uint32_t sOp = sW + C::kWBytes;
   const uint32_t sSt = sOp + OS * kOpBytes;
   const uint32_t sRaw = sSt + C::kStBytes;
-  __shared__ uint64_t op_full[4], op_free[4], acc_full[2], acc_free[2], w_full[2], w_free[2];
+  __shared__ uint64_t op_full[4], op_free[4], acc_full[2], acc_free[2], w_full[2], w_free[2], raw_full[4], raw_free[4];
   __shared__ uint32_t tmem_base_s;
   __shared__ int lerp_hist[16], lerp_lo_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr bool kTmaOp = PRO == PRO_PLAIN && !P3;                 // operand stages filled by TMA alone
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&op_full[i], kBldThreads);
+      mbar_init(&op_full[i], kTmaOp ? 1 : kBldThreads);
       mbar_init(&op_free[i], 1);
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_free[i], kBldWarps);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -151,7 +163,25 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
     }
     fence_mbar_init();
   }
-  if (tid < 16) lerp_hist[tid] = 0;
+  if constexpr (PRO == PRO_LERP) {
+    // window of floor(ypos) values the raw tile covers: the kWin consecutive values holding most channels
+    if (tid < 16) lerp_hist[tid] = 0;
+    __syncthreads();
+    for (int c = tid; c < K; c += kThreads) {
+      const int fl = (int)floorf(__ldg(p.pro_c + c));
+      if (fl >= -8 && fl < 8) atomicAdd(&lerp_hist[fl + 8], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int best = 0, bestn = -1;
+      for (int lo = 0; lo + C::kWin <= 16; ++lo) {
+        int n = 0;
+        for (int j = 0; j < C::kWin; ++j) n += lerp_hist[lo + j];
+        if (n > bestn) bestn = n, best = lo;
+      }
+      lerp_lo_s = best - 8;
+    }
+  }
   constexpr uint32_t tmem_cols = 2 * N <= 128 ? 128u : (2 * N <= 256 ? 256u : 512u);
   if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, tmem_cols);
   if (C::kWRes) {
@@ -242,6 +272,37 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         mbar_expect_tx(&w_full[s], C::kWStage);
         bulk_load(sW + (uint32_t)s * (uint32_t)C::kWStage, (const uint8_t*)p.wimg + src, C::kWStage, &w_full[s]);
       }
+    } else if (warp == kRowWarp && lane == 0 && (PRO != PRO_PLAIN || kTmaOp)) {
+      // ================================================================================ row loader (TMA tensor maps)
+      tma_prefetch_map(&tm0);
+      if constexpr (PRO == PRO_PLAIN) {
+        tma_prefetch_map(&tm1);
+        // {32 channels, V joints, G groups} boxes = whole 32-channel operand blocks in the SWIZZLE_128B layout.  The K
+        // channels may come from two row tensors side by side (p.k0 from in0, the rest from in1: the input-gradient GEMM
+        // of a conv + BN side branch contracts [g | x] in one pass), each with its own frame stride (inside its map).
+        const int k0 = p.k0 > 0 ? p.k0 : K;
+        for (int q = 0; q < total_chunks; ++q) {
+          const int s = q % OS, ti = q / KC, kc = q - ti * KC;
+          if (q >= OS) mbar_wait(&op_free[s], (uint32_t)(((q / OS) - 1) & 1));
+          const int g0 = (int)(tile_of(ti) * G);
+          const bool second = kc * 64 >= k0;
+          const CUtensorMap* map = second ? &tm1 : &tm0;
+          const int ch = second ? kc * 64 - k0 : kc * 64;
+          const uint32_t dst = sOp + (uint32_t)s * kOpBytes, bar = smem_u32(&op_full[s]);
+          mbar_expect_tx(&op_full[s], 2u * (uint32_t)(G * V * 128));
+          tma_load_3d(dst, map, ch, 0, g0, bar);
+          tma_load_3d(dst + kBlockBytes, map, ch + 32, 0, g0, bar);
+        }
+      } else {
+        const int lerp_lo = PRO == PRO_LERP ? lerp_lo_s : 0;
+        for (int q = 0; q < total_chunks; ++q) {
+          const int s = q % RS, ti = q / KC, kc = q - ti * KC;
+          if (q >= RS) mbar_wait(&raw_free[s], (uint32_t)(((q / RS) - 1) & 1));
+          const long long gfirst = tile_of(ti) * G + lerp_lo;      // first group of the raw tile (may be < 0: zeros)
+          mbar_expect_tx(&raw_full[s], (uint32_t)C::kRawBytes);
+          tma_load_2d(sRaw + (uint32_t)s * C::kRawBytes, &tm0, kc * 64, (int)(gfirst * V), smem_u32(&raw_full[s]));
+        }
+      }
     }
     __syncwarp();
   } else if (warp >= kBld0) {
@@ -252,8 +313,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
     const int prow = bt >> 4, pc4 = bt & 15;                       // this thread's 16-byte piece of rows prow + 24*i
     constexpr int kPieces = (C::kRawRows + 23) / 24;               // copies per thread and chunk (PLAIN: tile rows)
 
-    if constexpr (PRO == PRO_PLAIN) {
-      // cp.async straight into the swizzled operand stage (the tensor core reads the fp32 bit patterns as TF32)
+    if constexpr (kTmaOp) {
+      // nothing to build: the row loader's TMA boxes ARE the operand blocks
+    } else if constexpr (PRO == PRO_PLAIN) {
+      // fp32-accurate mode: cp.async straight into the swizzled operand stage, then every thread splits its own pieces
       const uint32_t dst0 = (uint32_t)(pc4 >> 3) * kBlockBytes + (uint32_t)prow * 128u + ((((uint32_t)pc4 ^ (uint32_t)prow) & 7u) << 4);
       // The K channels may come from two row tensors side by side (p.k0 from in0, the rest from in1: the input-gradient
       // GEMM of a conv + BN side branch contracts [g | x] in one pass), each with its own frame stride (1x1 conv, stride 2).
@@ -317,58 +380,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         mbar_arrive(&op_full[q % OS]);
       }
     } else {
-      // ---- raw chunk copies (16-byte pieces, dense rows of 64 floats)
-      int lerp_lo = 0;
-      if constexpr (PRO == PRO_LERP) {
-        // window of floor(ypos) values the raw tile covers: the kWin consecutive values holding most channels
-        for (int c = bt; c < K; c += kBldThreads) {
-          const int fl = (int)floorf(__ldg(p.pro_c + c));
-          if (fl >= -8 && fl < 8) atomicAdd(&lerp_hist[fl + 8], 1);
-        }
-        bld_sync();
-        if (bt == 0) {
-          int best = 0, bestn = -1;
-          for (int lo = 0; lo + C::kWin <= 16; ++lo) {
-            int n = 0;
-            for (int j = 0; j < C::kWin; ++j) n += lerp_hist[lo + j];
-            if (n > bestn) bestn = n, best = lo;
-          }
-          lerp_lo_s = best - 8;
-        }
-        bld_sync();
-        lerp_lo = lerp_lo_s;
-      }
-      auto issue = [&](int q) {
-        const int ti = q / KC, kc = q - ti * KC;
-        const long long g0 = tile_of(ti) * G;
-        const uint32_t dst = sRaw + (uint32_t)(q % RS) * C::kRawBytes + (uint32_t)prow * 256u + (uint32_t)pc4 * 16u;
-        const long long gfirst = g0 + lerp_lo;                     // first group of the raw tile
-        if (PRO == PRO_SPATIAL || (gfirst >= 0 && gfirst + G + C::kWin <= p.groups)) {
-          const int nrow = PRO == PRO_SPATIAL ? (int)((p.groups - g0) < G ? (p.groups - g0) : G) * V : C::kRawRows;
-          const float* src = p.in0 + ((size_t)gfirst * V + prow) * K + kc * 64 + pc4 * 4;
-#pragma unroll
-          for (int i = 0; i < kPieces; ++i)
-            if (prow + 24 * i < nrow) cp16(dst + (uint32_t)i * 6144u, src + (size_t)i * 24 * K);
-        } else {                                                   // first / last tiles of the tensor: clamp the groups
-#pragma unroll 1
-          for (int i = 0; i < kPieces; ++i) {
-            const int row = prow + 24 * i;
-            if (row < C::kRawRows) {
-              const int gr = row / V;
-              long long gi = gfirst + gr;
-              gi = gi < 0 ? 0 : (gi >= p.groups ? p.groups - 1 : gi);
-              cp16(dst + (uint32_t)i * 6144u, p.in0 + ((size_t)gi * V + (row - gr * V)) * K + kc * 64 + pc4 * 4);
-            }
-          }
-        }
-      };
+      // ---- raw chunks arrive by TMA (row loader); every builder warp waits and releases on its own
+      const int lerp_lo = PRO == PRO_LERP ? lerp_lo_s : 0;
       const uint32_t opb = sOp + (uint32_t)(lane & 3) * 4u;
-      // RS - 1 raw chunks in flight.  ONE barrier per chunk: it says that every thread's pieces of chunk q have landed
-      // and that every thread is done with chunk q - 1, whose raw stage is refilled right away with chunk q + RS - 1.
-      for (int j = 0; j < RS - 1; ++j) {
-        if (j < total_chunks) issue(j);
-        cp_async_commit();
-      }
       for (int q = 0; q < total_chunks; ++q) {
         const int ti = q / KC, kc = q - ti * KC;
         const long long g0 = tile_of(ti) * G;
@@ -384,10 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         } else {
           tab[0] = __ldg(p.pro_c + tc), tab[1] = __ldg(p.pro_a + tc), tab[2] = __ldg(p.pro_b + tc);
         }
-        cp_wait<RS - 2>();
-        bld_sync();
-        if (q + RS - 1 < total_chunks) issue(q + RS - 1);
-        cp_async_commit();
+        mbar_wait_relaxed(&raw_full[q % RS], (uint32_t)((q / RS) & 1));
         const int os = q % OS;
         if (q >= OS) mbar_wait_relaxed(&op_free[os], (uint32_t)(((q / OS) - 1) & 1));
         const uint32_t raw = sRaw + (uint32_t)(q % RS) * C::kRawBytes + (uint32_t)lane * 4u;
@@ -481,6 +492,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         }
         fence_proxy_async();
         mbar_arrive(&op_full[os]);
+        __syncwarp();                                              // every lane of this warp is done with the raw stage
+        if (lane == 0) mbar_arrive(&raw_free[q % RS]);
       }
     }
   } else {
@@ -695,7 +708,22 @@ static int launch_p(const SgcnRowGemm& p, cudaStream_t s) {
   if (ntiles == 0) return 0;
   long long grid = tile_ctas();
   if (grid > ntiles) grid = ntiles;
-  kern<<<(unsigned)grid, kThreads, C::kSmem, s>>>(p, next_direction());
+  // tensor maps of the activation inputs (tensormap.h): raw [rows x 64] boxes, or whole operand blocks for PRO_PLAIN
+  alignas(64) CUtensorMap tm0, tm1;
+  memset(&tm0, 0, sizeof(tm0));
+  if constexpr (PRO != PRO_PLAIN) {
+    if (int rc = make_rows_map(&tm0, p.in0, p.groups * V, K, 64, C::kRawRows)) return rc;
+    tm1 = tm0;
+  } else if constexpr (!P3) {
+    const int k0 = p.k0 > 0 ? p.k0 : K;
+    if (int rc = make_groups_map_sw128(&tm0, p.in0, p.groups, p.in0_gs, V, k0, C::G)) return rc;
+    tm1 = tm0;
+    if (k0 < K)
+      if (int rc = make_groups_map_sw128(&tm1, p.in1, p.groups, p.in1_gs, V, K - k0, C::G)) return rc;
+  } else {
+    tm1 = tm0;
+  }
+  kern<<<(unsigned)grid, kThreads, C::kSmem, s>>>(p, next_direction(), tm0, tm1);
   return check_launch("fused_gemm_kernel");
 }
 

@@ -68,7 +68,14 @@ struct Cfg {
   static constexpr int kSlots = V * 16;                            // (joint, 4-channel group) slots of a 64-wide chunk
   static constexpr int kEpiRounds = (kSlots + kEpiThreads - 1) / kEpiThreads;
   static constexpr int kBldRounds = (kSlots + kBldThreads - 1) / kBldThreads;
-  static constexpr size_t kSmem = 1024 + kWBytes + 2 * kOpBytes + kChunkBytes + 64;
+  // operand stages: as many as fit (at most 4), so that the register-staged builder loads run several chunks ahead of
+  // the tensor core and the epilogue
+#ifndef SGCN_SB_MAX_STAGES
+#define SGCN_SB_MAX_STAGES 2      // measured: 3-4 stages are SLOWER (269 vs 250 us at C=64, 382 vs 268 at C=128) -- the builders' loads then delay the epilogue's, which are on the critical path
+#endif
+  static constexpr int kFit = (232448 - 512 - 1024 - 64 - kWBytes - kChunkBytes) / kOpBytes;
+  static constexpr int kOpStages = kFit < 2 ? 2 : (kFit > SGCN_SB_MAX_STAGES ? SGCN_SB_MAX_STAGES : kFit);
+  static constexpr size_t kSmem = 1024 + kWBytes + kOpStages * kOpBytes + kChunkBytes + 64;
   static_assert(kSmem <= 232448 - 512, "shared memory budget");
 };
 
@@ -76,20 +83,22 @@ template <int V, int K, int N, bool P3>
 __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowGemm p, const int rev) {
   using C = Cfg<V, K, N, P3>;
   constexpr int kOpBytes = C::kOpBytes;
-  constexpr int G = C::G, KC = C::KC, NCH = C::NCH;
+  constexpr int G = C::G, KC = C::KC, NCH = C::NCH, OS = C::kOpStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
-  uint8_t* sOp = sW + C::kWBytes;                                  // 2 operand chunks
-  uint8_t* sSt = sOp + 2 * kOpBytes;                               // epilogue staging
-  __shared__ uint64_t op_full[2], op_free[2], acc_full[2], acc_free[2], w_full, w_free;
+  uint8_t* sOp = sW + C::kWBytes;                                  // OS operand chunks
+  uint8_t* sSt = sOp + OS * kOpBytes;                              // epilogue staging
+  __shared__ uint64_t op_full[4], op_free[4], acc_full[2], acc_free[2], w_full, w_free;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&op_full[i], kBldThreads);
       mbar_init(&op_free[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_free[i], 8 * 32);
     }
@@ -135,8 +144,8 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * N);
         for (int kc = 0; kc < KC; ++kc, ++q) {
-          const int s = (int)(q & 1);
-          mbar_wait(&op_full[s], (uint32_t)((q >> 1) & 1));
+          const int s = (int)(q % OS);
+          mbar_wait(&op_full[s], (uint32_t)((q / OS) & 1));
           tc_fence_after();
           const uint32_t a0 = smem_u32(sOp) + (uint32_t)s * kOpBytes;
 #pragma unroll
@@ -185,8 +194,8 @@ __global__ void __launch_bounds__(kThreads, 1) spatial_bwd_kernel(const SgcnRowG
       const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
       const size_t row0 = (size_t)g0 * V;
       for (int kc = 0; kc < KC; ++kc, ++q) {
-        const int s = (int)(q & 1);
-        if (q >= 2) mbar_wait_relaxed(&op_free[s], (uint32_t)(((q >> 1) - 1) & 1));
+        const int s = (int)(q % OS);
+        if (q >= OS) mbar_wait_relaxed(&op_free[s], (uint32_t)(((q / OS) - 1) & 1));
         uint8_t* op = sOp + (size_t)s * kOpBytes;
 #pragma unroll
         for (int rd = 0; rd < C::kBldRounds; ++rd) {
