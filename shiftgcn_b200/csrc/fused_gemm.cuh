@@ -136,7 +136,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
   constexpr int kOpBytes = C::kOpBytes;
   constexpr int G = C::G, KC = C::KC, NCH = C::NCH, OS = C::kOpStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // opaque to the compiler: otherwise the shared-window base (S2R CgaCtaId + four integer ops) and the lane-derived
+  // offsets are re-derived in front of every group of shared-memory accesses of the builder / epilogue loops
+  asm volatile("" : "+r"(smem0));
   constexpr int RS = C::kRawStages;
   const uint32_t sW = smem0;
   const uint32_t sOp = sW + C::kWBytes;
@@ -382,7 +385,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
     } else {
       // ---- raw chunks arrive by TMA (row loader); every builder warp waits and releases on its own
       const int lerp_lo = PRO == PRO_LERP ? lerp_lo_s : 0;
-      const uint32_t opb = sOp + (uint32_t)(lane & 3) * 4u;
+      uint32_t opb = sOp + (uint32_t)(lane & 3) * 4u, rawb = sRaw + (uint32_t)lane * 4u, lqs = lq << 4;
+      asm volatile("" : "+r"(opb), "+r"(rawb), "+r"(lqs));
       for (int q = 0; q < total_chunks; ++q) {
         const int ti = q / KC, kc = q - ti * KC;
         const long long g0 = tile_of(ti) * G;
@@ -401,14 +405,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         mbar_wait_relaxed(&raw_full[q % RS], (uint32_t)((q / RS) & 1));
         const int os = q % OS;
         if (q >= OS) mbar_wait_relaxed(&op_free[os], (uint32_t)(((q / OS) - 1) & 1));
-        const uint32_t raw = sRaw + (uint32_t)(q % RS) * C::kRawBytes + (uint32_t)lane * 4u;
+        const uint32_t raw = rawb + (uint32_t)(q % RS) * C::kRawBytes;
         const uint32_t ob = opb + (uint32_t)os * kOpBytes;
 
         // Operand row r = g*V + v (128-byte pitch, 16-byte chunk XOR-ed with (r & 7)), 32-channel half, channel lane:
         //   address = ob + half*16K + r*128 + (((lane >> 2) ^ r) & 7) * 16 + (lane & 3) * 4
         // with everything but the swizzle term folded into a per-pair base and a compile-time offset.  Rows of groups
         // beyond a partial last tile are written too (their operand rows and outputs are never used).
-        const uint32_t lqs = lq << 4;
         auto put = [&](uint32_t base, uint32_t v16, int g, float val) {
           const uint32_t addr = base + ((lqs ^ (v16 + (uint32_t)(g * V * 16))) & 0x70u) + (uint32_t)(g * V * 128);
           if constexpr (P3) {
@@ -506,7 +509,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
     float s1[NACC], s2[NACC];
 #pragma unroll
     for (int a = 0; a < NACC; ++a) s1[a] = 0.f, s2[a] = 0.f;
-    const uint32_t stb = sSt + (uint32_t)(((warp & 1) * 32 + lane) * 4);   // this lane's channel column of the staging tile
+    uint32_t stb = sSt + (uint32_t)(((warp & 1) * 32 + lane) * 4);   // this lane's channel column of the staging tile
+    asm volatile("" : "+r"(stb));
 
     for (int ti = 0; ti < my_tiles; ++ti) {
       const long long g0 = tile_of(ti) * G;
