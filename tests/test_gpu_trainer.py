@@ -95,9 +95,12 @@ def test_graph_replay_equals_eager_steps(cuda_device):
     assert rel_l2(first[1][~pos], first[0][~pos]) < 2e-2
     assert rel_l2(dg[~pos], de[~pos]) < 0.15
     # shift positions move by +-lr*0.01-sized steps whose SIGN comes from a reduced sum: identical except where that sum
-    # is at the noise level
-    same = ((de[pos] - dg[pos]).abs() < 1e-7).float().mean().item()
-    assert same > 0.8, same          # measured 0.88-0.97 across builds: the order of the fp64 atomics moves with kernel timing
+    # is at the noise level.  Compared after the first step (same parameters on both sides); later steps inherit the
+    # divergence of the trajectories (measured 0.75-0.97 after four steps, depending on the order of the fp64 atomics)
+    same = ((first[0][pos] - first[1][pos]).abs() < 1e-7).float().mean().item()
+    assert same > 0.85, same
+    same_end = ((de[pos] - dg[pos]).abs() < 1e-7).float().mean().item()
+    assert same_end > 0.5, same_end
     for (k, a), (_, b) in zip(m_eager.named_buffers(), m_graph.named_buffers()):
         if a.dtype.is_floating_point:
             assert rel_l2(b, a) < 2e-2, k
