@@ -90,6 +90,18 @@ int sgcn_window_stream(const float* seq, float* out, const int* start, const int
 int sgcn_window_scores(const float* logits, const int* start, const int* real, double* score, double* per_frame, int W,
                        int num_class, int cls, int total_frames, void* stream);
 
+/* Model head (model/shift_gcn.py:212-216: mean over (T, V) and the M persons, then fc).  pool_sums [N*M, C] fp64 holds
+ * the per-(sample, channel) SUMS over the rows of the last unit's output -- sgcn_tshift_fwd (mode 1) accumulates them when
+ * SgcnTShift::stats is set, and may then skip storing its output (out == NULL, inference).  sgcn_head_fwd:
+ * pooled[n, c] = inv_count * sum_m pool_sums[(n, m), c]  (inv_count = 1 / (T*V*M)),  logits = pooled W^T + b  (W [K, C]);
+ * pool_sums is handed back zeroed.  sgcn_head_bwd: dW = dlogits^T pooled, db = column sums of dlogits,
+ * gpool[(n, m), c] = scale * sum_k dlogits[n, k] W[k, c]  -- the gradient of every row of the last unit's output
+ * (scale = inv_count), spread over the rows by sgcn_bcast_rows. */
+int sgcn_head_fwd(double* pool_sums, const float* W, const float* b, float* pooled, float* logits, int N, int M, int C,
+                  int K, double inv_count, void* stream);
+int sgcn_head_bwd(const float* dlogits, const float* pooled, const float* W, float* dW, float* db, float* gpool, int N,
+                  int M, int C, int K, float scale, void* stream);
+
 /* Feeder augmentation on the device: feeders/tools.py:58-101 random_move for a batch [N, C, T, V, M] (C >= 2), in place.
  * node: int[K+1] frame indices 0 = node[0] < ... < node[K] = T (the reference's `node`, move_time = K); vals: fp64
  * [N, 4, K+1] = the angle (degrees), scale, x and y translation drawn at every node for every sample.  Between two nodes

@@ -173,8 +173,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) bn_res_
 
 // ------------------------------------------------------------------------------------------------ temporal shift, forward
 // s(to) = g * Q(to*stride + y1) + f * Q(to*stride + y1 + 1), Q zero padded           (K1 with xpos = 0)
-// MODE 0: stats[c] += {sum s, sum s^2};  MODE 1: out = [relu](s*sc + sh + res)
-template <int MODE, bool S1, int PITCH>
+// MODE 0: stats[c] += {sum s, sum s^2};  MODE 1: out = [relu](s*sc + sh + res), and with a stats pointer the global
+// pooling of the model head rides along: stats[n*C + c] += sum over (t, v) of out (model/shift_gcn.py:212-214); out may
+// then be NULL (inference: the last unit's output is only ever pooled)
+template <int MODE, bool S1, int PITCH, bool POOL = false>
 __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_fwd_kernel(const SgcnTShift p, int tper, int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32 * 2];
   const Col k = col_of(p.C, nchunks, rev);
@@ -216,12 +218,21 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
             float y = fmaf(s, sc, sh);
             if (p.res) y += rv[MODE == 1 ? u : 0];
             if (p.relu) y = fmaxf(y, 0.f);
-            p.out[ob + (size_t)(to + u) * pitch] = y;
+            if constexpr (POOL) {                                  // head of the model: pooled sums, output optional
+              if (p.out) p.out[ob + (size_t)(to + u) * pitch] = y;
+              acc[0] += y;
+            } else {
+              p.out[ob + (size_t)(to + u) * pitch] = y;
+            }
           }
         }
     }
   }
   if (MODE == 0) block_reduce_channels<2>(acc, p.stats, k.c, scratch);
+  if constexpr (MODE == 1 && POOL) {                               // pooled sums of sample k.n
+    const float a1[1] = {acc[0]};
+    block_reduce_channels<1>(a1, p.stats + (size_t)k.n * C, k.c, scratch, 1);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ output shift + BN, backward
@@ -756,8 +767,11 @@ extern "C" int sgcn_tshift_fwd(const SgcnTShift* p, int mode, void* stream) {
       tshift_fwd_kernel<0, false, 0><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
     }
   } else {
-    if (!p->out || !p->scale || !p->shift) return set_error("sgcn_tshift_fwd(apply): null pointer");
-    if (p->stride == 1) {
+    if ((!p->out && !p->stats) || !p->scale || !p->shift) return set_error("sgcn_tshift_fwd(apply): null pointer");
+    if (p->stats) {                                                // with the pooled sums of the model head (last unit)
+      if (p->stride != 1) return set_error("sgcn_tshift_fwd(apply): pooled sums need stride 1");
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_fwd_kernel<1, true, P, true><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+    } else if (p->stride == 1) {
       SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_fwd_kernel<1, true, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
     } else {
       SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_fwd_kernel<1, false, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))

@@ -293,7 +293,8 @@ def side_backward(saved, G, sg, Wd, bd, gamma, ws, accum_into=None):
 
 
 # ================================================================================================ temporal unit
-def temporal_forward(h, res, relu, bn, ypos_in, Wt, bt, ypos_out, bn2, stride, ws, h_stats_ready):
+def temporal_forward(h, res, relu, bn, ypos_in, Wt, bt, ypos_out, bn2, stride, ws, h_stats_ready, pool=None,
+                     store_out=True):
     """h: (n,T,V,C) rows -> y: (n,T/stride,V,C) rows = [relu](bn2(Shift_s(relu(conv(Shift_1(bn(h)))))) + res)"""
     n, T, V, C = h.shape
     To = T // stride
@@ -322,9 +323,11 @@ def temporal_forward(h, res, relu, bn, ypos_in, Wt, bt, ypos_out, bn2, stride, w
                        stats=stats_b)
     mean_b, invstd_b, scale_b, shift_b = ops.bn_fwd_finalize(stats_b if tr_b else None, gb, bb, rmb, rvb, nbtb, C,
                                                               n * To * V, momb, bn2.eps, tr_b)
-    y = torch.empty((n, To, V, C), device=dev, dtype=torch.float32)
+    # pool: fp64 [n, C] buffer that receives the sums over (t, v) of y (head of the model, model/shift_gcn.py:212-214);
+    # store_out=False (inference, pooled output only): y is never written
+    y = torch.empty((n, To, V, C), device=dev, dtype=torch.float32) if (store_out or pool is None) else None
     ops.tshift_fwd(1, q=q, ypos_eff=ypos_out_eff, n_samples=n, T_in=T, T_out=To, V=V, C=C, stride=stride, res=res,
-                   out=y, scale=scale_b, shift=shift_b, relu=relu)
+                   out=y, scale=scale_b, shift=shift_b, relu=relu, stats=pool)
     saved = dict(h=h, q=q, y=y, relu=relu, stride=stride, training_a=tr_a, training_b=tr_b, ypos_in_eff=ypos_in_eff,
                  ypos_out_eff=ypos_out_eff, mean_a=mean_a, invstd_a=invstd_a, scale_a=scale_a, shift_a=shift_a,
                  mean_b=mean_b, invstd_b=invstd_b)
@@ -563,8 +566,12 @@ class UnitFn(torch.autograd.Function):
         # the BatchNorm2d statistics of h come out of the kernel that writes h (not in the fully fused eval kernel)
         h_stats = tcn._ws.get("bn_a", 2 * C, x.device) if (bn_training(tcn.bn) and not fuse_eval) else None
         h, s_saved = spatial_forward(x, None, W, bias, mask, gcn.bn, gcn._ws, fuse_eval=fuse_eval, h_stats=h_stats)
+        pool = getattr(unit, "_pool_sums", None)                   # set by Model._trunk on the last unit only
         y, t_saved = temporal_forward(h, x, 1, tcn.bn, ypos_in, Wt.reshape(C, C), bt, ypos_out, tcn.bn2, 1,
-                                      tcn._ws, h_stats_ready=h_stats is not None)
+                                      tcn._ws, h_stats_ready=h_stats is not None, pool=pool,
+                                      store_out=need_grad or pool is None)
+        if y is None:                                              # pooled-only inference: nothing to return but a handle
+            return x.new_empty((0,))
         ctx.unit = unit
         _links(ctx, unit)
         if s_saved is not None:
@@ -648,6 +655,29 @@ class ConvUnitFn(torch.autograd.Function):
         return (s["gx"], s["dW"], s["dbias"], s["dmask"], s["dgamma"], s["dbeta"], rd["dWd"], rd["dbd"], rd["dgamma"],
                 rd["dbeta"], t["dgamma_a"], t["dbeta_a"], t["gx_in"], t["gy_in"], t["dWt"], t["dbt"], t["gx_out"],
                 t["gy_out"], t["dgamma_b"], t["dbeta_b"], rr["dWd"], rr["dbd"], rr["dgamma"], rr["dbeta"], None)
+
+
+class HeadFn(torch.autograd.Function):
+    """Global pooling over (T, V) and persons + fc (model/shift_gcn.py:212-216) from the pooled sums that the last unit's
+    output kernel left in ``pool_sums`` ([N*M, C] fp64).  ``y`` (the last unit's output rows, or an empty handle in
+    inference) only ties the node into the autograd graph; its gradient comes back in the row layout, written once."""
+
+    @staticmethod
+    def forward(ctx, y, W, b, pool_sums, N, M, rows_per_person):
+        pooled, logits = ops.head_fwd(pool_sums, W.detach().contiguous(), None if b is None else b.detach(), N, M,
+                                      rows_per_person * M)
+        ctx.dims = (N, M, rows_per_person, tuple(y.shape))
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(pooled, W)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dl):
+        pooled, W = ctx.saved_tensors
+        N, M, rpp, yshape = ctx.dims
+        dW, db, gpool = ops.head_bwd(dl.contiguous().float(), pooled, W.detach().contiguous(), N, M, rpp * M, ctx.has_bias)
+        gy = ops.bcast_rows(gpool, rpp, 1.0).view(yshape) if ctx.needs_input_grad[0] else None
+        return gy, dW, db, None, None, None, None
 
 
 class PoolRowsFn(torch.autograd.Function):

@@ -258,7 +258,7 @@ class TCN_GCN_unit(nn.Module):
         if self._res_mode == "identity" and gcn.fused_supported(x) and tcn1.fused_supported(x):
             FN.set_grad_mode(torch.is_grad_enabled())
             y = FN.UnitFn.apply(to_rows(x), *gcn._args(), *tcn1._args(), self)
-            return from_rows(y)
+            return y if y.dim() == 1 else from_rows(y)         # 1-D: the pooled-only handle of Model._trunk (inference)
         if (self._res_mode == "conv" and isinstance(gcn.down, nn.Sequential) and gcn.fused_supported(x)
                 and side_supported(gcn.down[0], x.shape[3]) and side_supported(self.residual.conv, x.shape[3])
                 and x.shape[2] % self.residual.conv.stride[0] == 0 and self._tcn_fused_for(x)):
@@ -349,21 +349,53 @@ class Model(nn.Module):
                                 scale=scale.float().contiguous(), shift=shift.float().contiguous())
         return self._trunk(rows.permute(0, 3, 1, 2), N, M)
 
+    def _head_fusable(self, unit, x):
+        """l10 takes the fused identity-unit path and the classifier is a plain fp32 Linear on the same device"""
+        ok = (unit._res_mode == "identity" and unit.gcn1.fused_supported(x) and unit.tcn1.fused_supported(x)
+              and unit.tcn1.shift_out.stride == 1 and isinstance(self.fc, nn.Linear) and self.fc.weight.is_cuda
+              and self.fc.weight.dtype == torch.float32 and self.fc.in_features == unit.gcn1.out_channels)
+        if ok:
+            self._last_tv = (x.shape[2], x.shape[3])
+        return ok
+
+    def _pool_buffer(self, n, C, device):
+        key = (n, C, str(device))
+        buf = getattr(self, "_pool_bufs", {}).get(key)
+        if buf is None:
+            buf = torch.zeros((n, C), device=device, dtype=torch.float64)   # sgcn_head_fwd hands it back zeroed
+            self.__dict__.setdefault("_pool_bufs", {})[key] = buf
+        return buf
+
     def _trunk(self, x, N, M):
         """l1..l10, pooling over (T, V) and persons, fc (reference :200-216); x: logical (N*M, C, T, V), channels-last"""
         # consecutive units exchange ReLU-masked gradients (functional._links): one dict per unit boundary, attached
         # only for the duration of the unit's forward call so that a unit used on its own never sees a stale link
         ops.restart_traversal()
         links = [dict(masked=False) for _ in range(9)] if torch.is_grad_enabled() else None
+        pool = None
         for i in range(1, 11):
             unit = getattr(self, f"l{i}")
             if links is not None:
                 unit._in_link = links[i - 2] if i >= 2 else None
                 unit._out_link = links[i - 1] if i <= 9 else None
+            if i == 10 and self._head_fusable(unit, x):
+                # the kernel that writes l10's output also accumulates the pooled sums of the head (and, in inference,
+                # does not write the output at all)
+                pool = self._pool_buffer(x.shape[0], unit.gcn1.out_channels, x.device)
+                unit._pool_sums = pool
             try:
                 x = unit(x)
+            except BaseException:
+                if pool is not None:
+                    pool.zero_()                                   # never leave partial sums behind
+                raise
             finally:
                 unit._in_link = unit._out_link = None
+                unit._pool_sums = None
+        if pool is not None:
+            rows = x if x.dim() == 1 else x.permute(0, 2, 3, 1)
+            T_last, V_last = getattr(self, "_last_tv")
+            return FN.HeadFn.apply(rows, self.fc.weight, self.fc.bias, pool, N, M, T_last * V_last)
         c_new = x.size(1)
         if x.is_cuda and x.dtype == torch.float32 and c_new % 4 == 0 and x.permute(0, 2, 3, 1).is_contiguous():
             x = FN.PoolRowsFn.apply(x.permute(0, 2, 3, 1))     # same mean; the gradient comes back in the row layout

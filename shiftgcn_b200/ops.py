@@ -374,6 +374,8 @@ def bn_res_relu_fwd(z, res, h, scale, shift, stats_out, rows, V, D, relu=1):
 
 def tshift_fwd(mode, *, q, ypos_eff, n_samples, T_in, T_out, V, C, stride, res=None, out=None, scale=None, shift=None,
                stats=None, relu=0):
+    """mode 0: stats [C, 2] f64 += {sum s, sum s^2};  mode 1: out = [relu](BN(s) + res); with stats [n, C] f64 the pooled
+    sums over (t, v) of out are accumulated as well and out may be None (include/shiftgcn_b200.h:sgcn_tshift_fwd)"""
     lib = _lib.load()
     p = SgcnTShift(q=_p(q), res=_p(res), out=_p(out), ypos_eff=_p(ypos_eff), scale=_p(scale), shift=_p(shift),
                    stats=_d(stats), n_samples=int(n_samples), T_in=T_in, T_out=T_out, V=V, C=C, stride=stride,
@@ -590,6 +592,30 @@ def bcast_rows(g, rows_per_n, scale):
         _launch("bcast_rows", 1, _nbytes(out), lib.sgcn_bcast_rows, _p(g, name="g"), _p(out), n, int(rows_per_n), C,
                 ctypes.c_float(scale), _STREAM)
     return out
+
+
+def head_fwd(pool_sums, W, b, N, M, count):
+    """(pooled [N, C], logits [N, K]) from the pooled sums [N*M, C] f64 (sgcn_head_fwd); count = T*V*M rows per sample"""
+    lib = _lib.load()
+    K, C = W.shape
+    pooled = torch.empty((N, C), device=W.device, dtype=torch.float32)
+    logits = torch.empty((N, K), device=W.device, dtype=torch.float32)
+    if N:
+        _launch("head_fwd", 1, _nbytes(pool_sums, logits), lib.sgcn_head_fwd, _d(pool_sums, "pool_sums"), _p(W, name="fc.weight"),
+                _p(b), _p(pooled), _p(logits), N, M, C, K, 1.0 / float(count), _STREAM)
+    return pooled, logits
+
+
+def head_bwd(dlogits, pooled, W, N, M, count, want_bias=True):
+    """(dW [K, C], db [K] or None, gpool [N*M, C]) -- sgcn_head_bwd"""
+    lib = _lib.load()
+    K, C = W.shape
+    dW = torch.empty((K, C), device=W.device, dtype=torch.float32)
+    db = torch.empty(K, device=W.device, dtype=torch.float32) if want_bias else None
+    gpool = torch.empty((N * M, C), device=W.device, dtype=torch.float32)
+    _launch("head_bwd", 1, _nbytes(dW, gpool), lib.sgcn_head_bwd, _p(dlogits, name="dlogits"), _p(pooled), _p(W), _p(dW),
+            _p(db), _p(gpool), N, M, C, K, ctypes.c_float(1.0 / float(count)), _STREAM)
+    return dW, db, gpool
 
 
 # ------------------------------------------------------------------------------------------------ optimizer step

@@ -66,8 +66,10 @@ def test_graph_replay_equals_eager_steps(cuda_device):
     xs = [torch.randn(4, 3, 32, 25, 2, generator=g).to(cuda_device) for _ in range(3)]
     ys = [torch.randint(0, 60, (4,), generator=g).to(cuda_device) for _ in range(3)]
     m_eager, m_graph = copy.deepcopy(base), copy.deepcopy(base)
-    t_eager = FlatSGDTrainer(m_eager, lr=0.05)
-    t_graph = FlatSGDTrainer(m_graph, lr=0.05)
+    # a small rate: with lr 0.05 one step takes the loss from 1.7 to 13.8 and the two trajectories (same arithmetic,
+    # different order of the fp64 atomics) separate chaotically, which made every bound below a coin toss
+    t_eager = FlatSGDTrainer(m_eager, lr=0.002)
+    t_graph = FlatSGDTrainer(m_graph, lr=0.002)
     init = t_eager.flat_param.clone()
     # capture() runs `warmup` real steps on its example batch first: give the eager trainer the same ones
     t_graph.capture(xs[0], ys[0], warmup=1)
