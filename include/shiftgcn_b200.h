@@ -102,6 +102,16 @@ int sgcn_head_fwd(double* pool_sums, const float* W, const float* b, float* pool
 int sgcn_head_bwd(const float* dlogits, const float* pooled, const float* W, float* dW, float* db, float* gpool, int N,
                   int M, int C, int K, float scale, void* stream);
 
+/* Input BatchNorm of the model in training mode (model/shift_gcn.py:196-198: BatchNorm1d(M*V*C) over (N, T)).
+ * sgcn_data_bn_stats: stats[f][2] (fp64, zeroed by the caller / handed back zeroed by sgcn_bn_fwd_finalize) +=
+ * {sum x, sum x^2} of feature f = (m*V + v)*C + c, x in the input layout [N, C, T, V, M] (V*M <= 128).  The scale / shift
+ * tables of sgcn_bn_fwd_finalize are then applied by sgcn_input_stream together with the change to the row layout.
+ * sgcn_data_bn_bwd: sums[f][2] += {sum g, sum g*xhat} with g the gradient wrt the BatchNorm output in the row layout
+ * [(N*M), T, V, C] (V*C <= 128): beta.grad and gamma.grad after sgcn_reduce_export. */
+int sgcn_data_bn_stats(const float* x, double* stats, long long N, int C, int T, int V, int M, void* stream);
+int sgcn_data_bn_bwd(const float* g, const float* x, const float* mean, const float* invstd, double* sums, long long N,
+                     int C, int T, int V, int M, void* stream);
+
 /* Feeder augmentation on the device: feeders/tools.py:58-101 random_move for a batch [N, C, T, V, M] (C >= 2), in place.
  * node: int[K+1] frame indices 0 = node[0] < ... < node[K] = T (the reference's `node`, move_time = K); vals: fp64
  * [N, 4, K+1] = the angle (degrees), scale, x and y translation drawn at every node for every sample.  Between two nodes

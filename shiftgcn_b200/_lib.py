@@ -84,6 +84,8 @@ SIGNATURES = {
     "sgcn_window_scores": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "sgcn_head_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _vp],
     "sgcn_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp],
+    "sgcn_data_bn_stats": [_vp, _vp, _ll, _i, _i, _i, _i, _vp],
+    "sgcn_data_bn_bwd": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp],
     "sgcn_random_move": [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp],
     "sgcn_side_fold": [ctypes.POINTER(SgcnSideFold), _vp],
     "sgcn_side_bwd": [ctypes.POINTER(SgcnSideBwd), _vp],

@@ -159,7 +159,76 @@ __global__ void __launch_bounds__(256) random_move_kernel(float* __restrict__ da
   *py = (float)(sn * x + cs * y + ty);
 }
 
+// Input BatchNorm of the model in TRAINING mode (model/shift_gcn.py:196-198: BatchNorm1d over the M*V*C features of
+// the (N, M*V*C, T) view).  Statistics of feature (m, v, c) over (n, t), read in the input layout [N, C, T, V, M]: a block
+// owns channel c and a chunk of (n, t) pairs, thread j the (v, m) column j of the contiguous V*M floats of a frame.
+// stats[f][2] += {sum x, sum x^2} with f = (m*V + v)*C + c (fp64); sgcn_bn_fwd_finalize turns them into scale / shift
+// (and updates the running statistics), which sgcn_input_stream applies together with the layout change.
+__global__ void __launch_bounds__(128) data_bn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, long long N,
+                                                            int C, int T, int V, int M, int per) {
+  const int c = blockIdx.y, j = threadIdx.x, VM = V * M;
+  if (j >= VM) return;
+  const long long first = (long long)blockIdx.x * per, last = min(first + per, N * T);
+  double s1 = 0.0, s2 = 0.0;
+  for (long long i = first; i < last; ++i) {                       // i = n*T + t
+    const long long n = i / T, t = i - n * T;
+    const double v = (double)__ldg(x + ((n * C + c) * T + t) * VM + j);
+    s1 += v, s2 += v * v;
+  }
+  const int v = j / M, m = j - v * M;
+  const size_t f = ((size_t)m * V + v) * C + c;
+  atomicAdd(stats + 2 * f, s1);
+  atomicAdd(stats + 2 * f + 1, s2);
+}
+
+// backward sums of the same BatchNorm: g = gradient wrt its output in the ROW layout [(N*M), T, V, C];
+// sums[f][2] += {sum g, sum g * xhat},  xhat = (x - mean_f) * invstd_f.  A block owns person m and a chunk of (n, t),
+// thread j the (v, c) column j of the contiguous V*C floats of a row group.
+__global__ void __launch_bounds__(128) data_bn_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                          double* __restrict__ sums, long long N, int C, int T, int V, int M,
+                                                          int per) {
+  const int m = blockIdx.y, j = threadIdx.x, VC = V * C;
+  if (j >= VC) return;
+  const int v = j / C, c = j - v * C;
+  const size_t f = ((size_t)m * V + v) * C + c;
+  const double mu = (double)__ldg(mean + f), is = (double)__ldg(invstd + f);
+  const long long first = (long long)blockIdx.x * per, last = min(first + per, N * T);
+  double s1 = 0.0, s2 = 0.0;
+  for (long long i = first; i < last; ++i) {
+    const long long n = i / T, t = i - n * T;
+    const double gv = (double)__ldg(g + ((n * M + m) * T + t) * VC + j);
+    const double xv = (double)__ldg(x + (((n * C + c) * T + t) * V + v) * M + m);
+    s1 += gv, s2 += gv * (xv - mu) * is;
+  }
+  atomicAdd(sums + 2 * f, s1);
+  atomicAdd(sums + 2 * f + 1, s2);
+}
+
 }  // namespace sgcn
+
+extern "C" int sgcn_data_bn_stats(const float* x, double* stats, long long N, int C, int T, int V, int M, void* stream) {
+  using namespace sgcn;
+  if (N < 0 || C < 1 || T < 1 || V < 1 || M < 1 || V * M > 128) return set_error("sgcn_data_bn_stats: bad shape (V*M <= 128)");
+  if (N == 0) return 0;
+  if (!x || !stats) return set_error("sgcn_data_bn_stats: null pointer");
+  const long long pairs = N * T;
+  const int chunks = (int)(pairs < 256 ? pairs : 256), per = (int)((pairs + chunks - 1) / chunks);
+  data_bn_stats_kernel<<<dim3((unsigned)((pairs + per - 1) / per), C), 128, 0, (cudaStream_t)stream>>>(x, stats, N, C, T, V, M, per);
+  return check_launch("data_bn_stats_kernel");
+}
+
+extern "C" int sgcn_data_bn_bwd(const float* g, const float* x, const float* mean, const float* invstd, double* sums,
+                                long long N, int C, int T, int V, int M, void* stream) {
+  using namespace sgcn;
+  if (N < 0 || C < 1 || T < 1 || V < 1 || M < 1 || V * C > 128) return set_error("sgcn_data_bn_bwd: bad shape (V*C <= 128)");
+  if (N == 0) return 0;
+  if (!g || !x || !mean || !invstd || !sums) return set_error("sgcn_data_bn_bwd: null pointer");
+  const long long pairs = N * T;
+  const int chunks = (int)(pairs < 256 ? pairs : 256), per = (int)((pairs + chunks - 1) / chunks);
+  data_bn_bwd_kernel<<<dim3((unsigned)((pairs + per - 1) / per), M), 128, 0, (cudaStream_t)stream>>>(g, x, mean, invstd, sums, N, C, T, V, M, per);
+  return check_launch("data_bn_bwd_kernel");
+}
 
 extern "C" int sgcn_random_move(float* data, const double* vals, const int* node, long long N, int C, int T, int V, int M,
                                 int K, void* stream) {

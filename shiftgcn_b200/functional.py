@@ -657,6 +657,34 @@ class ConvUnitFn(torch.autograd.Function):
                 t["gy_out"], t["dgamma_b"], t["dbeta_b"], rr["dWd"], rr["dbd"], rr["dgamma"], rr["dbeta"], None)
 
 
+class DataBnFn(torch.autograd.Function):
+    """The model's input BatchNorm in training mode + the change to the row layout (model/shift_gcn.py:196-198):
+    x (N, C, T, V, M) -> rows (N*M, T, V, C).  Statistics in the input layout (sgcn_data_bn_stats), running buffers in
+    sgcn_bn_fwd_finalize, normalisation fused with the layout change (sgcn_input_stream); the backward needs gamma.grad
+    and beta.grad only (the input is data)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, ws):
+        N, C, T, V, M = x.shape
+        F_ = M * V * C
+        stats = ws.get("data_bn", 2 * F_, x.device)
+        ops.data_bn_stats(x, stats)
+        g, b, rmean, rvar, nbt, mom = _bn_args(bn)
+        mean, invstd, scale, shift = ops.bn_fwd_finalize(stats, g, b, rmean, rvar, nbt, F_, N * T, mom, bn.eps, True)
+        rows = ops.input_stream(x, rows=True, scale=scale, shift=shift)
+        ctx.save_for_backward(x, mean, invstd)
+        ctx.ws = ws
+        return rows
+
+    @staticmethod
+    def backward(ctx, g):
+        x, mean, invstd = ctx.saved_tensors
+        sums = ctx.ws.get("data_bn_bwd", 2 * mean.numel(), x.device)
+        ops.data_bn_bwd(g.contiguous(), x, mean, invstd, sums)
+        out = ops.reduce_export(sums).view(-1, 2)
+        return None, out[:, 1].contiguous(), out[:, 0].contiguous(), None, None
+
+
 class HeadFn(torch.autograd.Function):
     """Global pooling over (T, V) and persons + fc (model/shift_gcn.py:212-216) from the pooled sums that the last unit's
     output kernel left in ``pool_sums`` ([N*M, C] fp64).  ``y`` (the last unit's output rows, or an empty handle in

@@ -313,8 +313,15 @@ class Model(nn.Module):
         # data_bn (reference :196-198) normalises feature (m, v, c) over (N, T).  Same arithmetic on the row-major
         # matrix [(N, T), (M, V, C)]: the 2-D batch-norm kernels are ~20x faster than the (N, F, T) ones here, and
         # the result is already channels-last, i.e. the logical (N*M, C, T, V) tensor the units consume without a copy.
-        x = x.permute(0, 2, 4, 3, 1).reshape(N * T, M * V * C)
         bn = self.data_bn
+        if (x.is_cuda and x.dtype == torch.float32 and not x.requires_grad and FN.bn_training(bn) and bn.affine
+                and V * M <= 128 and V * C <= 128 and C == 3 and N > 0):
+            # native training-mode path: statistics, running buffers, normalisation and the row layout in three kernels
+            if not hasattr(self, "_ws"):
+                self.__dict__["_ws"] = FN.Workspace()
+            rows = FN.DataBnFn.apply(x.contiguous(), bn.weight, bn.bias, bn, self.__dict__["_ws"])
+            return self._trunk(rows.permute(0, 3, 1, 2), N, M)
+        x = x.permute(0, 2, 4, 3, 1).reshape(N * T, M * V * C)
         track = bn.track_running_stats and bn.running_mean is not None
         if bn.training and track:
             bn.num_batches_tracked += 1

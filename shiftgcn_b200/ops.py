@@ -532,6 +532,21 @@ def random_move_(data, vals, node):
     return data
 
 
+def data_bn_stats(x, stats):
+    """stats [M*V*C, 2] f64 += {sum, sum of squares} of every input feature (m, v, c) of x (N, C, T, V, M) over (N, T)"""
+    lib = _lib.load()
+    N, C, T, V, M = x.shape
+    _launch("data_bn[stats]", 1, _nbytes(x), lib.sgcn_data_bn_stats, _p(x, name="x"), _d(stats), N, C, T, V, M, _STREAM)
+
+
+def data_bn_bwd(g_rows, x, mean, invstd, sums):
+    """sums [M*V*C, 2] f64 += {sum g, sum g*xhat}: g_rows (N*M, T, V, C) = gradient wrt the data_bn output (row layout)"""
+    lib = _lib.load()
+    N, C, T, V, M = x.shape
+    _launch("data_bn[bwd]", 1, _nbytes(g_rows, x), lib.sgcn_data_bn_bwd, _p(g_rows, name="g"), _p(x, name="x"), _p(mean),
+            _p(invstd), _d(sums), N, C, T, V, M, _STREAM)
+
+
 def frame_aggregate(score, start, real, total_frames):
     """per-frame mean of given window scores (fp64 [W]) -- the aggregation half of sgcn_window_scores"""
     lib = _lib.load()

@@ -67,3 +67,33 @@ def test_model_head_is_native_and_inference_skips_the_last_output(cuda_device):
             del mod._head_fusable
         tol = 2e-3 if train else 1e-5                               # training: the second pass sees updated running stats only
         assert (got - want).abs().max().item() < tol * want.abs().max().item(), train
+
+
+@pytest.mark.parametrize("N,T,V,M", [(4, 9, 25, 2), (3, 7, 33, 1)])
+def test_training_data_bn_matches_torch(cuda_device, N, T, V, M):
+    """input side (model/shift_gcn.py:196-198): the native training-mode data_bn (statistics kernel, finalize with the
+    running buffers, normalisation fused with the row layout) and its backward against nn.BatchNorm1d in fp64"""
+    from shiftgcn_b200 import functional as FN
+    C = 3
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(N, C, T, V, M, generator=g) * 2 + 0.5
+    go = torch.randn(N * M, T, V, C, generator=g)
+    bn = torch.nn.BatchNorm1d(M * V * C)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(M * V * C, generator=g) + 0.5), bn.bias.copy_(torch.randn(M * V * C, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(M * V * C, generator=g) * 0.1), bn.running_var.copy_(torch.rand(M * V * C, generator=g) + 0.5)
+    import copy
+    ref = copy.deepcopy(bn).double().train()
+    bn = bn.to(cuda_device).train()
+    # reference: the model's own sequence of views (model/shift_gcn.py:196-198)
+    xr = x.double().permute(0, 4, 3, 1, 2).contiguous().view(N, M * V * C, T)
+    yr = ref(xr).view(N, M, V, C, T).permute(0, 1, 3, 4, 2).contiguous().view(N * M, C, T, V)
+    yr.backward(go.double().permute(0, 3, 1, 2))
+    rows = FN.DataBnFn.apply(x.to(cuda_device), bn.weight, bn.bias, bn, FN.Workspace())
+    rows.backward(go.to(cuda_device))
+    want_rows = yr.detach().permute(0, 2, 3, 1)
+    assert (rows.double().cpu() - want_rows).abs().max() < 1e-5 * want_rows.abs().max()
+    for got, want in ((bn.weight.grad, ref.weight.grad), (bn.bias.grad, ref.bias.grad), (bn.running_mean, ref.running_mean),
+                      (bn.running_var, ref.running_var)):
+        assert (got.double().cpu() - want).abs().max() < 1e-5 * want.abs().max()
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == 1
