@@ -150,6 +150,14 @@ int make_rows_map(CUtensorMap* m, const float* base, long long rows, int pitch, 
   return encode(m, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
+int make_frames_map(CUtensorMap* m, const float* base, long long frames, int V, int pitch, int box_ch, int box_v,
+                    int box_frames) {
+  const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)V, (cuuint64_t)frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)V * pitch * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)box_ch, (cuuint32_t)box_v, (cuuint32_t)box_frames};
+  return encode(m, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
 int make_groups_map_sw128(CUtensorMap* m, const float* base, long long groups, long long gs, int V, int pitch,
                           int box_groups) {
   const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)V, (cuuint64_t)groups};

@@ -32,6 +32,11 @@
 //   EPI_ROT_RAW    + bias, rotate z[v,d]=y[(v-d)%V,d], store, per-(v,d) batch statistics   :131-137 (training)
 //   EPI_ROT_FUSED  + bias, rotate, folded BN, + residual, ReLU                              :131-141 (eval)
 //   EPI_LINEAR     + bias, optional ReLU, store                                             :69-70
+//   EPI_TSHIFT     + bias, ReLU, fractional OUTPUT shift, folded BN, + residual, ReLU        :69-73, 161-162 (eval, stride 1)
+//                  -- the whole temporal unit in one kernel.  Tile geometry "joints x frames": the template V is a joint
+//                  SUBSET (5 of 25) and the G = 25 row groups are consecutive FRAMES of one sample, so the second shift
+//                  finds its taps inside the tile; a tile yields G - kWo output frames (q is recomputed for the kWo halo
+//                  frames, 12 %) and q never crosses HBM.  Needs all floor(ypos_out) inside one window of kWo values.
 #pragma once
 #include "capi_internal.h"
 #include "common.cuh"
@@ -44,7 +49,7 @@ namespace sgcn {
 namespace fg {
 
 enum { PRO_SPATIAL = 0, PRO_LERP = 1, PRO_PLAIN = 2 };
-enum { EPI_ROT_RAW = 0, EPI_ROT_FUSED = 1, EPI_LINEAR = 2 };
+enum { EPI_ROT_RAW = 0, EPI_ROT_FUSED = 1, EPI_LINEAR = 2, EPI_TSHIFT = 4 };   // (3 = the spatial backward, spatial_bwd.cu)
 
 constexpr int kEpiWarps = 12, kBldWarps = 12;
 constexpr int kEpiThreads = kEpiWarps * 32, kBldThreads = kBldWarps * 32;
@@ -115,6 +120,9 @@ struct Cfg {
   // reads need no swizzle arithmetic: bank = (4*row + channel) % 32, at most 2-way conflicts where the rotation wraps
   static constexpr int kStPitch = 272;
   static constexpr int kStBytes = EPI == EPI_LINEAR ? 128 * 32 * 4 : 128 * kStPitch;
+  // EPI_TSHIFT: window of floor(ypos_out) values and output frames per tile
+  static constexpr int kWo = 3;
+  static constexpr int kFo = G - kWo;
   // HBM latency x bandwidth needs >= 64 KiB of loads in flight per SM: spend what is left on input stages
   static constexpr int kAvail = 232448 - 1600 - kWBytes - kStBytes;
   static constexpr int kRaw2 = PRO == PRO_PLAIN ? 0 : (kAvail - 2 * kOpBytes) / kRawBytes;
@@ -147,9 +155,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
   const uint32_t sRaw = sSt + C::kStBytes;
   __shared__ uint64_t op_full[4], op_free[4], acc_full[2], acc_free[2], w_full[2], w_free[2], raw_full[4], raw_free[4];
   __shared__ uint32_t tmem_base_s;
-  __shared__ int lerp_hist[16], lerp_lo_s;
+  __shared__ int lerp_hist[16], lerp_lo_s, out_lo_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr bool kTmaOp = PRO == PRO_PLAIN && !P3;                 // operand stages filled by TMA alone
+  constexpr bool TV = EPI == EPI_TSHIFT;                           // "joints x frames" tiles (V = joint subset, groups = frames)
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
@@ -167,23 +176,28 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
     fence_mbar_init();
   }
   if constexpr (PRO == PRO_LERP) {
-    // window of floor(ypos) values the raw tile covers: the kWin consecutive values holding most channels
-    if (tid < 16) lerp_hist[tid] = 0;
-    __syncthreads();
-    for (int c = tid; c < K; c += kThreads) {
-      const int fl = (int)floorf(__ldg(p.pro_c + c));
-      if (fl >= -8 && fl < 8) atomicAdd(&lerp_hist[fl + 8], 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int best = 0, bestn = -1;
-      for (int lo = 0; lo + C::kWin <= 16; ++lo) {
-        int n = 0;
-        for (int j = 0; j < C::kWin; ++j) n += lerp_hist[lo + j];
-        if (n > bestn) bestn = n, best = lo;
+    // window of floor(ypos) values the raw tile covers: the `win` consecutive values holding most channels
+    auto pick_window = [&](const float* ypos, int nch, int win, int* result) {
+      if (tid < 16) lerp_hist[tid] = 0;
+      __syncthreads();
+      for (int c = tid; c < nch; c += kThreads) {
+        const int fl = (int)floorf(__ldg(ypos + c));
+        if (fl >= -8 && fl < 8) atomicAdd(&lerp_hist[fl + 8], 1);
       }
-      lerp_lo_s = best - 8;
-    }
+      __syncthreads();
+      if (tid == 0) {
+        int best = 0, bestn = -1;
+        for (int lo = 0; lo + win <= 16; ++lo) {
+          int n = 0;
+          for (int j = 0; j < win; ++j) n += lerp_hist[lo + j];
+          if (n > bestn) bestn = n, best = lo;
+        }
+        *result = best - 8;
+      }
+      __syncthreads();
+    };
+    pick_window(p.pro_c, K, C::kWin, &lerp_lo_s);
+    if constexpr (TV) pick_window(p.res2, N, C::kWo, &out_lo_s);   // EPI_TSHIFT: res2 = effective output shift positions
   }
   constexpr uint32_t tmem_cols = 2 * N <= 128 ? 128u : (2 * N <= 256 ? 256u : 512u);
   if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, tmem_cols);
@@ -198,8 +212,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  const long long ntiles = (p.groups + G - 1) / G;
+  // TV tiles: (sample, frame block of kFo output frames, joint subset); p.V is the tensor's joint count, p.groups = n * T
+  const int tvNJ = TV ? p.V / V : 1, tvFB = TV ? (p.T + C::kFo - 1) / C::kFo : 1;
+  const long long ntiles = TV ? (p.groups / (p.T > 0 ? p.T : 1)) * tvFB * tvNJ : (p.groups + G - 1) / G;
   const int my_tiles = (long long)blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  struct TvTile {
+    int n, fb, js, tq0;                                            // sample, frame block, joint subset, first staged q frame
+  };
+  auto tv_tile = [&](long long tile) -> TvTile {
+    TvTile t;
+    t.js = (int)(tile % tvNJ);
+    const long long r = tile / tvNJ;
+    t.fb = (int)(r % tvFB);
+    t.n = (int)(r / tvFB);
+    t.tq0 = t.fb * C::kFo + out_lo_s;
+    return t;
+  };
   const int total_chunks = my_tiles * KC;
   // snake traversal (capi_internal.h): rev walks the tiles from the last one down
   auto tile_of = [&](int ti) -> long long {
@@ -301,9 +329,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         for (int q = 0; q < total_chunks; ++q) {
           const int s = q % RS, ti = q / KC, kc = q - ti * KC;
           if (q >= RS) mbar_wait(&raw_free[s], (uint32_t)(((q / RS) - 1) & 1));
-          const long long gfirst = tile_of(ti) * G + lerp_lo;      // first group of the raw tile (may be < 0: zeros)
           mbar_expect_tx(&raw_full[s], (uint32_t)C::kRawBytes);
-          tma_load_2d(sRaw + (uint32_t)s * C::kRawBytes, &tm0, kc * 64, (int)(gfirst * V), smem_u32(&raw_full[s]));
+          if constexpr (TV) {                                      // box {64 channels, V joints, G + kWin frames}
+            const TvTile t = tv_tile(tile_of(ti));
+            tma_load_3d(sRaw + (uint32_t)s * C::kRawBytes, &tm0, kc * 64, t.js * V, t.n * p.T + t.tq0 + lerp_lo,
+                        smem_u32(&raw_full[s]));
+          } else {
+            const long long gfirst = tile_of(ti) * G + lerp_lo;    // first group of the raw tile (may be < 0: zeros)
+            tma_load_2d(sRaw + (uint32_t)s * C::kRawBytes, &tm0, kc * 64, (int)(gfirst * V), smem_u32(&raw_full[s]));
+          }
         }
       }
     }
@@ -389,8 +423,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
       asm volatile("" : "+r"(opb), "+r"(rawb), "+r"(lqs));
       for (int q = 0; q < total_chunks; ++q) {
         const int ti = q / KC, kc = q - ti * KC;
-        const long long g0 = tile_of(ti) * G;
-        const int ng = (int)((p.groups - g0) < G ? (p.groups - g0) : G);
+        const long long g0 = TV ? 0 : tile_of(ti) * G;
+        const int ng = TV ? G : (int)((p.groups - g0) < G ? (p.groups - g0) : G);
         // the per-(joint, channel) / per-channel tables of this chunk are requested BEFORE the wait for its raw rows:
         // loaded right in front of their use, every (joint, half) pair paid a full global-load latency (ncu: 28 % of
         // the builder warps' stall samples sat on the first multiply of each pair)
@@ -447,8 +481,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         } else {
           // p[(g,v), c] = (1-f) U(t+y1) + f U(t+y1+1),  U = sa*h + sb inside the sample, 0 outside   (K1 with xpos = 0)
           const int T = p.T;
-          const int t0 = p.groups < (1ll << 31) ? (int)((unsigned)g0 % (unsigned)T) : (int)(g0 % T);
-          const bool interior = ng == G && t0 + lerp_lo >= 0 && t0 + G - 1 + lerp_lo + C::kWin < T && t0 + G <= T;
+          TvTile tvt = {0, 0, 0, 0};
+          if constexpr (TV) tvt = tv_tile(tile_of(ti));
+          // frame of the tile's first group; TV tiles stay inside one sample and may start in front of it (t0 < 0)
+          const int t0 = TV ? tvt.tq0 : (p.groups < (1ll << 31) ? (int)((unsigned)g0 % (unsigned)T) : (int)(g0 % T));
+          const bool interior = ng == G && t0 + lerp_lo >= 0 && t0 + G - 1 + lerp_lo + C::kWin < T && (TV || t0 + G <= T);
           const int half = bw & 1;
           const int c = tc;
           const float ypos = tab[0], sa = tab[1], sb = tab[2];
@@ -467,6 +504,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
                 const uint32_t rb = rbh + (uint32_t)v * 256u;
 #pragma unroll
                 for (int g = 0; g <= G; ++g) s[g] = lds32(rb + (uint32_t)(g * V * 256));
+              } else if constexpr (TV) {                           // ... global taps, frames clamped into the sample
+                const float* col = p.in0 + (((size_t)tvt.n * T) * p.V + tvt.js * V + v) * K + c;
+#pragma unroll
+                for (int g = 0; g <= G; ++g) s[g] = __ldg(col + (size_t)min(max(t0 + g + y1, 0), T - 1) * p.V * K);
               } else {                                             // shift position outside the staged window: global taps
                 const long long last = p.groups - 1;
 #pragma unroll
@@ -484,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                   int t = t0 + g;                                  // frame of this group (tiles may straddle samples)
-                  if (t >= T) t -= T;
+                  if (!TV && t >= T) t -= T;
                   const float u0 = ((unsigned)(t + y1) < (unsigned)T) ? fmaf(a0, s[g], b0) : 0.f;
                   const float u1 = ((unsigned)(t + y1 + 1) < (unsigned)T) ? fmaf(a1, s[g + 1], b1) : 0.f;
                   put(b, v16, g, u0 + u1);
@@ -547,7 +588,81 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         mbar_wait_relaxed(&acc_full[buf], (uint32_t)((ti >> 1) & 1));
         tc_fence_after();
       }
-      if constexpr (EPI == EPI_LINEAR) {
+      if constexpr (EPI == EPI_TSHIFT) {
+        // q = relu(acc + bias) of frames tq0 .. tq0+G-1 and V joints sits in the accumulator; per 64-channel chunk it goes
+        // through the staging tile (row = frame * V + joint), then lane <-> channel: a warp owns ONE (joint, half) pair and
+        // walks the output frames with the two-tap filter of its channel's shift position, folded BatchNorm, residual and
+        // ReLU -- the walker kernel tshift_fwd_apply, fed from shared memory (same arithmetic, same rounding).
+        const TvTile t = tv_tile(tile_of(ti));
+        const int T = p.T, Vr = p.V, out_lo = out_lo_s;
+        const int nfo = min(C::kFo, T - t.fb * C::kFo);            // output frames of this tile
+        const bool inner = t.tq0 >= 0 && t.tq0 + G <= T;           // every staged frame of q lies inside the sample
+        const bool active = wv < 2 * V;
+        const int v = min(wv >> 1, V - 1);
+        const size_t fstride = (size_t)Vr * N;                     // one frame of the output / residual tensors
+        int nch_rt = NCH;                                          // rolled: one chunk's residual values live at a time
+        asm volatile("" : "+r"(nch_rt));
+#pragma unroll 1
+        for (int nc = 0; nc < nch_rt; ++nc) {
+          const int d = nc * 64 + (wv & 1) * 32 + lane;
+          const float yo = __ldg(p.res2 + d), scb = __ldg(p.epi_a + d), shb = __ldg(p.epi_b + d);
+          const float bias = p.bias ? __ldg(p.bias + d) : 0.f;
+          const float fl = floorf(yo), f = yo - fl, gw = 1.f - f;
+          const int idx = min(max((int)fl - out_lo, 0), C::kWo - 1);
+          const size_t o0 = (((size_t)t.n * T + (size_t)t.fb * C::kFo) * Vr + (size_t)(t.js * V + v)) * N + d;
+          float rv[C::kFo];
+          {
+            const float* rp = res + o0;                            // requested in front of the drain and its barrier
+#pragma unroll
+            for (int fo = 0; fo < C::kFo; ++fo) {
+              rv[fo] = __ldg(rp);
+              if (fo + 1 < nfo) rp += fstride;
+            }
+          }
+          if (warp < 8) {   // TMEM -> staging: lane quarter (warp & 3), column half (warp >> 2)
+            const int qd = warp & 3, hf = warp >> 2;
+            const uint32_t row = (uint32_t)(qd * 32 + lane);
+            const uint32_t rb = sSt + row * (uint32_t)C::kStPitch + (uint32_t)(hf * 128);
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              float a[16];
+              tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * N + nc * 64 + hf * 32 + h2 * 16), a);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                sts128(rb + (uint32_t)((h2 * 4 + i) * 16), make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]));
+            }
+            if (nc == NCH - 1) {                                   // last read of this accumulator buffer
+              tc_fence_before();
+              mbar_arrive(&acc_free[buf]);
+            }
+          }
+          epi_sync();
+          if (active) {
+            const uint32_t sb = stb + (uint32_t)((idx * V + v) * C::kStPitch);   // staging row of tap 0 of output frame 0
+            const int tq = t.tq0 + idx;                            // its frame inside the sample
+            auto qtap = [&](int i) -> float {                      // q of staged frame idx + i, zero padded outside [0, T)
+              float qv = fmaxf(lds32(sb + (uint32_t)(i * V * C::kStPitch)) + bias, 0.f);
+              if (!inner && (unsigned)(tq + i) >= (unsigned)T) qv = 0.f;
+              return qv;
+            };
+            float* op = p.out + o0;
+            float a = qtap(0);
+#pragma unroll
+            for (int fo = 0; fo < C::kFo; ++fo) {
+              const float b = qtap(fo + 1);
+              float y = fmaf(fmaf(f, b, gw * a), scb, shb);
+              if (p.res) y += rv[fo];
+              if (p.relu) y = fmaxf(y, 0.f);
+              if (fo < nfo) {
+                *op = y;
+                op += fstride;
+              }
+              a = b;
+            }
+          }
+          epi_sync();                                              // staging is reused by the next chunk / tile
+        }
+      } else if constexpr (EPI == EPI_LINEAR) {
         // 32 output channels per step through a [128 x 32] staging tile (128-byte rows, 16-byte chunk ^ (row & 7)):
         // piece = thread + 384*i  ->  row = (thread >> 3) + 48*i, chunk = thread & 7
         const int lrow = et >> 3, lc = et & 7;
@@ -708,14 +823,19 @@ static int launch_p(const SgcnRowGemm& p, cudaStream_t s) {
     if (e != cudaSuccess) return set_cuda_error("fused_gemm smem attribute", e);
     mark_configured(configured);
   }
-  const long long ntiles = (p.groups + C::G - 1) / C::G;
+  constexpr bool TV = EPI == EPI_TSHIFT;
+  if (TV && (p.T < 1 || p.groups % p.T != 0 || p.V % V != 0)) return set_error("temporal unit (fused): bad frame / joint geometry");
+  const long long ntiles = TV ? (p.groups / p.T) * ((p.T + C::kFo - 1) / C::kFo) * (p.V / V) : (p.groups + C::G - 1) / C::G;
   if (ntiles == 0) return 0;
   long long grid = tile_ctas();
   if (grid > ntiles) grid = ntiles;
   // tensor maps of the activation inputs (tensormap.h): raw [rows x 64] boxes, or whole operand blocks for PRO_PLAIN
   alignas(64) CUtensorMap tm0, tm1;
   memset(&tm0, 0, sizeof(tm0));
-  if constexpr (PRO != PRO_PLAIN) {
+  if constexpr (TV) {
+    if (int rc = make_frames_map(&tm0, p.in0, p.groups, p.V, K, 64, V, C::G + C::kWin)) return rc;
+    tm1 = tm0;
+  } else if constexpr (PRO != PRO_PLAIN) {
     if (int rc = make_rows_map(&tm0, p.in0, p.groups * V, K, 64, C::kRawRows)) return rc;
     tm1 = tm0;
   } else if constexpr (!P3) {

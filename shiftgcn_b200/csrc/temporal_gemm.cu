@@ -26,6 +26,18 @@ static int temporal_gemm_v(const SgcnRowGemm& p, cudaStream_t s) {
   return set_error("row GEMM: unsupported (in, out) channel pair");
 }
 
+// the whole eval-mode temporal unit in one kernel (EPI_TSHIFT): joint subsets of 5 over 25 consecutive frames
+int temporal_unit_launch(const SgcnRowGemm& p, cudaStream_t s) {
+  using namespace fg;
+  if (p.V != 25) return set_error("fused temporal unit: num_point must be 25");
+  switch (p.K * 1000 + p.N) {
+    case 64064: return launch<PRO_LERP, EPI_TSHIFT, 5, 64, 64>(p, s);
+    case 128128: return launch<PRO_LERP, EPI_TSHIFT, 5, 128, 128>(p, s);
+    case 256256: return launch<PRO_LERP, EPI_TSHIFT, 5, 256, 256>(p, s);
+    default: return set_error("fused temporal unit: unsupported channel count");
+  }
+}
+
 int temporal_gemm_launch(const SgcnRowGemm& p, int lerp, cudaStream_t s) {
   if (p.V == 25) return lerp ? temporal_gemm_v<fg::PRO_LERP, 25>(p, s) : temporal_gemm_v<fg::PRO_PLAIN, 25>(p, s);
   if (p.V == 33) return lerp ? temporal_gemm_v<fg::PRO_LERP, 33>(p, s) : temporal_gemm_v<fg::PRO_PLAIN, 33>(p, s);

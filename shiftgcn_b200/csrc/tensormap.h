@@ -20,6 +20,11 @@ int make_rows_map(CUtensorMap* m, const float* base, long long rows, int pitch, 
 // K-major SWIZZLE_128B layout, i.e. directly as one 32-channel operand block.
 int make_groups_map_sw128(CUtensorMap* m, const float* base, long long groups, long long gs, int V, int pitch, int box_groups);
 
+// 3-D map [frames, joints, pitch] of a row tensor, dense box {box_ch channels, box_v joints, box_frames frames}: the
+// "joints x frames" tiles of the fused temporal unit (a joint subset over consecutive frames of one sample).
+int make_frames_map(CUtensorMap* m, const float* base, long long frames, int V, int pitch, int box_ch, int box_v,
+                    int box_frames);
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(

@@ -266,7 +266,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
         const int rel_lo = (int)(-g0 < -(1 << 20) ? -(1 << 20) : -g0);                     // clamp window of the
         const long long room = p.groups - 1 - g0;                                          // tap frame groups,
         const int rel_hi = (int)(room > (1 << 20) ? (1 << 20) : room);                     // relative to g0
-        constexpr int NBT = G >= 3 ? 1 : 2;                  // 32-channel blocks per batch (loads in flight)
+#ifndef SGCN_WG_NBT3
+#define SGCN_WG_NBT3 1
+#endif
+        constexpr int NBT = G >= 3 ? SGCN_WG_NBT3 : 2;       // 32-channel blocks per batch (loads in flight)
         constexpr int kDeep = 8;                             // |floor(ypos)| < kDeep and >= kDeep frames from both sample ends
         const bool deep = ng == G && t0 >= kDeep && t0 + G + kDeep <= T;   // (warp uniform) no clamps, no zero padding
         if (deep) {
@@ -393,9 +396,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p,
         // the BASE32B swizzle spreads over all 32 banks.
         // ---- A = xm[(g,u), c] = x[g, (u+c) % V, c] * maskmul[u, c]          (model/shift_gcn.py:127-129)
         //      loaded as x[g, sv, c] -> row u = (sv - c) mod V;  a_tab0[sv, c] = maskmul[(sv - c) mod V, c]
-        constexpr int NB0 = G >= 4 ? 1 : (G >= 2 ? 2 : 4);  // 32-channel blocks per batch: ~16 independent loads in flight
+#ifndef SGCN_WG_NB4
+#define SGCN_WG_NB4 1
+#endif
+#ifndef SGCN_WG_NBB4
+#define SGCN_WG_NBB4 1
+#endif
+        constexpr int NB0 = G >= 4 ? SGCN_WG_NB4 : (G >= 2 ? 2 : 4);  // 32-channel blocks per batch: ~16 independent loads in flight
         constexpr int NB = NB0 < (int)ablocks ? NB0 : (int)ablocks;   // (never more blocks than A has: CA = 64 with G = 1)
-        constexpr int NBB = G >= 4 ? 1 : 2;
+        constexpr int NBB = G >= 4 ? SGCN_WG_NBB4 : 2;
         for (uint32_t blk0 = 0; blk0 < ablocks; blk0 += NB) {
           float val[NB][KV][G], mm[NB][KV];
           uint32_t off[NB][KV];

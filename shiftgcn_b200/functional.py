@@ -294,7 +294,7 @@ def side_backward(saved, G, sg, Wd, bd, gamma, ws, accum_into=None):
 
 # ================================================================================================ temporal unit
 def temporal_forward(h, res, relu, bn, ypos_in, Wt, bt, ypos_out, bn2, stride, ws, h_stats_ready, pool=None,
-                     store_out=True):
+                     store_out=True, fuse_eval=False):
     """h: (n,T,V,C) rows -> y: (n,T/stride,V,C) rows = [relu](bn2(Shift_s(relu(conv(Shift_1(bn(h)))))) + res)"""
     n, T, V, C = h.shape
     To = T // stride
@@ -312,6 +312,15 @@ def temporal_forward(h, res, relu, bn, ypos_in, Wt, bt, ypos_out, bn2, stride, w
                                                               n * T * V, moma, bn.eps, tr_a)
     wimg = ops.weight_image(Wt, C, 1, C, C)                        # B[n=co][k=ci] = Wt[co][ci]
     ypos_in_eff = ypos_in.detach().contiguous()
+    if fuse_eval and not tr_a and not tr_b and stride == 1 and V == 25 and pool is None:
+        # inference: the whole unit in ONE kernel (sgcn_rowgemm LERP x TSHIFT) -- q never crosses HBM
+        gb, bb, rmb, rvb, nbtb, momb = _bn_args(bn2)
+        _, _, scale_b, shift_b = ops.bn_fwd_finalize(None, gb, bb, rmb, rvb, nbtb, C, n * To * V, momb, bn2.eps, False)
+        y = torch.empty((n, To, V, C), device=dev, dtype=torch.float32)
+        ops.rowgemm(ops.PRO_LERP, ops.EPI_TSHIFT, in0=h, out=y, wimg=wimg, groups=n * T, V=V, K=C, N=C, T=T,
+                    pro_a=scale_a, pro_b=shift_a, pro_c=ypos_in_eff, bias=bt, res2=ypos_out.detach().contiguous(),
+                    epi_a=scale_b, epi_b=shift_b, res=res, relu=relu)
+        return y, None
     q = torch.empty((n, T, V, C), device=dev, dtype=torch.float32)
     ops.rowgemm(ops.PRO_LERP, ops.EPI_LINEAR, in0=h, out=q, wimg=wimg, groups=n * T, V=V, K=C, N=C, T=T,
                 pro_a=scale_a, pro_b=shift_a, pro_c=ypos_in_eff, bias=bt, relu=1)
@@ -525,8 +534,10 @@ class TemporalFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h, res, ga, ba, xpos_in, ypos_in, Wt, bt, xpos_out, ypos_out, gb, bb, module, relu):
+        need_grad = grad_mode() and any(ctx.needs_input_grad)
         y, saved = temporal_forward(h, res, relu, module.bn, ypos_in, Wt.reshape(Wt.shape[0], Wt.shape[1]), bt,
-                                    ypos_out, module.bn2, module.shift_out.stride, module._ws, False)
+                                    ypos_out, module.bn2, module.shift_out.stride, module._ws, False,
+                                    fuse_eval=not need_grad and module.out_window_ok())
         ctx.module = module
         ctx.has_res = res is not None
         _links(ctx, module, produces_gx=False)
@@ -569,7 +580,8 @@ class UnitFn(torch.autograd.Function):
         pool = getattr(unit, "_pool_sums", None)                   # set by Model._trunk on the last unit only
         y, t_saved = temporal_forward(h, x, 1, tcn.bn, ypos_in, Wt.reshape(C, C), bt, ypos_out, tcn.bn2, 1,
                                       tcn._ws, h_stats_ready=h_stats is not None, pool=pool,
-                                      store_out=need_grad or pool is None)
+                                      store_out=need_grad or pool is None,
+                                      fuse_eval=not need_grad and tcn.out_window_ok())
         if y is None:                                              # pooled-only inference: nothing to return but a handle
             return x.new_empty((0,))
         ctx.unit = unit

@@ -137,6 +137,20 @@ class Shift_tcn(nn.Module):
 
     def reset_xpos_check(self):
         self._xpos_ok = None
+        self._out_win = None
+
+    def out_window_ok(self):
+        """Can the fused inference kernel (LERP x TSHIFT) serve this unit?  It recomputes the conv output for a halo of
+        kWo = 3 frame offsets, so every floor(ypos) of the OUTPUT shift must lie in one window of three values (true at
+        the reference's initialisation, ypos ~ U(-1, 1), and for as long as training leaves the positions near it).
+        One host sync per load_state_dict / reset_xpos_check(), like the xpos check."""
+        gen = (self.shift_in._load_generation, self.shift_out._load_generation)
+        if getattr(self, "_out_win", None) is None or self._out_win[0] != gen:
+            with torch.no_grad():
+                fl = torch.floor(self.shift_out.ypos.detach().float())
+                ok = bool((fl.max() - fl.min()).item() <= 2 and fl.min().item() >= -8 and fl.max().item() < 8)
+            self._out_win = (gen, ok)
+        return self._out_win[1]
 
     def _args(self):
         return (self.bn.weight, self.bn.bias, self.shift_in.xpos, self.shift_in.ypos, self.temporal_linear.weight,

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import SgcnRowGemm, SgcnSideBwd, SgcnSideFold, SgcnStem, SgcnTShift, SgcnTShiftBwd, SgcnTShiftInBwd, SgcnTShiftInSums, SgcnWgrad
 
 PRO_SPATIAL, PRO_LERP, PRO_PLAIN, PRO_DY = 0, 1, 2, 3
-EPI_ROT_RAW, EPI_ROT_FUSED, EPI_LINEAR, EPI_SPATIAL_BWD = 0, 1, 2, 3
+EPI_ROT_RAW, EPI_ROT_FUSED, EPI_LINEAR, EPI_SPATIAL_BWD, EPI_TSHIFT = 0, 1, 2, 3, 4
 WG_SPATIAL, WG_TEMPORAL, WG_PLAIN = 0, 1, 2
 
 
@@ -321,7 +321,7 @@ def rowgemm(pro, epi, *, in0, out, wimg, groups, V, K, N, T=1, in1=None, pro_a=N
                     in1_gs=int(in1_gs), out_gs=int(out_gs), accum=int(accum), prec=_precision)
     if wimg.numel() != (2 if _precision == PREC_FP32 else 1) * K * N:
         raise RuntimeError("rowgemm: the weight image was prepared under a different precision mode")
-    name = "rowgemm[%s/%s]" % (("spatial", "lerp", "plain", "dy")[pro], ("rot_raw", "rot_fused", "linear", "spatial_bwd")[epi])
+    name = "rowgemm[%s/%s]" % (("spatial", "lerp", "plain", "dy")[pro], ("rot_raw", "rot_fused", "linear", "spatial_bwd", "tshift")[epi])
     nbytes = int(groups) * V * 4 * (K + N * (2 if accum else 1)) if pro == PRO_PLAIN else _nbytes(in0, in1, out, res, res2, res2m, xin)
     _launch(name, 1, nbytes, lib.sgcn_rowgemm, ctypes.byref(p), pro, epi, _STREAM)
 

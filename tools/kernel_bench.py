@@ -69,6 +69,7 @@ for C in [int(c) for c in args.layers.split(",")]:
     timeit(lambda: ops.rowgemm(ops.PRO_SPATIAL, ops.EPI_ROT_FUSED, in0=x, out=out, wimg=wimg, groups=R, V=V, K=C, N=C, pro_a=mm, bias=bias, epi_a=A, epi_b=B_, res=x, relu=1), 2 * a, "rowgemm spatial/rot_fused (2a) " + tag)
     timeit(lambda: ops.bn_res_relu_fwd(z, x, out, A, B_, cstats, R * V, V, C), 3 * a, "bn_res_relu_fwd (3a) " + tag)
     timeit(lambda: ops.rowgemm(ops.PRO_LERP, ops.EPI_LINEAR, in0=h, out=out, wimg=wimg, groups=R, V=V, K=C, N=C, T=T, pro_a=sc, pro_b=sh, pro_c=ypos, bias=bias, relu=1), 2 * a, "rowgemm lerp/linear (2a) " + tag)
+    timeit(lambda: ops.rowgemm(ops.PRO_LERP, ops.EPI_TSHIFT, in0=h, out=out, wimg=wimg, groups=R, V=V, K=C, N=C, T=T, pro_a=sc, pro_b=sh, pro_c=ypos, bias=bias, res2=ypos, epi_a=sc, epi_b=sh, res=x, relu=1), 3 * a, "rowgemm lerp/tshift, whole eval temporal unit (3a) " + tag)
     timeit(lambda: ops.tshift_fwd(0, q=h, ypos_eff=ypos, n_samples=n, T_in=T, T_out=T, V=V, C=C, stride=1, stats=cstats), a, "tshift_fwd stats (1a) " + tag)
     timeit(lambda: ops.tshift_fwd(1, q=h, ypos_eff=ypos, n_samples=n, T_in=T, T_out=T, V=V, C=C, stride=1, res=x, out=out, scale=sc, shift=sh, relu=1), 3 * a, "tshift_fwd apply (3a) " + tag)
     common = dict(q=h, gy=gy, y=h, relu=1, ypos_eff=ypos, mean=mean, invstd=inv, n_samples=n, T_in=T, T_out=T, V=V, C=C, stride=1)
