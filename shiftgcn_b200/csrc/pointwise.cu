@@ -171,6 +171,72 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) bn_res_
   if (stats_out) block_reduce_channels<2>(acc, stats_out, k.c, scratch);
 }
 
+// The same op with 128-bit accesses: no shift is involved, so a thread can own FOUR consecutive channels of one joint
+// (float4 column j of the V*D floats of a row group) and stream the groups of its chunk: whole 16-byte requests, a
+// quarter of the load / store instructions.  Block = a divisor of the column count (<= 256); the per-channel statistics of the block are combined
+// in shared memory (fp32 atomics on D*2 words) and published with one fp64 atomic per value and block.
+#ifndef SGCN_BRR_U
+#define SGCN_BRR_U 4
+#endif
+__global__ void __launch_bounds__(256, 4) bn_res_relu_fwd4_kernel(const float4* __restrict__ z, const float4* __restrict__ res,
+                                                                  float4* __restrict__ h, const float4* __restrict__ sc,
+                                                                  const float4* __restrict__ sh, double* __restrict__ stats_out,
+                                                                  long long groups, int gper, int cols, int D, int relu,
+                                                                  int rev) {
+  extern __shared__ float sstat[];                                 // [D][2]
+  const unsigned cblocks = cols / blockDim.x;               // blockDim.x divides cols
+  unsigned b = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int j = (int)((b % cblocks) * blockDim.x + threadIdx.x);            // float4 column inside a row group
+  const long long g0 = (long long)(b / cblocks) * gper;
+  const int ng = (int)((groups - g0) < gper ? (groups - g0) : gper);
+  if (stats_out) {
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sstat[i] = 0.f;
+    __syncthreads();
+  }
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  if (j < cols) {
+    const float4 a = __ldg(sc + j), bb = __ldg(sh + j);
+    const size_t o0 = (size_t)g0 * cols + j;
+    const float4* zp = z + o0;
+    const float4* rp = res ? res + o0 : zp;
+    const float rsel = res ? 1.f : 0.f;
+    float4* hp = h + o0;
+    for (int g = 0; g < ng; g += SGCN_BRR_U) {
+      float4 zv[SGCN_BRR_U], rv[SGCN_BRR_U];
+#pragma unroll
+      for (int u = 0; u < SGCN_BRR_U; ++u) {
+        const size_t o = (size_t)min(g + u, ng - 1) * cols;
+        zv[u] = __ldg(zp + o);
+        rv[u] = __ldg(rp + o);
+      }
+#pragma unroll
+      for (int u = 0; u < SGCN_BRR_U; ++u)
+        if (g + u < ng) {
+          float4 y;
+          y.x = fmaf(rv[u].x, rsel, fmaf(zv[u].x, a.x, bb.x));
+          y.y = fmaf(rv[u].y, rsel, fmaf(zv[u].y, a.y, bb.y));
+          y.z = fmaf(rv[u].z, rsel, fmaf(zv[u].z, a.z, bb.z));
+          y.w = fmaf(rv[u].w, rsel, fmaf(zv[u].w, a.w, bb.w));
+          if (relu) y.x = fmaxf(y.x, 0.f), y.y = fmaxf(y.y, 0.f), y.z = fmaxf(y.z, 0.f), y.w = fmaxf(y.w, 0.f);
+          hp[(size_t)(g + u) * cols] = y;
+          s1.x += y.x, s1.y += y.y, s1.z += y.z, s1.w += y.w;
+          s2.x = fmaf(y.x, y.x, s2.x), s2.y = fmaf(y.y, y.y, s2.y), s2.z = fmaf(y.z, y.z, s2.z), s2.w = fmaf(y.w, y.w, s2.w);
+        }
+    }
+  }
+  if (stats_out) {
+    if (j < cols) {
+      const int d = (j * 4) % D;                                   // first of this thread's four channels
+      atomicAdd(&sstat[2 * d + 0], s1.x), atomicAdd(&sstat[2 * d + 1], s2.x);
+      atomicAdd(&sstat[2 * d + 2], s1.y), atomicAdd(&sstat[2 * d + 3], s2.y);
+      atomicAdd(&sstat[2 * d + 4], s1.z), atomicAdd(&sstat[2 * d + 5], s2.z);
+      atomicAdd(&sstat[2 * d + 6], s1.w), atomicAdd(&sstat[2 * d + 7], s2.w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) atomicAdd(stats_out + i, (double)sstat[i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ temporal shift, forward
 // s(to) = g * Q(to*stride + y1) + f * Q(to*stride + y1 + 1), Q zero padded           (K1 with xpos = 0)
 // MODE 0: stats[c] += {sum s, sum s^2};  MODE 1: out = [relu](s*sc + sh + res), and with a stats pointer the global
@@ -745,6 +811,24 @@ extern "C" int sgcn_bn_res_relu_fwd(const float* z, const float* res, float* h, 
   if (rows <= 0) return 0;
   if (rows % V != 0) return set_error("sgcn_bn_res_relu_fwd: rows must be a multiple of V");
   const long long groups = rows / V;
+#ifndef SGCN_BRR_VEC
+#define SGCN_BRR_VEC 1
+#endif
+  if (SGCN_BRR_VEC) {                                              // 128-bit streaming variant
+    const int cols = V * D / 4;
+    int threads = 256;
+    while (cols % threads) --threads;                              // 200 (V = 25) / 176 (V = 33): every thread has a column
+    const int cblocks = cols / threads;
+    long long nch = ((long long)num_sms() * 16 + cblocks - 1) / cblocks;    // ~4 waves of 4 resident blocks per SM
+    if (nch > groups) nch = groups;
+    const int gper = (int)((groups + nch - 1) / nch);
+    nch = (groups + gper - 1) / gper;
+    const int rev = next_direction();
+    bn_res_relu_fwd4_kernel<<<(unsigned)(nch * cblocks), threads, 2 * D * sizeof(float), (cudaStream_t)stream>>>(
+        (const float4*)z, (const float4*)res, (float4*)h, (const float4*)scale, (const float4*)shift, stats_out, groups, gper,
+        cols, D, relu, rev);
+    return check_launch("bn_res_relu_fwd4_kernel");
+  }
   const Geo g = geometry(D, V, 1, groups, 8);
   const int rev = next_direction();
   SGCN_PITCH_DISPATCH(V * D, (bn_res_relu_fwd_kernel<P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(
