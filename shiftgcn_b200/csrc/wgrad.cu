@@ -88,7 +88,8 @@ template <int MODE, int V, int CA, int CB, bool P3>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const SgcnWgrad p, const WgGeom geo, const int rev) {
   constexpr int G = wg_pick_g(CA, CB, V, P3 ? 2 : 1);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // aligned as an OFFSET from the __shared__ array (a pointer rebuilt from an integer becomes generic: LD/ST instead of LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int KV = (V + 7) / 8;                           // joint slots per builder warp
   constexpr int VP = KV * 8;
