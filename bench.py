@@ -438,6 +438,9 @@ def run_b200(args):
                     "ms_per_launch": t_ms / cnt, "share_of_step_kernel_time": t_ms / max(total_kernel_ms, 1e-9),
                     "algorithmic_bytes_per_launch": by / cnt,
                     "breakdown_ms": {k: round(v[0], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
+                    # the same classes as fractions of the HBM peak on their own algorithmic bytes (0 = no tensor pass)
+                    "breakdown_frac": {k: round(v[2] / max(v[0] * 1e-3, 1e-12) / 1e9 / peak, 3)
+                                       for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
                     "profiled_step_ms": e0.elapsed_time(e1)}
     note("profiling pass done")
     if world > 1:
