@@ -159,6 +159,19 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr bool kTmaOp = PRO == PRO_PLAIN && !P3;                 // operand stages filled by TMA alone
   constexpr bool TV = EPI == EPI_TSHIFT;                           // "joints x frames" tiles (V = joint subset, groups = frames)
+  // Built operands are handed to the tensor core per 32-channel BLOCK (two per chunk, barriers 2*stage + block): the
+  // builders finish block 0 of a chunk, signal it and carry on with block 1 while its MMAs already run, and they wait
+  // for the tensor core per block as well.  With the single operand stage most shapes can afford (shared memory goes
+  // to the raw-input ring) the chunk-granular handshake left the builders idle for a quarter of the kernel (ncu: 26 %
+  // of their samples on the op_free wait) and starved the epilogue behind them.
+  // It costs the builders a second set of per-channel constants per chunk (a warp then works in both blocks), which
+  // only pays where the MMAs of a chunk are long: the temporal GEMMs from 128 channels on (lerp/linear 106 -> 99 us at
+  // C=128, 123 -> 110 us at C=256; at C=64 it lost 18 %, and the spatial / fused-epilogue kernels are epilogue-bound).
+#ifndef SGCN_BLKPIPE
+#define SGCN_BLKPIPE 1
+#endif
+  constexpr bool kBlkPipe = SGCN_BLKPIPE && PRO == PRO_LERP && EPI == EPI_LINEAR && K >= 128;
+  static_assert(!kBlkPipe || 2 * OS <= 4, "block-granular handshake: at most four block stages");
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
@@ -253,12 +266,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
 #pragma unroll 1
         for (int kc = 0; kc < KC; ++kc, ++q) {
           const int s = q % OS;
-          mbar_wait(&op_full[s], (uint32_t)((q / OS) & 1));
-          tc_fence_after();
+          if constexpr (!kBlkPipe) {
+            mbar_wait(&op_full[s], (uint32_t)((q / OS) & 1));
+            tc_fence_after();
+          }
           const uint32_t a_lo = dlo | ((sOp + (uint32_t)s * kOpBytes) >> 4);      // head half of the stage
           const uint32_t a_tail = a_lo + (uint32_t)(kChunkBytes >> 4);                // tail half (P3)
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk) {
+            if constexpr (kBlkPipe) {
+              mbar_wait(&op_full[2 * s + blk], (uint32_t)((q / OS) & 1));
+              tc_fence_after();
+            }
             // weight block (head image; in P3 mode followed by the same block of the tail image)
 #pragma unroll
             for (int part = 0; part < (P3 ? 2 : 1); ++part) {
@@ -286,8 +305,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
               }
               if (!C::kWRes) tc_commit(&w_free[slot]);
             }
+            if constexpr (kBlkPipe) tc_commit(&op_free[2 * s + blk]);
           }
-          tc_commit(&op_free[s]);
+          if constexpr (!kBlkPipe) tc_commit(&op_free[s]);
         }
         tc_commit(&acc_full[buf]);
       }
@@ -421,6 +441,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
       const int lerp_lo = PRO == PRO_LERP ? lerp_lo_s : 0;
       uint32_t opb = sOp + (uint32_t)(lane & 3) * 4u, rawb = sRaw + (uint32_t)lane * 4u, lqs = lq << 4;
       asm volatile("" : "+r"(opb), "+r"(rawb), "+r"(lqs));
+      if constexpr (!kBlkPipe) {
+      // ---- chunk-granular hand-over: unit = 2 * joint + block, a warp stays in block (warp & 1)
       for (int q = 0; q < total_chunks; ++q) {
         const int ti = q / KC, kc = q - ti * KC;
         const long long g0 = TV ? 0 : tile_of(ti) * G;
@@ -538,6 +560,175 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemm_kernel(const SgcnRowGe
         mbar_arrive(&op_full[os]);
         __syncwarp();                                              // every lane of this warp is done with the raw stage
         if (lane == 0) mbar_arrive(&raw_free[q % RS]);
+      }
+      } else {
+      // ---- block-granular hand-over: units are block-major, unit = block * V + joint, dealt round-robin to the 12 warps
+      // (unit k*12 + warp in round k), so a warp's units of block 0 come before its units of block 1 and block 0 is
+      // complete after ~half of the rounds
+      auto unit_of = [&](int k, int& hb, int& u) -> bool {
+        const int i = k * kBldWarps + bw;
+        hb = i >= V ? 1 : 0;
+        u = i - hb * V;
+        return i < 2 * V;
+      };
+      for (int q = 0; q < total_chunks; ++q) {
+        const int ti = q / KC, kc = q - ti * KC;
+        const long long g0 = TV ? 0 : tile_of(ti) * G;
+        const int ng = TV ? G : (int)((p.groups - g0) < G ? (p.groups - g0) : G);
+        // the per-(joint, channel) / per-channel tables of this chunk are requested BEFORE the wait for its raw rows:
+        // loaded right in front of their use, every unit paid a full global-load latency (ncu: 28 % of the builder
+        // warps' stall samples sat on the first multiply of each unit)
+        const int tc0 = kc * 64 + lane;                            // this lane's channel in block 0 (block 1: + 32)
+        float tab[PRO == PRO_SPATIAL ? C::kJ : 6];
+        if constexpr (PRO == PRO_SPATIAL) {
+#pragma unroll
+          for (int k = 0; k < C::kJ; ++k) {
+            int hb, u;
+            unit_of(k, hb, u);
+            tab[k] = __ldg(p.pro_a + min(u, V - 1) * K + tc0 + hb * 32);
+          }
+        } else {
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb)
+            tab[3 * hb] = __ldg(p.pro_c + tc0 + hb * 32), tab[3 * hb + 1] = __ldg(p.pro_a + tc0 + hb * 32),
+                     tab[3 * hb + 2] = __ldg(p.pro_b + tc0 + hb * 32);
+        }
+        mbar_wait_relaxed(&raw_full[q % RS], (uint32_t)((q / RS) & 1));
+        const int os = q % OS;
+        const uint32_t free_par = (uint32_t)(((q / OS) - 1) & 1);
+        const uint32_t raw = rawb + (uint32_t)(q % RS) * C::kRawBytes;
+        const uint32_t ob = opb + (uint32_t)os * kOpBytes;
+
+        // Operand row r = g*V + v (128-byte pitch, 16-byte chunk XOR-ed with (r & 7)), 32-channel block, channel lane:
+        //   address = ob + block*16K + r*128 + (((lane >> 2) ^ r) & 7) * 16 + (lane & 3) * 4
+        // with everything but the swizzle term folded into a per-unit base and a compile-time offset.  Rows of groups
+        // beyond a partial last tile are written too (their operand rows and outputs are never used).
+        auto put = [&](uint32_t base, uint32_t v16, int g, float val) {
+          const uint32_t addr = base + ((lqs ^ (v16 + (uint32_t)(g * V * 16))) & 0x70u) + (uint32_t)(g * V * 128);
+          if constexpr (P3) {
+            float hi, lo;
+            split_tf32(val, hi, lo);
+            sts32(addr, hi);
+            sts32(addr + (uint32_t)kChunkBytes, lo);
+          } else {
+            sts32(addr, tf32_half_ulp(val));
+          }
+        };
+        // Block hand-over.  EVERY builder thread arrives once per block and chunk, and only after it has seen the
+        // tensor core release the block's previous use (an arrival of use n+1 must not be counted into phase n of the
+        // barrier), whether or not this warp has units in the block.
+        int cur = -1;                                              // block this warp is building (warp uniform)
+        auto enter = [&](int hb) {                                 // hb > cur
+          if (cur == 0) fence_proxy_async();
+          if (cur < 0 && hb == 1 && q >= OS) mbar_wait_relaxed(&op_free[2 * os], free_par);   // no unit in block 0
+          if (hb == 1) mbar_arrive(&op_full[2 * os]);
+          if (q >= OS) mbar_wait_relaxed(&op_free[2 * os + hb], free_par);
+          cur = hb;
+        };
+        auto leave = [&]() {
+          if (cur >= 0) fence_proxy_async();
+          if (cur < 1) {                                           // no unit in block 1 (joint-subset tiles), or no unit at all
+            if (cur < 0 && q >= OS) mbar_wait_relaxed(&op_free[2 * os], free_par);
+            mbar_arrive(&op_full[2 * os]);
+            if (q >= OS) mbar_wait_relaxed(&op_free[2 * os + 1], free_par);
+          }
+          mbar_arrive(&op_full[2 * os + 1]);
+        };
+        if constexpr (PRO == PRO_SPATIAL) {
+          // xm[(g,u), c] = x[g, (u+c) % V, c] * maskmul[u, c]
+          int cm = 0;
+          uint32_t rbh = 0, obh = 0;
+          auto set_block = [&](int hb) {
+            enter(hb);
+            cm = (tc0 + hb * 32) % V;
+            rbh = raw + (uint32_t)(hb * 128), obh = ob + (uint32_t)(hb * kBlockBytes);
+          };
+#pragma unroll
+          for (int k = 0; k < C::kJ; ++k) {
+            int hb, u;
+            if (unit_of(k, hb, u)) {
+              if (hb != cur) set_block(hb);
+              int sv = u + cm;
+              if (sv >= V) sv -= V;
+              const float mm = tab[k];
+              const uint32_t rb = rbh + (uint32_t)sv * 256u;
+              float s[G];
+#pragma unroll
+              for (int g = 0; g < G; ++g) s[g] = lds32(rb + (uint32_t)(g * V * 256));
+              const uint32_t b = obh + (uint32_t)u * 128u, u16 = (uint32_t)u << 4;
+#pragma unroll
+              for (int g = 0; g < G; ++g) put(b, u16, g, s[g] * mm);
+            }
+          }
+        } else {
+          // p[(g,v), c] = (1-f) U(t+y1) + f U(t+y1+1),  U = sa*h + sb inside the sample, 0 outside   (K1 with xpos = 0)
+          const int T = p.T;
+          TvTile tvt = {0, 0, 0, 0};
+          if constexpr (TV) tvt = tv_tile(tile_of(ti));
+          // frame of the tile's first group; TV tiles stay inside one sample and may start in front of it (t0 < 0)
+          const int t0 = TV ? tvt.tq0 : (p.groups < (1ll << 31) ? (int)((unsigned)g0 % (unsigned)T) : (int)(g0 % T));
+          const bool interior = ng == G && t0 + lerp_lo >= 0 && t0 + G - 1 + lerp_lo + C::kWin < T && (TV || t0 + G <= T);
+          int c = 0, y1 = 0;
+          float sb = 0.f, f = 0.f, a1 = 0.f, a0 = 0.f;
+          bool inwin = false;
+          uint32_t rbh = 0, obh = 0;
+          auto set_block = [&](int hb) {
+            enter(hb);
+            c = tc0 + hb * 32;
+            const float ypos = hb ? tab[3] : tab[0], sa = hb ? tab[4] : tab[1];
+            sb = hb ? tab[5] : tab[2];
+            const float fl = floorf(ypos);
+            y1 = (int)fl;
+            const int idx = y1 - lerp_lo;
+            f = ypos - fl, a1 = sa * f, a0 = sa - a1;
+            inwin = idx >= 0 && idx < C::kWin;
+            rbh = raw + (uint32_t)(hb * 128 + (inwin ? idx : 0) * (V * 256)), obh = ob + (uint32_t)(hb * kBlockBytes);
+          };
+#pragma unroll
+          for (int k = 0; k < C::kJ; ++k) {
+            int hb, v;
+            if (unit_of(k, hb, v)) {
+              if (hb != cur) set_block(hb);
+              const uint32_t b = obh + (uint32_t)v * 128u, v16 = (uint32_t)v << 4;
+              float s[G + 1];
+              if (inwin) {
+                const uint32_t rb = rbh + (uint32_t)v * 256u;
+#pragma unroll
+                for (int g = 0; g <= G; ++g) s[g] = lds32(rb + (uint32_t)(g * V * 256));
+              } else if constexpr (TV) {                           // ... global taps, frames clamped into the sample
+                const float* col = p.in0 + (((size_t)tvt.n * T) * p.V + tvt.js * V + v) * K + c;
+#pragma unroll
+                for (int g = 0; g <= G; ++g) s[g] = __ldg(col + (size_t)min(max(t0 + g + y1, 0), T - 1) * p.V * K);
+              } else {                                             // shift position outside the staged window: global taps
+                const long long last = p.groups - 1;
+#pragma unroll
+                for (int g = 0; g <= G; ++g) {
+                  long long gi = g0 + g + y1;
+                  gi = gi < 0 ? 0 : (gi > last ? last : gi);
+                  s[g] = __ldg(p.in0 + ((size_t)gi * V + v) * K + c);
+                }
+              }
+              if (interior && inwin) {                             // every tap inside the sample: the affine commutes with the lerp
+#pragma unroll
+                for (int g = 0; g < G; ++g) put(b, v16, g, fmaf(a0, s[g], fmaf(a1, s[g + 1], sb)));
+              } else {
+                const float b1 = sb * f, b0 = sb - b1;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                  int t = t0 + g;                                  // frame of this group (tiles may straddle samples)
+                  if (!TV && t >= T) t -= T;
+                  const float u0 = ((unsigned)(t + y1) < (unsigned)T) ? fmaf(a0, s[g], b0) : 0.f;
+                  const float u1 = ((unsigned)(t + y1 + 1) < (unsigned)T) ? fmaf(a1, s[g + 1], b1) : 0.f;
+                  put(b, v16, g, u0 + u1);
+                }
+              }
+            }
+          }
+        }
+        leave();
+        __syncwarp();                                              // every lane of this warp is done with the raw stage
+        if (lane == 0) mbar_arrive(&raw_free[q % RS]);
+      }
       }
     }
   } else {
