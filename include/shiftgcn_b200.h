@@ -375,8 +375,11 @@ typedef struct SgcnSideBwd {
 int sgcn_side_bwd(const SgcnSideBwd* p, void* stream);
 
 /* out[n, r, c] = g[n, c] * scale for every row r < rows_per_n: the gradient of the global mean over (T, V)
- * (model/shift_gcn.py:212-214) written directly in the row layout */
-int sgcn_bcast_rows(const float* g, float* out, long long n, long long rows_per_n, int C, float scale, void* stream);
+ * (model/shift_gcn.py:212-214) written directly in the row layout.  mask_y (optional, [n, rows_per_n, C]): the pooled rows
+ * themselves, the output of a unit that ends in a ReLU (:162); out is then multiplied by [mask_y > 0], i.e. it is the
+ * gradient in front of that ReLU, and the unit's backward kernels skip their own reads of the mask source. */
+int sgcn_bcast_rows(const float* g, float* out, const float* mask_y, long long n, long long rows_per_n, int C, float scale,
+                    void* stream);
 
 /* stats[c][2] += {sum, sumsq} over rows */
 int sgcn_channel_stats(const float* x, double* stats, long long rows, int C, void* stream);

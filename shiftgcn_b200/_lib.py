@@ -100,7 +100,7 @@ SIGNATURES = {
     "sgcn_tshift_in_bwd_sums": [ctypes.POINTER(SgcnTShiftInSums), _vp],
     "sgcn_shift_pos_finalize": [_vp, _vp, _vp, _vp, _i, _d, _vp],
     "sgcn_relu_bn1d_bwd_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
-    "sgcn_bcast_rows": [_vp, _vp, _ll, _ll, _i, ctypes.c_float, _vp],
+    "sgcn_bcast_rows": [_vp, _vp, _vp, _ll, _ll, _i, ctypes.c_float, _vp],
     "sgcn_channel_stats": [_vp, _vp, _ll, _i, _vp],
     "sgcn_channel_stats_groups": [_vp, _vp, _ll, _i, _i, _i, _vp],
     "sgcn_relu_mask_grad": [_vp, _vp, _vp, _ll, _vp],

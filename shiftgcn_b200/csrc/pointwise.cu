@@ -743,14 +743,21 @@ __global__ void __launch_bounds__(256) relu_mask_grad_kernel(const float4* __res
 
 // out[n, r, c] = g[n, c] * scale for r in [0, rows_per_n): gradient of the global mean pooling (model/shift_gcn.py:212-214)
 // written straight into the row layout (autograd would expand, scale and copy: three passes over a full tensor)
+// mask_y (optional, same shape as out): out *= [mask_y > 0] -- the rows are the output y of a unit that ends in a ReLU, and
+// its backward then finds the gradient already masked (functional._links) instead of reading y in three kernels
 __global__ void __launch_bounds__(256) bcast_rows_kernel(const float4* __restrict__ g, float4* __restrict__ out,
-                                                         long long rows_per_n, int c4, float scale, long long total4) {
+                                                         const float4* __restrict__ mask_y, long long rows_per_n, int c4,
+                                                         float scale, long long total4) {
   const long long per_n = rows_per_n * c4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / per_n;
     const int c = (int)(i % c4);
     float4 v = __ldg(g + n * c4 + c);
     v.x *= scale, v.y *= scale, v.z *= scale, v.w *= scale;
+    if (mask_y) {
+      const float4 y = __ldg(mask_y + i);
+      v.x = y.x > 0.f ? v.x : 0.f, v.y = y.y > 0.f ? v.y : 0.f, v.z = y.z > 0.f ? v.z : 0.f, v.w = y.w > 0.f ? v.w : 0.f;
+    }
     out[i] = v;
   }
 }
@@ -989,8 +996,8 @@ extern "C" int sgcn_relu_bn1d_bwd_stats(const float* g, const float* h, const fl
   return check_launch("relu_bn1d_bwd_stats_kernel");
 }
 
-extern "C" int sgcn_bcast_rows(const float* g, float* out, long long n, long long rows_per_n, int C, float scale,
-                               void* stream) {
+extern "C" int sgcn_bcast_rows(const float* g, float* out, const float* mask_y, long long n, long long rows_per_n, int C,
+                               float scale, void* stream) {
   if (!g || !out) return set_error("sgcn_bcast_rows: null pointer");
   if (C < 4 || C % 4 != 0) return set_error("sgcn_bcast_rows: C must be a positive multiple of 4");
   if (n <= 0 || rows_per_n <= 0) return 0;
@@ -998,8 +1005,8 @@ extern "C" int sgcn_bcast_rows(const float* g, float* out, long long n, long lon
   long long blocks = (total4 + 1023) / 1024;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  bcast_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)g, (float4*)out, rows_per_n, C / 4,
-                                                                       scale, total4);
+  bcast_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)g, (float4*)out, (const float4*)mask_y,
+                                                                       rows_per_n, C / 4, scale, total4);
   return check_launch("bcast_rows_kernel");
 }
 

@@ -703,21 +703,32 @@ class HeadFn(torch.autograd.Function):
     inference) only ties the node into the autograd graph; its gradient comes back in the row layout, written once."""
 
     @staticmethod
-    def forward(ctx, y, W, b, pool_sums, N, M, rows_per_person):
+    def forward(ctx, y, W, b, pool_sums, N, M, rows_per_person, link=None):
         pooled, logits = ops.head_fwd(pool_sums, W.detach().contiguous(), None if b is None else b.detach(), N, M,
                                       rows_per_person * M)
         ctx.dims = (N, M, rows_per_person, tuple(y.shape))
         ctx.has_bias = b is not None
-        ctx.save_for_backward(pooled, W)
+        # link: the out-link of the last unit (functional._links).  y is that unit's ReLU output; masking the broadcast
+        # gradient here costs one read of y, and the unit's backward then skips y in three kernels.
+        ctx.link = link if (PREMASK and link is not None and y.dim() == 4 and y.is_contiguous()) else None
+        if ctx.link is not None:
+            ctx.save_for_backward(pooled, W, y)
+        else:
+            ctx.save_for_backward(pooled, W)
         return logits
 
     @staticmethod
     def backward(ctx, dl):
-        pooled, W = ctx.saved_tensors
+        pooled, W = ctx.saved_tensors[:2]
         N, M, rpp, yshape = ctx.dims
         dW, db, gpool = ops.head_bwd(dl.contiguous().float(), pooled, W.detach().contiguous(), N, M, rpp * M, ctx.has_bias)
-        gy = ops.bcast_rows(gpool, rpp, 1.0).view(yshape) if ctx.needs_input_grad[0] else None
-        return gy, dW, db, None, None, None, None
+        gy = None
+        if ctx.needs_input_grad[0]:
+            mask_y = ctx.saved_tensors[2] if ctx.link is not None else None
+            gy = ops.bcast_rows(gpool, rpp, 1.0, mask_y=mask_y).view(yshape)
+            if ctx.link is not None:
+                ctx.link["masked"] = True
+        return gy, dW, db, None, None, None, None, None
 
 
 class PoolRowsFn(torch.autograd.Function):

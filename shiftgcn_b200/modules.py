@@ -392,13 +392,13 @@ class Model(nn.Module):
         # consecutive units exchange ReLU-masked gradients (functional._links): one dict per unit boundary, attached
         # only for the duration of the unit's forward call so that a unit used on its own never sees a stale link
         ops.restart_traversal()
-        links = [dict(masked=False) for _ in range(9)] if torch.is_grad_enabled() else None
+        links = [dict(masked=False) for _ in range(10)] if torch.is_grad_enabled() else None   # links[9]: l10 -> head
         pool = None
         for i in range(1, 11):
             unit = getattr(self, f"l{i}")
             if links is not None:
                 unit._in_link = links[i - 2] if i >= 2 else None
-                unit._out_link = links[i - 1] if i <= 9 else None
+                unit._out_link = links[i - 1] if (i <= 9 or self._head_fusable(unit, x)) else None
             if i == 10 and self._head_fusable(unit, x):
                 # the kernel that writes l10's output also accumulates the pooled sums of the head (and, in inference,
                 # does not write the output at all)
@@ -416,7 +416,8 @@ class Model(nn.Module):
         if pool is not None:
             rows = x if x.dim() == 1 else x.permute(0, 2, 3, 1)
             T_last, V_last = getattr(self, "_last_tv")
-            return FN.HeadFn.apply(rows, self.fc.weight, self.fc.bias, pool, N, M, T_last * V_last)
+            return FN.HeadFn.apply(rows, self.fc.weight, self.fc.bias, pool, N, M, T_last * V_last,
+                                   links[9] if links is not None else None)
         c_new = x.size(1)
         if x.is_cuda and x.dtype == torch.float32 and c_new % 4 == 0 and x.permute(0, 2, 3, 1).is_contiguous():
             x = FN.PoolRowsFn.apply(x.permute(0, 2, 3, 1))     # same mean; the gradient comes back in the row layout

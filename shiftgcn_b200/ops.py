@@ -598,14 +598,17 @@ def side_bwd(P, sg, Wd, bd, gamma, invstd, mean_r, rows, training, sx=None, XX=N
     return dict(dgamma=vec[0], dbeta=vec[1], dWd=dWd, dbd=vec[2], Wcat=Wcat, kvec=kvec)
 
 
-def bcast_rows(g, rows_per_n, scale):
-    """(n, C) -> (n, rows_per_n, C) with every row = g[n] * scale (gradient of a mean over the rows)"""
+def bcast_rows(g, rows_per_n, scale, mask_y=None):
+    """(n, C) -> (n, rows_per_n, C) with every row = g[n] * scale (gradient of a mean over the rows); mask_y: the pooled
+    rows themselves (a ReLU output): the result is additionally multiplied by [mask_y > 0]"""
     lib = _lib.load()
     n, C = g.shape
     out = torch.empty((n, rows_per_n, C), device=g.device, dtype=torch.float32)
+    if mask_y is not None and (mask_y.numel() != out.numel() or not mask_y.is_contiguous()):
+        raise ValueError("bcast_rows: mask_y must be a contiguous tensor of the output's size")
     if out.numel():
-        _launch("bcast_rows", 1, _nbytes(out), lib.sgcn_bcast_rows, _p(g, name="g"), _p(out), n, int(rows_per_n), C,
-                ctypes.c_float(scale), _STREAM)
+        _launch("bcast_rows", 1, _nbytes(out, mask_y), lib.sgcn_bcast_rows, _p(g, name="g"), _p(out), _p(mask_y), n,
+                int(rows_per_n), C, ctypes.c_float(scale), _STREAM)
     return out
 
 
