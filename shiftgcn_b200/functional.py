@@ -164,8 +164,10 @@ def spatial_backward(saved, gh, W, mask, gamma, vd_sums_ready, ws, unit_res=None
 
 
 # ================================================================================================ first spatial unit
-def stem_forward(x, W, bias, mask, bn, Wd, bd, bn2, ws):
-    """l1.gcn1 = Shift_gcn(3, 64) with its conv + BN `down` branch (model/shift_gcn.py:82-86,121-142); x: (n,T,V,3)."""
+def stem_forward(x, W, bias, mask, bn, Wd, bd, bn2, ws, h_stats=None):
+    """l1.gcn1 = Shift_gcn(3, 64) with its conv + BN `down` branch (model/shift_gcn.py:82-86,121-142); x: (n,T,V,3).
+    h_stats: optional fp64 [64][2] buffer that receives the per-channel sums of h (the statistics the temporal unit's
+    first BatchNorm would otherwise collect with a pass of its own)."""
     n, T, V, C = x.shape
     D = W.shape[1]
     R = n * T
@@ -184,7 +186,7 @@ def stem_forward(x, W, bias, mask, bn, Wd, bd, bn2, ws):
     if tr1 != tr2:                 # the statistics kernel fills both buffers; the frozen BatchNorm does not consume its own
         (s_r if tr1 else s_vd).zero_()
     h = torch.empty((n, T, V, D), device=dev, dtype=torch.float32)
-    ops.stem_fwd(1, sc1=sc1, sh1=sh1, sc2=sc2, sh2=sh2, h=h, **common)
+    ops.stem_fwd(1, sc1=sc1, sh1=sh1, sc2=sc2, sh2=sh2, h=h, stats_h=h_stats, **common)
     saved = dict(x=x, h=h, mm=mm, mean1=mean1, invstd1=invstd1, mean2=mean2, invstd2=invstd2, training1=tr1,
                  training2=tr2)
     return h, saved
@@ -486,7 +488,14 @@ class StemSpatialFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, bias, mask, g1, b1, Wd, bd, g2, b2, module):
-        h, saved = stem_forward(x, W, bias, mask, module.bn, Wd, bd, module.down[1], module._ws)
+        # TCN_GCN_unit.forward names the temporal unit that consumes h (module._h_stats_for, live for this call only):
+        # the kernel that writes h then also sums it for that unit's first BatchNorm
+        tcn = getattr(module, "_h_stats_for", None)
+        h_stats = None
+        if tcn is not None and bn_training(tcn.bn):
+            h_stats = tcn._ws.get("bn_a", 2 * W.shape[1], x.device)
+            tcn._h_stats_ready = True
+        h, saved = stem_forward(x, W, bias, mask, module.bn, Wd, bd, module.down[1], module._ws, h_stats=h_stats)
         ctx.module = module
         _stash(ctx, s=saved, p=dict(W=W, bias=bias, mask=mask, g1=g1, Wd=Wd, bd=bd, g2=g2))
         return h
@@ -535,8 +544,10 @@ class TemporalFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, res, ga, ba, xpos_in, ypos_in, Wt, bt, xpos_out, ypos_out, gb, bb, module, relu):
         need_grad = grad_mode() and any(ctx.needs_input_grad)
+        stats_ready = bool(getattr(module, "_h_stats_ready", False))    # left by the producer of h (StemSpatialFn)
+        module._h_stats_ready = False
         y, saved = temporal_forward(h, res, relu, module.bn, ypos_in, Wt.reshape(Wt.shape[0], Wt.shape[1]), bt,
-                                    ypos_out, module.bn2, module.shift_out.stride, module._ws, False,
+                                    ypos_out, module.bn2, module.shift_out.stride, module._ws, stats_ready,
                                     fuse_eval=not need_grad and module.out_window_ok())
         ctx.module = module
         ctx.has_res = res is not None

@@ -281,7 +281,14 @@ class TCN_GCN_unit(nn.Module):
             y = FN.ConvUnitFn.apply(to_rows(x), *gcn._args(), d[0].weight, d[0].bias, d[1].weight, d[1].bias,
                                     *tcn1._args(), r.conv.weight, r.conv.bias, r.bn.weight, r.bn.bias, self)
             return from_rows(y)
-        h = gcn(x)
+        # first layer: the kernel that writes h also sums it for tcn1's first BatchNorm (FN.StemSpatialFn)
+        hand_over = gcn.stem_supported(x) and self._tcn_fused_for(x) and tcn1.training == self.training
+        gcn._h_stats_for = tcn1 if hand_over else None
+        tcn1._h_stats_ready = False
+        try:
+            h = gcn(x)
+        finally:
+            gcn._h_stats_for = None
         if tcn1.fused_supported(h):
             tcn1._out_link = getattr(self, "_out_link", None)             # see functional._links
             if self._res_mode == "none":
@@ -299,6 +306,10 @@ class TCN_GCN_unit(nn.Module):
                 return from_rows(tcn1.forward_rows(to_rows(h), res, 1))
             finally:
                 tcn1._out_link = None
+                tcn1._h_stats_ready = False
+        if getattr(tcn1, "_h_stats_ready", False):                   # nobody consumed the sums: leave the buffer clean
+            tcn1._ws.get("bn_a", 2 * gcn.out_channels, h.device).zero_()
+            tcn1._h_stats_ready = False
         return self.relu(tcn1(h) + self.residual(x))
 
 
