@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
   const float sc = MODE == 1 ? __ldg(p.scale + k.c) : 0.f, sh = MODE == 1 ? __ldg(p.shift + k.c) : 0.f;
   const int to0 = k.chunk * tper, to1 = min(To, to0 + tper);
   // loads per frame: statistics pass 1 (16 frames in flight), stride-1 apply 2 (8), strided apply 3 (4)
-  constexpr int U = MODE == 0 ? kUnrollMax : (S1 ? kUnrollWide : kUnroll);
+  constexpr int U = MODE == 0 ? (S1 ? kUnrollMax : kUnrollWide) : (S1 ? kUnrollWide : kUnroll);   // strided: 2U taps per batch
   float acc[2] = {0.f, 0.f};
   for (int v = k.warp; v < V; v += k.nw) {
     const float* qb = p.q + ((size_t)k.n * Ti * V + v) * C + k.c;
@@ -262,12 +262,19 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
       float q0[S1 ? 1 : U], q1[U], rv[MODE == 1 ? U : 1];
       if (S1) {
         load_frames<U, PITCH>(q1, qb, to + L.y1 + 1, Ti, pitch);
+      } else if (st == 2) {
+        // stride 2: output frame to + u taps input frames 2(to + u) + y1 and + 1 -- 2U consecutive frames, one base
+        // address and immediate offsets like the stride-1 walk (frames past the chunk are loaded but never used)
+        float qq[2 * U];
+        load_frames<2 * U, PITCH>(qq, qb, 2 * to + L.y1, Ti, pitch);
+#pragma unroll
+        for (int u = 0; u < U; ++u) q0[S1 ? 0 : u] = qq[2 * u], q1[u] = qq[2 * u + 1];
       } else {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int ta = min(to + u, to1 - 1) * st + L.y1;
           q1[u] = tap(qb, ta + 1, Ti, pitch);
-          q0[u] = tap(qb, ta, Ti, pitch);
+          q0[S1 ? 0 : u] = tap(qb, ta, Ti, pitch);
         }
       }
       if (MODE == 1) load_frames<(MODE == 1 ? U : 1), PITCH>(rv, MODE == 1 && p.res ? p.res + ob : qb, to, MODE == 1 && p.res ? To : Ti, pitch);
@@ -322,12 +329,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
       float q0[S1 ? 1 : kUnrollWide], q1[kUnrollWide], gv[kUnrollWide], yv[kUnrollWide];
       if (S1) {
         load_frames<kUnrollWide, PITCH>(q1, qb, to + L.y1 + 1, Ti, pitch);
+      } else if (st == 2) {                                       // 2U consecutive frames (see tshift_fwd_kernel)
+        float qq[2 * kUnrollWide];
+        load_frames<2 * kUnrollWide, PITCH>(qq, qb, 2 * to + L.y1, Ti, pitch);
+#pragma unroll
+        for (int u = 0; u < kUnrollWide; ++u) q0[S1 ? 0 : u] = qq[2 * u], q1[u] = qq[2 * u + 1];
       } else {
 #pragma unroll
         for (int u = 0; u < kUnrollWide; ++u) {
           const int ta = min(to + u, to1 - 1) * st + L.y1;
           q1[u] = tap(qb, ta + 1, Ti, pitch);
-          q0[u] = tap(qb, ta, Ti, pitch);
+          q0[S1 ? 0 : u] = tap(qb, ta, Ti, pitch);
         }
       }
       load_frames<kUnrollWide, PITCH>(gv, p.gy + ob, to, To, pitch);
@@ -436,6 +448,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
 
 // stride 2 (K3): output frame to feeds input frames t = 2*to + y1 (weight g) and t + 1 (weight f); frames that no
 // output frame touches get 0.  Walk over output frames.
+template <bool RELU, int PITCH>
 __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_bwd_apply_s2_kernel(const SgcnTShiftBwd p, int tper,
                                                                             int nchunks, int rev) {
   __shared__ float scratch[kMaxWarps * 32];
@@ -444,7 +457,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
   const int pitch = V * C;
   const LerpCh L = lerp_of(__ldg(p.ypos_eff + k.c));
   const BwdCh B = bwd_of(p, k.c);
-  const int relu = p.relu;
+  const int relu = RELU ? 1 : 0;
   const int to0 = k.chunk * tper, to1 = min(To, to0 + tper);
   float acc[1] = {0.f};
   for (int v = k.warp; v < V; v += k.nw) {
@@ -457,29 +470,33 @@ __global__ void __launch_bounds__(kMaxWarps * 32, SGCN_WALKER_MINBLOCKS) tshift_
     if (k.chunk == nchunks - 1)                           // frames after the last touched one
       for (int t = max(0, 2 * To + L.y1); t < Ti; ++t) db[(size_t)t * pitch] = 0.f;
     for (int to = to0; to < to1; to += kUnroll) {
-      float q0[kUnroll], q1[kUnroll], gv[kUnroll], yv[kUnroll];
+      // output frames to .. to+U-1 tap (and feed) the 2U CONSECUTIVE input frames 2*to + y1 ..: one base address and
+      // immediate offsets for the loads, and for the stores of a batch that lies inside the chunk and the sequence
+      float qq[2 * kUnroll], gv[kUnroll], yv[kUnroll];
+      const int ta0 = 2 * to + L.y1;
+      load_frames<2 * kUnroll, PITCH>(qq, qb, ta0, Ti, pitch);
+      load_frames<kUnroll, PITCH>(gv, p.gy + ob, to, To, pitch);
+      if (RELU) {
+        load_frames<kUnroll, PITCH>(yv, yb, to, To, pitch);
+      } else {
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int tc = min(to + u, to1 - 1);
-        const int ta = tc * 2 + L.y1;
-        q0[u] = tap(qb, ta, Ti, pitch);
-        q1[u] = tap(qb, ta + 1, Ti, pitch);
-        gv[u] = __ldg(p.gy + ob + (size_t)tc * pitch);
-        yv[u] = __ldg(yb + (size_t)tc * pitch);
+        for (int u = 0; u < kUnroll; ++u) yv[u] = 1.f;
       }
+      const bool whole = to + kUnroll <= to1 && ta0 >= 0 && ta0 + 2 * kUnroll <= Ti;
+      float* dq = db + (size_t)ta0 * (size_t)(PITCH ? PITCH : pitch);      // (only dereferenced inside the sequence)
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u)
-        if (to + u < to1) {
-          const int ta = (to + u) * 2 + L.y1;
-          const float ds = ds_eval(true, gv[u], yv[u], relu, q0[u], q1[u], L, B);
-          if ((unsigned)ta < (unsigned)Ti) {
-            const float d = (q0[u] > 0.f) ? L.g * ds : 0.f;
-            db[(size_t)ta * pitch] = d;
+        if (whole || to + u < to1) {
+          const int ta = ta0 + 2 * u;
+          const float ds = ds_eval(true, gv[u], yv[u], relu, qq[2 * u], qq[2 * u + 1], L, B);
+          if (whole || (unsigned)ta < (unsigned)Ti) {
+            const float d = (qq[2 * u] > 0.f) ? L.g * ds : 0.f;
+            dq[(size_t)(2 * u) * (size_t)(PITCH ? PITCH : pitch)] = d;
             acc[0] += d;
           }
-          if ((unsigned)(ta + 1) < (unsigned)Ti) {
-            const float d = (q1[u] > 0.f) ? L.f * ds : 0.f;
-            db[(size_t)(ta + 1) * pitch] = d;
+          if (whole || (unsigned)(ta + 1) < (unsigned)Ti) {
+            const float d = (qq[2 * u + 1] > 0.f) ? L.f * ds : 0.f;
+            dq[(size_t)(2 * u + 1) * (size_t)(PITCH ? PITCH : pitch)] = d;
             acc[0] += d;
           }
         }
@@ -855,7 +872,7 @@ extern "C" int sgcn_tshift_fwd(const SgcnTShift* p, int mode, void* stream) {
     if (p->stride == 1) {
       SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_fwd_kernel<0, true, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
     } else {
-      tshift_fwd_kernel<0, false, 0><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_fwd_kernel<0, false, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
     }
   } else {
     if ((!p->out && !p->stats) || !p->scale || !p->shift) return set_error("sgcn_tshift_fwd(apply): null pointer");
@@ -908,7 +925,11 @@ extern "C" int sgcn_tshift_bwd(const SgcnTShiftBwd* p, int mode, void* stream) {
   if (p->stride == 2) {   // the reference's backward exists for strides 1 and 2 only (shift_cuda_kernel.cu:156-256)
     if (p->T_out <= 0) return set_error("sgcn_tshift_bwd(apply): empty output");
     const Geo g = geometry(p->C, p->V, p->n_samples, p->T_out, 8);
-    tshift_bwd_apply_s2_kernel<<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev);
+    if (p->relu) {
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_apply_s2_kernel<true, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+    } else {
+      SGCN_PITCH_DISPATCH(p->V * p->C, (tshift_bwd_apply_s2_kernel<false, P><<<g.grid, g.threads, 0, (cudaStream_t)stream>>>(*p, g.per, g.nchunks, rev)))
+    }
     return check_launch("tshift_bwd_apply_s2_kernel");
   }
   return set_error("sgcn_tshift_bwd(apply): stride must be 1 or 2 (as in the reference's backward kernels)");
