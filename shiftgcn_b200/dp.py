@@ -204,6 +204,7 @@ class FlatSGDTrainer:
         self._static_x.copy_(x, non_blocking=True)
         self._static_y.copy_(label, non_blocking=True)
         self._graph.replay()
+        ops.params_changed()                                       # the captured step rewrites parameters and BatchNorm buffers
         return self._static_loss
 
 
@@ -277,8 +278,16 @@ class GraphedInference:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self._graph):
+        # The warm-up calls left the parameter-derived tables (weight images, folded BatchNorm tables, ...) in the cache of
+        # ops._frozen_get, so the graph holds only the activation kernels and READS those tables: record them and keep them
+        # alive with the graph.  The weights are frozen as of the capture; after changing them call refresh().
+        with ops.frozen_recording() as rec, torch.no_grad(), torch.cuda.graph(self._graph):
             self._static_out = self._fn(self._static_x)
+        self._tables = rec.tables
+
+    def refresh(self):
+        """re-derive the parameter tables the captured graph reads, in place, from the module's current parameters"""
+        ops.frozen_refresh(self._tables)
 
     def replay(self, x):
         """x: same shape / dtype as the example (device or pinned host tensor); returns the static output tensor"""

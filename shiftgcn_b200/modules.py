@@ -95,7 +95,16 @@ class tcn(nn.Module):
         return self.bn(self.conv(x))
 
 
-class Shift_tcn(nn.Module):
+class _FrozenTables:
+    """nn.Module.train() / .eval() of the drop-in modules invalidate the parameter-derived tables that inference keeps
+    between calls (ops._frozen_get): a mode switch is where weights usually changed hands."""
+
+    def train(self, mode=True):
+        ops.params_changed()
+        return super().train(mode)
+
+
+class Shift_tcn(_FrozenTables, nn.Module):
     """bn -> Shift(stride 1) -> 1x1 conv -> ReLU -> Shift(stride) -> bn2  (reference :48-74)."""
 
     def __init__(self, in_channels, out_channels, kernel_size=9, stride=1):
@@ -172,7 +181,7 @@ class Shift_tcn(nn.Module):
         return self.bn2(x)
 
 
-class Shift_gcn(nn.Module):
+class Shift_gcn(_FrozenTables, nn.Module):
     """Spatial shift graph convolution (reference :77-142): joint-shift gather, tanh mask, C x D contraction,
     joint-shift gather, BatchNorm1d over (v, d), residual (identity or 1x1 conv + BN), ReLU."""
 
@@ -243,7 +252,7 @@ class Shift_gcn(nn.Module):
         return from_rows(self.forward_rows(to_rows(x0), x0))
 
 
-class TCN_GCN_unit(nn.Module):
+class TCN_GCN_unit(_FrozenTables, nn.Module):
     """relu(tcn1(gcn1(x)) + residual(x))  (reference :145-162)."""
 
     def __init__(self, in_channels, out_channels, A, stride=1, residual=True, num_point=25):
@@ -313,7 +322,7 @@ class TCN_GCN_unit(nn.Module):
         return self.relu(tcn1(h) + self.residual(x))
 
 
-class Model(nn.Module):
+class Model(_FrozenTables, nn.Module):
     """data_bn -> 10 TCN_GCN_units (3-64-64-64-64-128-128-128-256-256-256, stride 2 at l5 and l8) -> global mean
     over (T, V) and persons -> fc  (reference :165-216)."""
 

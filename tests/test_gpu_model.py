@@ -138,3 +138,67 @@ def test_pool_rows_matches_autograd_mean(cuda_device):
     b.mean(dim=(1, 2)).backward(go)
     assert torch.allclose(FN.PoolRowsFn.apply(rows), rows.mean(dim=(1, 2)))
     assert a.grad.shape == b.grad.shape and torch.allclose(a.grad, b.grad, rtol=1e-6, atol=1e-9)
+
+
+def test_frozen_tables_follow_the_parameters(cuda_device):
+    """Inference keeps the parameter-derived tables (weight images, folded BatchNorm tables, mask multipliers) between calls
+    (ops._frozen_get).  The second call launches fewer kernels and returns the same logits; an in-place weight update, a
+    load_state_dict, a training step in between and ops.params_changed() after a raw .data edit all show up in the next
+    call; a captured inference graph follows the weights after refresh()."""
+    from shiftgcn_b200 import ops
+    from shiftgcn_b200.dp import GraphedInference
+    mod, ref = _build(60, 25, 2, cuda_device)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 3, 20, 25, 2, generator=g).to(cuda_device)
+    _calibrate(ref, mod, x.cpu())
+    mod.eval()
+
+    def infer(m):
+        with torch.no_grad():
+            return m(x).clone()
+
+    def fresh(m):                                  # the same parameters in a module that has no cached tables
+        ops.params_changed()
+        return infer(m)
+
+    n0 = ops.LAUNCHES
+    a = infer(mod)
+    n1 = ops.LAUNCHES
+    b = infer(mod)
+    n2 = ops.LAUNCHES
+    assert torch.equal(a, b)
+    assert (n2 - n1) < (n1 - n0) - 40, (n1 - n0, n2 - n1)      # the table kernels ran once
+
+    with torch.no_grad():                          # in-place update (what optimizers and load_state_dict do)
+        mod.l3.gcn1.Linear_weight.mul_(1.5)
+        mod.l6.tcn1.bn.running_var.mul_(2.0)
+    c = infer(mod)
+    assert not torch.equal(b, c)
+    assert torch.equal(c, fresh(mod))
+
+    sd = {k: v.clone() for k, v in mod.state_dict().items()}
+    sd["l9.gcn1.Feature_Mask"] = sd["l9.gcn1.Feature_Mask"] + 0.3
+    mod.load_state_dict(sd)
+    d = infer(mod)
+    assert not torch.equal(c, d) and torch.equal(d, fresh(mod))
+
+    mod.l2.tcn1.temporal_linear.weight.data.mul_(0.5)             # raw edit: the version counter does not move
+    ops.params_changed()
+    e = infer(mod)
+    assert not torch.equal(d, e) and torch.equal(e, fresh(mod))
+
+    mod.train()                                    # a training forward rewrites the running statistics through raw pointers
+    with torch.no_grad():
+        mod(x)
+    mod.eval()
+    f = infer(mod)
+    assert not torch.equal(e, f) and torch.equal(f, fresh(mod))
+
+    gi = GraphedInference(mod, x)                  # captured with the tables of the current weights
+    assert torch.equal(gi.replay(x), f)
+    with torch.no_grad():
+        mod.fc.weight.mul_(2.0)                    # fc is a library op inside the graph: follows immediately
+        mod.l4.gcn1.Linear_weight.mul_(0.7)        # a table the graph only reads: needs refresh()
+    gi.refresh()
+    torch.cuda.synchronize()
+    assert torch.allclose(gi.replay(x), fresh(mod), rtol=0, atol=0)
