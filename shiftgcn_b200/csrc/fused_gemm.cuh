@@ -112,7 +112,19 @@ struct Cfg {
   static constexpr int kJ = (kPairs + kBldWarps - 1) / kBldWarps;  // kBldWarps == kEpiWarps
   // flattened 16-byte pieces of a [rows x 64] chunk: piece = thread + 384 * i  ->  row = (thread >> 4) + 24 * i
   static constexpr int kTileRows = G * V;
-  static constexpr int kWin = PRO == PRO_LERP ? (K == 64 ? 3 : 2) : 0;   // distinct floor(ypos) values the raw tile covers
+#ifndef SGCN_LERP_WIN64
+#define SGCN_LERP_WIN64 3
+#endif
+#ifndef SGCN_LERP_WIN128
+#define SGCN_LERP_WIN128 3
+#endif
+#ifndef SGCN_LERP_WIN256
+#define SGCN_LERP_WIN256 3
+#endif
+  // distinct floor(ypos) values the raw tile covers (channels outside take global taps: slow, see the builders)
+  static constexpr int kWin = PRO != PRO_LERP ? 0
+                              : (EPI == EPI_TSHIFT ? (K == 64 ? 3 : 2)
+                                                   : (K == 64 ? (P3 ? 3 : SGCN_LERP_WIN64) : (K == 128 ? SGCN_LERP_WIN128 : SGCN_LERP_WIN256)));
   static constexpr int kRawRows = (G + kWin) * V;
   static constexpr int kRawBytes = PRO == PRO_PLAIN ? 0 : kRawRows * 256;
   // epilogue staging tile.  ROT_*: [128 rows x 64 channels] with a row pitch of 68 floats -- "thread = row" 128-bit
