@@ -7,9 +7,11 @@ timeout 300 python bench.py --workload ntu60-infer --no-cpu-baseline > gpurun_ou
 timeout 300 python bench.py --workload mediapipe-train --no-cpu-baseline > gpurun_out/bench_mp.json 2> gpurun_out/bench_mp.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
 timeout 300 python tools/kernel_bench.py > gpurun_out/kernel_bench.txt 2>&1
+if [ -z "$NO_LISTS" ]; then
 timeout 200 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/b_nograph.json 2>gpurun_out/b_nograph.err && \
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_step.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_step.log 2>&1
+fi
 if [ -n "$INFER_LIST" ]; then
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_infer.csv \
   python bench.py --workload ntu60-infer --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_infer.log 2>&1
