@@ -136,6 +136,21 @@ def test_tcn_gcn_unit_full_length_train(cuda_device, C, D, V, n, T, stride):
     _compare(mod, ref, x, go, True, cuda_device, robust=True)
 
 
+@pytest.mark.parametrize("V,n,T", [(25, 16, 300), (33, 6, 300), (25, 3, 41)])
+def test_first_unit_full_length_train(cuda_device, V, n, T):
+    """l1 (3 -> 64 channels, residual=False): the stem backward streams g and h through a two-stage bulk-copy ring;
+    4800 groups = 6 chunks of 8 groups per block on the full grid (V=33: chunks of 6 with a partial last one)"""
+    from shiftgcn_b200.modules import TCN_GCN_unit
+    torch.manual_seed(1)
+    mod = TCN_GCN_unit(3, 64, None, residual=False, num_point=V)
+    ref = model_ref.RefUnit(3, 64, None, residual=False, num_point=V)
+    fill_pair(mod, ref)
+    g = torch.Generator().manual_seed(34)
+    x = torch.randn(n, 3, T, V, generator=g)
+    go = torch.randn(n, 64, T, V, generator=g)
+    _compare(mod, ref, x, go, True, cuda_device, robust=True)
+
+
 @pytest.mark.parametrize("C,V,n,T,stride", [(64, 25, 8, 300, 1), (128, 25, 8, 300, 2), (256, 25, 16, 75, 1)])
 def test_shift_tcn_full_length_eval(cuda_device, C, V, n, T, stride):
     from shiftgcn_b200.modules import Shift_tcn
