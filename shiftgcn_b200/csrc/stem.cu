@@ -78,11 +78,17 @@ __device__ __forceinline__ Thread<kMaxJ> setup(const SgcnStem& p) {
   return t;
 }
 
-// stage groups [g, g+n) of x into shared memory (coalesced), n <= kGS
-__device__ __forceinline__ void stage_x(const SgcnStem& p, float* sx, long long g, int n) {
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+// all cp.async of this thread, committed or not (cp.async.wait_group alone ignores the copies that were never committed)
+__device__ __forceinline__ void cp_async_drain() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// request groups [g, g+n) of x into shared memory (coalesced 4-byte cp.async: x has no 16-byte alignment per group),
+// n <= kGS; the caller waits with cp_async_drain() + __syncthreads() one chunk later
+__device__ __forceinline__ void prefetch_x(const SgcnStem& p, float* sx, long long g, int n) {
   const int cnt = n * p.V * 3;
   const float* src = p.x + (size_t)g * p.V * 3;
-  for (int i = threadIdx.x; i < cnt; i += blockDim.x) sx[i] = __ldg(src + i);
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) cp_async4(sx + i, src + i);
 }
 
 template <int NV>
@@ -107,7 +113,7 @@ __device__ __forceinline__ void reduce_channels(const float (&v)[NV], double* __
 // ------------------------------------------------------------------------------------------------ forward
 template <int MODE, int kMaxJ>
 __global__ void __launch_bounds__(832, 1) stem_fwd_kernel(const SgcnStem p, int gper, int rev) {
-  __shared__ float sx[kGS * 40 * 3];
+  __shared__ float sxb[2][kGS * 40 * 3];                          // x of this chunk / of the next one (in flight)
   __shared__ float scratch[16 * 2 * D];
   const Thread<kMaxJ> t = setup<kMaxJ>(p);
   const Lay l = layout(p.V);
@@ -129,11 +135,13 @@ __global__ void __launch_bounds__(832, 1) stem_fwd_kernel(const SgcnStem p, int 
     sc2 = __ldg(p.sc2 + t.d);
     sh2 = __ldg(p.sh2 + t.d) + t.bd * sc2;                       // conv bias folded into the BN shift
   }
-  for (int gs = 0; gs < ng; gs += kGS) {
+  prefetch_x(p, sxb[0], g0, min(kGS, ng));
+  for (int gs = 0, ci = 0; gs < ng; gs += kGS, ++ci) {
     const int n = min(kGS, ng - gs);
-    __syncthreads();
-    stage_x(p, sx, g0 + gs, n);
-    __syncthreads();
+    const float* sx = sxb[ci & 1];
+    cp_async_drain();
+    __syncthreads();                                               // this chunk's x has landed, the other buffer is free
+    if (gs + kGS < ng) prefetch_x(p, sxb[(ci & 1) ^ 1], g0 + gs + kGS, min(kGS, ng - gs - kGS));
 #pragma unroll
     for (int j = 0; j < kMaxJ; ++j)
       if (j < t.nj) {
@@ -196,9 +204,6 @@ __device__ __forceinline__ void issue_chunk(const SgcnStem& p, float* stage, int
   mbar_expect_tx(bar, 2u * bytes);
   bulk_load(smem_u32(stage), p.g + (size_t)g * p.V * D, bytes, bar);
   bulk_load(smem_u32(stage + half), p.h + (size_t)g * p.V * D, bytes, bar);
-}
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 constexpr int kRedPitch = 65, kRedFloats = 40 * 3 * kRedPitch + 8;   // mask-gradient staging (V <= 39), conflict-free pitch
 constexpr int kSxFloats = 624;     // kgb * V * 3 <= 609 for every V <= 39 (host: chunk_groups)
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(832, 1) stem_bwd_stats_kernel(const SgcnStem p
           acc[1] = fmaf(gm, (r - m2) * i2, acc[1]);
         }
       }
-    cp_async_wait_all();
+    cp_async_drain();
     __syncthreads();                                               // stage s and sx[s] are free, sx[s^1] is written
     if (tid == 0 && ci + 2 < nchunks)
       issue_chunk(p, dyn + (size_t)s * 2 * half, half, &full[s], g0 + gs + 2 * kgb, min(kgb, ng - gs - 2 * kgb));
@@ -478,7 +483,7 @@ __global__ void __launch_bounds__(832, 1) stem_bwd_apply_kernel(const SgcnStem p
         }
       }
     }
-    cp_async_wait_all();
+    cp_async_drain();
     fence_proxy_async();                                           // this thread's dz / dr stores before the next bulk copy
     __syncthreads();                                               // phase B is done with stage s
     if (tid == 0 && ci + 2 < nchunks)
