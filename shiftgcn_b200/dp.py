@@ -270,13 +270,23 @@ class GraphedInference:
         self.module = module.eval()
         self._fn = fn if fn is not None else (lambda x: self.module(x))
         self._static_x = example.clone()
+        self._warmup = max(warmup, 1)
+        self._capture()
+
+    def _decisions(self):
+        """host-side kernel choices that depend on parameter VALUES and are baked into a captured graph: whether a
+        temporal unit's output shift positions fit the one-kernel inference path (Shift_tcn.out_window_ok)"""
+        return tuple(m.out_window_ok() for m in self.module.modules() if hasattr(m, "out_window_ok"))
+
+    def _capture(self):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(max(warmup, 1)):
+            for _ in range(self._warmup):
                 self._fn(self._static_x)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self._choices = self._decisions()
         self._graph = torch.cuda.CUDAGraph()
         # The warm-up calls left the parameter-derived tables (weight images, folded BatchNorm tables, ...) in the cache of
         # ops._frozen_get, so the graph holds only the activation kernels and READS those tables: record them and keep them
@@ -286,7 +296,12 @@ class GraphedInference:
         self._tables = rec.tables
 
     def refresh(self):
-        """re-derive the parameter tables the captured graph reads, in place, from the module's current parameters"""
+        """re-derive the parameter tables the captured graph reads, in place, from the module's current parameters; if the
+        new parameters change a kernel choice the graph has baked in (shift positions that left the window of the
+        one-kernel temporal unit), the graph is captured again (``replay`` then returns a NEW static output tensor)"""
+        if self._decisions() != self._choices:
+            self._capture()
+            return
         ops.frozen_refresh(self._tables)
 
     def replay(self, x):

@@ -152,8 +152,12 @@ class Shift_tcn(_FrozenTables, nn.Module):
         """Can the fused inference kernel (LERP x TSHIFT) serve this unit?  It recomputes the conv output for a halo of
         kWo = 3 frame offsets, so every floor(ypos) of the OUTPUT shift must lie in one window of three values (true at
         the reference's initialisation, ypos ~ U(-1, 1), and for as long as training leaves the positions near it).
-        One host sync per load_state_dict / reset_xpos_check(), like the xpos check."""
-        gen = (self.shift_in._load_generation, self.shift_out._load_generation)
+        Training MOVES the positions (K5: +-0.01 * lr per step, four floor values after 25 steps in some units), so the
+        answer is re-derived (one host sync) whenever ypos may have changed: another storage or tensor version (in-place
+        optimizer updates, load_state_dict) or another parameter epoch (raw-pointer writers such as sgcn_sgd_epilogue,
+        Module.train() / .eval(), ops.params_changed())."""
+        yp = self.shift_out.ypos
+        gen = (self.shift_in._load_generation, self.shift_out._load_generation, ops.param_epoch(), yp.data_ptr(), yp._version)
         if getattr(self, "_out_win", None) is None or self._out_win[0] != gen:
             with torch.no_grad():
                 fl = torch.floor(self.shift_out.ypos.detach().float())

@@ -245,6 +245,11 @@ _param_epoch = 0
 _frozen = {}
 
 
+def param_epoch():
+    """current parameter epoch (cache keys of parameter-derived decisions outside this module)"""
+    return _param_epoch
+
+
 def params_changed():
     """invalidate every cached parameter-derived table (see above)"""
     global _param_epoch

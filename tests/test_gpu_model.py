@@ -202,3 +202,42 @@ def test_frozen_tables_follow_the_parameters(cuda_device):
     gi.refresh()
     torch.cuda.synchronize()
     assert torch.allclose(gi.replay(x), fresh(mod), rtol=0, atol=0)
+
+
+def test_eval_unit_follows_shift_positions_that_leave_the_window(cuda_device):
+    """The one-kernel inference temporal unit serves output shift positions within three floor values; training moves the
+    positions (K5), so the choice is re-derived when ypos changes: eager calls switch to the two-kernel path at the next
+    call, a captured inference graph is captured again by refresh()."""
+    from shiftgcn_b200.dp import GraphedInference
+    from shiftgcn_b200.modules import TCN_GCN_unit
+    torch.manual_seed(1)
+    mod = TCN_GCN_unit(64, 64, None, num_point=25)
+    ref = model_ref.RefUnit(64, 64, None, num_point=25)
+    fill_pair(mod, ref)
+    g = torch.Generator().manual_seed(41)
+    yp = torch.rand(64, generator=g) * 1.9 - 0.95                  # the reference's initialisation range: U(-1, 1)
+    with torch.no_grad():
+        mod.tcn1.shift_out.ypos.copy_(yp)
+        ref.tcn1.shift_out.ypos.copy_(yp)
+    mod, ref = mod.to(cuda_device).eval(), ref.double().eval()
+    x = torch.randn(2, 64, 40, 25, generator=g)
+    xd = x.to(cuda_device)
+
+    def both():
+        with torch.no_grad():
+            return mod(xd).clone(), ref(x.double())
+
+    assert mod.tcn1.out_window_ok()
+    a, want = both()
+    assert rel_err(a, want) < 1e-2
+    gi = GraphedInference(mod, xd)
+    assert torch.equal(gi.replay(xd), a)
+    with torch.no_grad():                                          # in-place, like an optimizer step: four floor values now
+        mod.tcn1.shift_out.ypos[::4] += 2.7
+        ref.tcn1.shift_out.ypos[::4] += 2.7
+    assert not mod.tcn1.out_window_ok()
+    b, want = both()
+    assert rel_err(b, want) < 1e-2 and not torch.equal(a, b)
+    gi.refresh()
+    torch.cuda.synchronize()
+    assert torch.equal(gi.replay(xd), b)

@@ -132,3 +132,26 @@ def test_graph_adjacency_equals_live_reference():
     for mine, ref in ((ntu, ns.graph_ntu), (mp, ns.graph_mediapipe)):
         a, b = mine.Graph("spatial"), ref.Graph("spatial")
         assert np.array_equal(a.A, b.A) and a.num_node == b.num_node and sorted(a.inward) == sorted(b.inward)
+
+
+def test_output_window_choice_follows_the_shift_positions():
+    """host logic of Shift_tcn.out_window_ok (which inference kernel serves the unit): re-derived after an in-place
+    update of ypos (optimizer step), after a raw .data edit + ops.params_changed(), and after load_state_dict"""
+    from shiftgcn_b200 import ops
+    from shiftgcn_b200.modules import Shift_tcn
+    torch.manual_seed(3)
+    m = Shift_tcn(64, 64)
+    assert m.out_window_ok()                              # U(-1, 1): two floor values
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        m.shift_out.ypos[::4] += 2.7                      # four floor values
+    assert not m.out_window_ok()
+    m.load_state_dict(sd)
+    assert m.out_window_ok()
+    m.shift_out.ypos.data[0] = 5.3                        # raw edit: the version counter of the parameter does not move
+    ops.params_changed()
+    assert not m.out_window_ok()
+    with torch.no_grad():
+        m.shift_out.ypos[0] = 0.3
+        m.shift_out.ypos[1] = 9.5                         # outside the clamp range of the kernel's window base
+    assert not m.out_window_ok()
